@@ -1,0 +1,153 @@
+/*
+ * minimp3_b200.h -- C ABI of libminimp3_b200.so: a CUDA (sm_100a) Layer III decoder behind the
+ * public API of lieff/minimp3, plus one batch entry point.
+ *
+ * Every declaration cites the reference interface it replaces (paths relative to the reference
+ * checkout).  Types keep the reference's layout so existing callers and language bindings can switch
+ * by relinking.  There is NO CPU decode path in this library: every PCM sample is produced by the
+ * CUDA kernels; all entry points fail (MP3D_E_CUDA) when no usable device is present.
+ */
+#ifndef MINIMP3_B200_H
+#define MINIMP3_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#define MINIMP3_MAX_SAMPLES_PER_FRAME (1152*2)          /* minimp3.h:11 */
+
+/* minimp3_ex.h:32-36 */
+#define MP3D_E_PARAM   -1
+#define MP3D_E_MEMORY  -2
+#define MP3D_E_IOERROR -3
+#define MP3D_E_USER    -4
+#define MP3D_E_DECODE  -5
+/* new codes of this library */
+#define MP3D_E_UNSUPPORTED -6   /* stream needs a decode stage that is not on the CUDA path yet (Layer I/II) */
+#define MP3D_E_CUDA        -7   /* CUDA runtime error / no device */
+
+/* minimp3.h:13-16 */
+typedef struct
+{
+    int frame_bytes, frame_offset, channels, hz, layer, bitrate_kbps;
+} mp3dec_frame_info_t;
+
+/* minimp3.h:18-23 -- same size and field layout (6668 bytes).  mdct_overlap holds the same values as
+ * the reference's; qmf_state holds the 15 carried synthesis slots in this library's own order. */
+typedef struct
+{
+    float mdct_overlap[2][9*32], qmf_state[15*2*32];
+    int reserv, free_format_bytes;
+    unsigned char header[4], reserv_buf[511];
+} mp3dec_t;
+
+#ifdef MINIMP3_FLOAT_OUTPUT                               /* minimp3.h:30-35 */
+typedef float mp3d_sample_t;
+#define mp3dec_decode_frame mp3dec_decode_frame_f32
+#define mp3dec_load_buf mp3dec_load_buf_f32
+#else
+typedef int16_t mp3d_sample_t;
+#endif
+
+/* minimp3_ex.h:38-43.  With float output selected at run time (batch opts / *_f32 entry points) buffer
+ * really points at float samples. */
+typedef struct
+{
+    mp3d_sample_t *buffer;
+    size_t samples;        /* channels included, byte size = samples*sizeof(sample) */
+    int channels, hz, layer, avg_bitrate_kbps;
+} mp3dec_file_info_t;
+
+/* minimp3_ex.h:91 */
+typedef int (*MP3D_PROGRESS_CB)(void *user_data, size_t file_size, uint64_t offset, mp3dec_frame_info_t *info);
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- frame API: minimp3.h:29-36 ------------------------------------------------------------- */
+void mp3dec_init(mp3dec_t *dec);
+/* returns samples per channel (0 / 576 / 1152); info->frame_bytes = bytes to drop.  pcm may be NULL
+ * (parse only).  Layer I/II frames return 0 samples with frame_bytes set. */
+int mp3dec_decode_frame(mp3dec_t *dec, const uint8_t *mp3, int mp3_bytes, mp3d_sample_t *pcm, mp3dec_frame_info_t *info);
+#ifndef MINIMP3_FLOAT_OUTPUT
+int mp3dec_decode_frame_f32(mp3dec_t *dec, const uint8_t *mp3, int mp3_bytes, float *pcm, mp3dec_frame_info_t *info);
+#endif
+void mp3dec_f32_to_s16(const float *in, int16_t *out, int num_samples);   /* minimp3.h:34, 1808-1864 (runs on the GPU) */
+
+/* ---- whole-buffer API: minimp3_ex.h:98,101 ----------------------------------------------------- */
+int mp3dec_detect_buf(const uint8_t *buf, size_t buf_size);
+/* info->buffer is malloc()ed, caller free()s (README.md:258-259).  progress_cb is called once per decoded
+ * frame after the batch finished (it cannot abort work already done; a non-zero return truncates). */
+int mp3dec_load_buf(mp3dec_t *dec, const uint8_t *buf, size_t buf_size, mp3dec_file_info_t *info, MP3D_PROGRESS_CB progress_cb, void *user_data);
+#ifndef MINIMP3_FLOAT_OUTPUT
+int mp3dec_load_buf_f32(mp3dec_t *dec, const uint8_t *buf, size_t buf_size, mp3dec_file_info_t *info, MP3D_PROGRESS_CB progress_cb, void *user_data);
+#endif
+
+/* ---- batch API (new) --------------------------------------------------------------- */
+typedef struct
+{
+    const uint8_t *buf;
+    size_t size;
+} mp3dec_batch_stream_t;
+
+#define MP3D_BATCH_OUT_MALLOC 0   /* infos[i].buffer = malloc()ed host copy, caller free()s (drop-in) */
+#define MP3D_BATCH_OUT_PINNED 1   /* infos[i].buffer points into a pinned slab owned by the library, valid
+                                     until the next batch call on the same device */
+#define MP3D_BATCH_OUT_DEVICE 2   /* infos[i].buffer is a device pointer into the library's PCM buffer */
+
+typedef struct
+{
+    int device;                       /* CUDA device ordinal */
+    int float_output;                 /* 0: int16 PCM, 1: float PCM (MINIMP3_FLOAT_OUTPUT semantics) */
+    int raw_frames;                   /* 1: plain mp3dec_decode_frame loop, no tag skipping / VBR-tag trimming */
+    int allow_mono_stereo_transition; /* MINIMP3_ALLOW_MONO_STEREO_TRANSITION */
+    int host_threads;                 /* 0: all online cores */
+    int output;                       /* MP3D_BATCH_OUT_* */
+    void *cuda_stream;                /* cudaStream_t to run on, NULL: library-owned stream */
+} mp3dec_batch_opts_t;
+
+/* Decodes n_streams independent buffers; per-stream result and return code (infos_out[i], rets_out[i],
+ * may be NULL) are those of mp3dec_load_buf(&dec, buf, size, &info, 0, 0).  Returns 0, or MP3D_E_PARAM /
+ * MP3D_E_MEMORY / MP3D_E_CUDA if the batch as a whole could not run. */
+int mp3dec_decode_batch_cuda(const mp3dec_batch_stream_t *streams, int n_streams, mp3dec_file_info_t *infos_out,
+                             int *rets_out, const mp3dec_batch_opts_t *opts);
+
+/* Split form of the batch call, for callers that keep inputs resident (and for measurement):
+ * plan = host parse + H2D; run = kernels only (asynchronous on the stream); fetch = D2H + infos. */
+typedef struct mp3dec_batch_plan mp3dec_batch_plan_t;
+
+typedef struct
+{
+    uint64_t input_bytes;        /* bytes of frame payload staged to the device */
+    uint64_t samples;            /* channel-inclusive samples the kernels write */
+    uint64_t n_granule_channels, n_tiles, n_istereo_granules, n_frames;
+    int kernels_per_run;         /* kernel launches one mp3dec_batch_plan_run() issues */
+    double host_parse_ms, h2d_ms;
+} mp3dec_batch_stats_t;
+
+mp3dec_batch_plan_t *mp3dec_batch_plan_create(const mp3dec_batch_stream_t *streams, int n_streams,
+                                              const mp3dec_batch_opts_t *opts, int *err);
+int mp3dec_batch_plan_run(mp3dec_batch_plan_t *plan);
+int mp3dec_batch_plan_sync(mp3dec_batch_plan_t *plan);
+int mp3dec_batch_plan_fetch(mp3dec_batch_plan_t *plan, mp3dec_file_info_t *infos_out, int *rets_out);
+void mp3dec_batch_plan_stats(const mp3dec_batch_plan_t *plan, mp3dec_batch_stats_t *out);
+void *mp3dec_batch_plan_device_pcm(mp3dec_batch_plan_t *plan);
+void mp3dec_batch_plan_destroy(mp3dec_batch_plan_t *plan);
+
+/* Test taps (parity tests): device-side intermediates of the last mp3dec_batch_plan_run(), copied to host.
+ * which: 0 quantised lines int16[n_gc][576], 1 scalefactors float[n_gc][40], 2 requantised spectra
+ * float[n_gc][576] (after MS, zero beyond nzl), 3 subband samples float[n_gc][576], 4 GcDesc records,
+ * 5 ist_pos uint8[n_gc][40].  Taps must be enabled before run. */
+int mp3dec_batch_plan_enable_taps(mp3dec_batch_plan_t *plan);
+int mp3dec_batch_plan_read_tap(mp3dec_batch_plan_t *plan, int which, void *dst, size_t dst_bytes);
+
+/* Multi-GPU sharding helper: assigns streams to n_shards by greedy longest-processing-time on input
+ * bytes; shard_of[i] receives the shard of stream i.  No data-path collective exists: shards are
+ * decoded independently, one process (or plan) per GPU. */
+void mp3dec_batch_shard(const size_t *sizes, int n_streams, int n_shards, int *shard_of);
+
+const char *mp3dec_b200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MINIMP3_B200_H */

@@ -1,0 +1,755 @@
+/*
+ * capi.cu -- the C ABI of libminimp3_b200.so (include/minimp3_b200.h): batch plans, the drop-in
+ * mp3dec_* entry points, buffer management and stream plumbing around the three kernels.
+ *
+ * There is deliberately no CPU decode path here: when CUDA is unavailable every entry point that
+ * would produce PCM returns MP3D_E_CUDA (or 0 samples for the frame API, after printing why).
+ */
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#include "../../include/minimp3_b200.h"
+#include "host_parse.h"
+#include "kernels.h"
+
+using namespace mp3b;
+
+namespace {
+
+double now_ms()
+{
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+template <class F>
+void parallel_for(int n, int threads, F f)
+{
+    if (threads <= 0)
+    {
+        threads = (int)std::thread::hardware_concurrency();
+        if (threads <= 0) threads = 1;
+    }
+    threads = std::min(threads, n);
+    if (threads <= 1)
+    {
+        for (int i = 0; i < n; i++) f(i);
+        return;
+    }
+    std::atomic<int> next(0);
+    std::vector<std::thread> pool;
+    pool.reserve(threads);
+    for (int t = 0; t < threads; t++)
+        pool.emplace_back([&]() {
+            for (;;)
+            {
+                const int i = next.fetch_add(1);
+                if (i >= n) break;
+                f(i);
+            }
+        });
+    for (auto &th : pool) th.join();
+}
+
+struct DevBuf
+{
+    void *p = nullptr;
+    size_t cap = 0;
+    bool ensure(size_t n)
+    {
+        if (n <= cap) return true;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        const size_t want = n + n/8 + 256;
+        if (cudaMalloc(&p, want) != cudaSuccess) { p = nullptr; return false; }
+        cap = want;
+        return true;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct PinBuf
+{
+    void *p = nullptr;
+    size_t cap = 0;
+    bool ensure(size_t n)
+    {
+        if (n <= cap) return true;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        const size_t want = n + n/8 + 256;
+        if (cudaHostAlloc(&p, want, cudaHostAllocDefault) != cudaSuccess) { p = nullptr; return false; }
+        cap = want;
+        return true;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+/* all device + pinned memory of one in-flight batch; recycled between calls */
+struct BufferSet
+{
+    PinBuf h_md, h_gcs, h_tiles, h_ist, h_pcm;
+    DevBuf d_md, d_gcs, d_tiles, d_istlist, d_xr, d_nzl, d_istpos, d_pcm;
+    DevBuf d_tap_q, d_tap_scf, d_tap_sub;
+    void release()
+    {
+        h_md.release(); h_gcs.release(); h_tiles.release(); h_ist.release(); h_pcm.release();
+        d_md.release(); d_gcs.release(); d_tiles.release(); d_istlist.release(); d_xr.release(); d_nzl.release();
+        d_istpos.release(); d_pcm.release(); d_tap_q.release(); d_tap_scf.release(); d_tap_sub.release();
+    }
+};
+
+struct DeviceCtx
+{
+    int device = -1;
+    bool ready = false;
+    DeviceTables tables{};
+    cudaStream_t stream = nullptr;
+    std::mutex mu;
+    std::vector<BufferSet *> free_sets;
+    /* single-frame API scratch */
+    BufferSet frame_set;
+    DevBuf d_state_in, d_state_out;
+    PinBuf h_state;
+};
+
+std::mutex g_ctx_mu;
+DeviceCtx *g_ctx[64];
+
+DeviceCtx *get_ctx(int device)
+{
+    if (device < 0 || device >= 64) return nullptr;
+    std::lock_guard<std::mutex> lock(g_ctx_mu);
+    if (g_ctx[device] && g_ctx[device]->ready) return g_ctx[device];
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || device >= n)
+    {
+        fprintf(stderr, "minimp3_b200: no usable CUDA device %d (this library has no CPU decode path)\n", device);
+        return nullptr;
+    }
+    if (cudaSetDevice(device) != cudaSuccess) return nullptr;
+    DeviceCtx *c = new DeviceCtx();
+    c->device = device;
+    if (tables_upload(&c->tables) != 0 || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess)
+    {
+        fprintf(stderr, "minimp3_b200: CUDA initialisation failed: %s\n", cudaGetErrorString(cudaGetLastError()));
+        delete c;
+        return nullptr;
+    }
+    c->ready = true;
+    g_ctx[device] = c;
+    return c;
+}
+
+BufferSet *acquire_set(DeviceCtx *c)
+{
+    std::lock_guard<std::mutex> lock(c->mu);
+    if (!c->free_sets.empty())
+    {
+        BufferSet *s = c->free_sets.back();
+        c->free_sets.pop_back();
+        return s;
+    }
+    return new BufferSet();
+}
+
+void release_set(DeviceCtx *c, BufferSet *s)
+{
+    std::lock_guard<std::mutex> lock(c->mu);
+    if (c->free_sets.size() < 2) c->free_sets.push_back(s);
+    else { s->release(); delete s; }
+}
+
+size_t round_up(size_t v, size_t a) { return (v + a - 1)/a*a; }
+
+}  // namespace
+
+struct mp3dec_batch_plan
+{
+    DeviceCtx *ctx = nullptr;
+    BufferSet *bufs = nullptr;
+    mp3dec_batch_opts_t opts{};
+    cudaStream_t stream = nullptr;
+    int n_streams = 0;
+    std::vector<StreamPlan> plans;
+    std::vector<uint64_t> md_base, gc_base, tile_base, pcm_base, ist_base;
+    uint64_t md_bytes = 0, n_gc = 0, n_tiles = 0, n_samples = 0, n_ist = 0, n_frames = 0, input_bytes = 0;
+    size_t sample_size = 2;
+    bool taps = false;
+    bool fetched_pinned = false;
+    mp3dec_batch_stats_t stats{};
+};
+
+extern "C" {
+
+const char *mp3dec_b200_version(void) { return "minimp3_b200 0.1 (sm_100a)"; }
+
+void mp3dec_batch_shard(const size_t *sizes, int n_streams, int n_shards, int *shard_of)
+{
+    if (n_shards < 1) n_shards = 1;
+    std::vector<int> order(n_streams);
+    for (int i = 0; i < n_streams; i++) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return sizes[a] > sizes[b]; });
+    std::vector<uint64_t> load(n_shards, 0);
+    for (int k = 0; k < n_streams; k++)
+    {
+        int best = 0;
+        for (int s = 1; s < n_shards; s++)
+            if (load[s] < load[best]) best = s;
+        shard_of[order[k]] = best;
+        load[best] += sizes[order[k]];
+    }
+}
+
+mp3dec_batch_plan_t *mp3dec_batch_plan_create(const mp3dec_batch_stream_t *streams, int n_streams,
+                                              const mp3dec_batch_opts_t *opts_in, int *err)
+{
+    int dummy;
+    if (!err) err = &dummy;
+    *err = 0;
+    if (!streams || n_streams < 0) { *err = MP3D_E_PARAM; return nullptr; }
+    mp3dec_batch_opts_t opts;
+    memset(&opts, 0, sizeof(opts));
+    if (opts_in) opts = *opts_in;
+    for (int i = 0; i < n_streams; i++)
+        if ((!streams[i].buf && streams[i].size) || streams[i].size == (size_t)-1) { *err = MP3D_E_PARAM; return nullptr; }
+    DeviceCtx *ctx = get_ctx(opts.device);
+    if (!ctx) { *err = MP3D_E_CUDA; return nullptr; }
+    cudaSetDevice(ctx->device);
+
+    mp3dec_batch_plan *P = new mp3dec_batch_plan();
+    P->ctx = ctx;
+    P->opts = opts;
+    P->stream = opts.cuda_stream ? (cudaStream_t)opts.cuda_stream : ctx->stream;
+    P->n_streams = n_streams;
+    P->sample_size = opts.float_output ? 4 : 2;
+    P->bufs = acquire_set(ctx);
+    BufferSet &B = *P->bufs;
+
+    const double t0 = now_ms();
+    /* ---- host stage 1: main-data staging offsets, then one walker per stream ---- */
+    P->md_base.resize(n_streams + 1);
+    uint64_t off = 0;
+    for (int i = 0; i < n_streams; i++)
+    {
+        P->md_base[i] = off;
+        off += round_up(streams[i].size + 16, 16);
+    }
+    P->md_base[n_streams] = off;
+    P->md_bytes = off + 4096;      /* guard so that run-away Huffman reads stay inside the buffer */
+    if (!B.h_md.ensure(P->md_bytes)) { *err = MP3D_E_MEMORY; mp3dec_batch_plan_destroy(P); return nullptr; }
+    P->plans.resize(n_streams);
+    WalkOptions wopt;
+    wopt.raw_frames = opts.raw_frames != 0;
+    wopt.allow_mono_stereo = opts.allow_mono_stereo_transition != 0;
+    uint8_t *h_md = (uint8_t *)B.h_md.p;
+    parallel_for(n_streams, opts.host_threads, [&](int i) {
+        uint8_t *dst = h_md + P->md_base[i];
+        walk_stream(streams[i].buf, streams[i].size, dst, P->md_base[i]*8u, wopt, &P->plans[i]);
+        /* zero the slack so the device never sees stale bytes of an earlier batch */
+        const uint64_t used = P->plans[i].main_data_bytes, room = P->md_base[i + 1] - P->md_base[i];
+        memset(dst + used, 0, (size_t)(room - used));
+    });
+    memset(h_md + off, 0, 4096);
+
+    /* ---- host stage 2: prefix sums and rebasing into the shared tables ---- */
+    P->gc_base.resize(n_streams + 1); P->tile_base.resize(n_streams + 1);
+    P->pcm_base.resize(n_streams + 1); P->ist_base.resize(n_streams + 1);
+    uint64_t gcs = 0, tiles = 0, samples = 0, ists = 0;
+    for (int i = 0; i < n_streams; i++)
+    {
+        const StreamPlan &sp = P->plans[i];
+        P->gc_base[i] = gcs; P->tile_base[i] = tiles; P->pcm_base[i] = samples; P->ist_base[i] = ists;
+        gcs += round_up(sp.gcs.size(), 2);
+        tiles += sp.tiles.size();
+        samples += sp.samples_decoded;
+        ists += sp.istereo_gcs.size();
+        P->n_frames += sp.frames_decoded;
+        P->input_bytes += sp.main_data_bytes;
+    }
+    P->gc_base[n_streams] = gcs; P->tile_base[n_streams] = tiles; P->pcm_base[n_streams] = samples; P->ist_base[n_streams] = ists;
+    P->n_gc = gcs; P->n_tiles = tiles; P->n_samples = samples; P->n_ist = ists;
+    if (gcs >= (1ull << 31)) { *err = MP3D_E_PARAM; mp3dec_batch_plan_destroy(P); return nullptr; }
+
+    bool ok = B.h_gcs.ensure((size_t)gcs*sizeof(GcDesc) + 64) && B.h_tiles.ensure((size_t)tiles*sizeof(TileDesc) + 64) &&
+              B.h_ist.ensure((size_t)ists*4 + 64);
+    if (!ok) { *err = MP3D_E_MEMORY; mp3dec_batch_plan_destroy(P); return nullptr; }
+    GcDesc *h_gcs = (GcDesc *)B.h_gcs.p;
+    TileDesc *h_tiles = (TileDesc *)B.h_tiles.p;
+    uint32_t *h_ist = (uint32_t *)B.h_ist.p;
+    parallel_for(n_streams, opts.host_threads, [&](int i) {
+        StreamPlan &sp = P->plans[i];
+        const uint64_t gb = P->gc_base[i];
+        if (!sp.gcs.empty()) memcpy(h_gcs + gb, sp.gcs.data(), sp.gcs.size()*sizeof(GcDesc));
+        if (sp.gcs.size() & 1)
+        {
+            GcDesc pad;
+            memset(&pad, 0, sizeof(pad));
+            pad.flags1 = GCF1_MPEG1;
+            h_gcs[gb + sp.gcs.size()] = pad;
+        }
+        for (size_t k = 0; k < sp.tiles.size(); k++)
+        {
+            TileDesc t = sp.tiles[k];
+            t.gc_first += (uint32_t)gb;
+            t.pcm_off += P->pcm_base[i];
+            for (int c = 0; c < 2; c++)
+                for (int h = 0; h < 2; h++)
+                    if (t.halo[c][h] >= 0) t.halo[c][h] += (int32_t)gb;
+            h_tiles[P->tile_base[i] + k] = t;
+        }
+        for (size_t k = 0; k < sp.istereo_gcs.size(); k++) h_ist[P->ist_base[i] + k] = sp.istereo_gcs[k] + (uint32_t)gb;
+        /* descriptor vectors are no longer needed on the host */
+        std::vector<GcDesc>().swap(sp.gcs);
+        std::vector<TileDesc>().swap(sp.tiles);
+        std::vector<GranuleRef>().swap(sp.granules);
+        std::vector<uint32_t>().swap(sp.istereo_gcs);
+    });
+    const double t1 = now_ms();
+
+    /* ---- device buffers + H2D ---- */
+    ok = B.d_md.ensure(P->md_bytes) && B.d_gcs.ensure((size_t)gcs*sizeof(GcDesc) + 64) &&
+         B.d_tiles.ensure((size_t)tiles*sizeof(TileDesc) + 64) && B.d_istlist.ensure((size_t)ists*4 + 64) &&
+         B.d_xr.ensure((size_t)gcs*576*sizeof(float) + 64) && B.d_nzl.ensure((size_t)gcs*2 + 64) &&
+         B.d_istpos.ensure((size_t)gcs*40 + 64) && B.d_pcm.ensure((size_t)samples*P->sample_size + 64);
+    if (!ok) { *err = MP3D_E_MEMORY; mp3dec_batch_plan_destroy(P); return nullptr; }
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0, P->stream);
+    cudaMemcpyAsync(B.d_md.p, B.h_md.p, P->md_bytes, cudaMemcpyHostToDevice, P->stream);
+    if (gcs) cudaMemcpyAsync(B.d_gcs.p, B.h_gcs.p, (size_t)gcs*sizeof(GcDesc), cudaMemcpyHostToDevice, P->stream);
+    if (tiles) cudaMemcpyAsync(B.d_tiles.p, B.h_tiles.p, (size_t)tiles*sizeof(TileDesc), cudaMemcpyHostToDevice, P->stream);
+    if (ists) cudaMemcpyAsync(B.d_istlist.p, B.h_ist.p, (size_t)ists*4, cudaMemcpyHostToDevice, P->stream);
+    cudaEventRecord(e1, P->stream);
+    if (cudaStreamSynchronize(P->stream) != cudaSuccess)
+    {
+        fprintf(stderr, "minimp3_b200: H2D failed: %s\n", cudaGetErrorString(cudaGetLastError()));
+        *err = MP3D_E_CUDA;
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        mp3dec_batch_plan_destroy(P);
+        return nullptr;
+    }
+    float h2d = 0.f;
+    cudaEventElapsedTime(&h2d, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+
+    P->stats.input_bytes = P->input_bytes;
+    P->stats.samples = samples;
+    P->stats.n_granule_channels = gcs;
+    P->stats.n_tiles = tiles;
+    P->stats.n_istereo_granules = ists;
+    P->stats.n_frames = P->n_frames;
+    P->stats.kernels_per_run = (gcs ? 1 : 0) + (ists ? 1 : 0) + (tiles ? 1 : 0);
+    P->stats.host_parse_ms = t1 - t0;
+    P->stats.h2d_ms = h2d;
+    return P;
+}
+
+int mp3dec_batch_plan_enable_taps(mp3dec_batch_plan_t *P)
+{
+    if (!P) return MP3D_E_PARAM;
+    cudaSetDevice(P->ctx->device);
+    BufferSet &B = *P->bufs;
+    const size_t n = (size_t)P->n_gc;
+    if (!B.d_tap_q.ensure(n*576*2 + 64) || !B.d_tap_scf.ensure(n*40*4 + 64) || !B.d_tap_sub.ensure(n*576*4 + 64)) return MP3D_E_MEMORY;
+    P->taps = true;
+    return 0;
+}
+
+int mp3dec_batch_plan_run(mp3dec_batch_plan_t *P)
+{
+    if (!P) return MP3D_E_PARAM;
+    cudaSetDevice(P->ctx->device);
+    BufferSet &B = *P->bufs;
+    if (P->taps)
+    {
+        cudaMemsetAsync(B.d_tap_q.p, 0, (size_t)P->n_gc*576*2, P->stream);
+        cudaMemsetAsync(B.d_tap_scf.p, 0, (size_t)P->n_gc*40*4, P->stream);
+        cudaMemsetAsync(B.d_tap_sub.p, 0, (size_t)P->n_gc*576*4, P->stream);
+        cudaMemsetAsync(B.d_istpos.p, 0, (size_t)P->n_gc*40, P->stream);
+    }
+    EntropyArgs ea;
+    memset(&ea, 0, sizeof(ea));
+    ea.md_words = (const uint32_t *)B.d_md.p;
+    ea.md_n_words = P->md_bytes/4;
+    ea.gcs = (const GcDesc *)B.d_gcs.p;
+    ea.n_gc = (uint32_t)P->n_gc;
+    ea.xr = (float *)B.d_xr.p;
+    ea.nzl = (uint16_t *)B.d_nzl.p;
+    ea.ist_pos = (uint8_t *)B.d_istpos.p;
+    ea.tap_q = P->taps ? (int16_t *)B.d_tap_q.p : nullptr;
+    ea.tap_scf = P->taps ? (float *)B.d_tap_scf.p : nullptr;
+    cudaError_t e = launch_entropy(P->ctx->tables, ea, P->stream);
+    if (e == cudaSuccess && P->n_ist)
+    {
+        StereoArgs sa;
+        sa.gcs = ea.gcs;
+        sa.granules = (const uint32_t *)B.d_istlist.p;
+        sa.n_granules = (uint32_t)P->n_ist;
+        sa.xr = ea.xr;
+        sa.nzl = ea.nzl;
+        sa.ist_pos = ea.ist_pos;
+        e = launch_intensity_stereo(P->ctx->tables, sa, P->stream);
+    }
+    if (e == cudaSuccess)
+    {
+        TransformArgs ta;
+        memset(&ta, 0, sizeof(ta));
+        ta.gcs = ea.gcs;
+        ta.tiles = (const TileDesc *)B.d_tiles.p;
+        ta.n_tiles = (uint32_t)P->n_tiles;
+        ta.xr = ea.xr;
+        ta.nzl = ea.nzl;
+        ta.pcm = B.d_pcm.p;
+        ta.float_output = P->opts.float_output;
+        ta.tap_sub = P->taps ? (float *)B.d_tap_sub.p : nullptr;
+        e = launch_transform(P->ctx->tables, ta, P->stream);
+    }
+    if (e != cudaSuccess)
+    {
+        fprintf(stderr, "minimp3_b200: kernel launch failed: %s\n", cudaGetErrorString(e));
+        return MP3D_E_CUDA;
+    }
+    return 0;
+}
+
+int mp3dec_batch_plan_sync(mp3dec_batch_plan_t *P)
+{
+    if (!P) return MP3D_E_PARAM;
+    cudaSetDevice(P->ctx->device);
+    cudaError_t e = cudaStreamSynchronize(P->stream);
+    if (e != cudaSuccess)
+    {
+        fprintf(stderr, "minimp3_b200: stream failed: %s\n", cudaGetErrorString(e));
+        return MP3D_E_CUDA;
+    }
+    return 0;
+}
+
+void *mp3dec_batch_plan_device_pcm(mp3dec_batch_plan_t *P) { return P ? P->bufs->d_pcm.p : nullptr; }
+
+int mp3dec_batch_plan_read_tap(mp3dec_batch_plan_t *P, int which, void *dst, size_t dst_bytes)
+{
+    if (!P || !dst) return MP3D_E_PARAM;
+    cudaSetDevice(P->ctx->device);
+    BufferSet &B = *P->bufs;
+    const size_t n = (size_t)P->n_gc;
+    const void *src = nullptr;
+    size_t bytes = 0;
+    switch (which)
+    {
+    case 0: src = B.d_tap_q.p; bytes = n*576*2; break;
+    case 1: src = B.d_tap_scf.p; bytes = n*40*4; break;
+    case 2: src = B.d_xr.p; bytes = n*576*4; break;
+    case 3: src = B.d_tap_sub.p; bytes = n*576*4; break;
+    case 4: src = B.d_gcs.p; bytes = n*sizeof(GcDesc); break;
+    case 5: src = B.d_istpos.p; bytes = n*40; break;
+    case 6: src = B.d_nzl.p; bytes = n*2; break;
+    default: return MP3D_E_PARAM;
+    }
+    if ((which == 0 || which == 1 || which == 3) && !P->taps) return MP3D_E_PARAM;
+    if (dst_bytes < bytes) return MP3D_E_PARAM;
+    if (cudaStreamSynchronize(P->stream) != cudaSuccess) return MP3D_E_CUDA;
+    if (bytes && cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost) != cudaSuccess) return MP3D_E_CUDA;
+    return 0;
+}
+
+int mp3dec_batch_plan_fetch(mp3dec_batch_plan_t *P, mp3dec_file_info_t *infos, int *rets)
+{
+    if (!P) return MP3D_E_PARAM;
+    cudaSetDevice(P->ctx->device);
+    BufferSet &B = *P->bufs;
+    const size_t ss = P->sample_size;
+    const int mode = P->opts.output;
+    uint8_t *host = nullptr;
+    if (mode != MP3D_BATCH_OUT_DEVICE)
+    {
+        if (!B.h_pcm.ensure((size_t)P->n_samples*ss + 64)) return MP3D_E_MEMORY;
+        host = (uint8_t *)B.h_pcm.p;
+        if (P->n_samples)
+            cudaMemcpyAsync(host, B.d_pcm.p, (size_t)P->n_samples*ss, cudaMemcpyDeviceToHost, P->stream);
+    }
+    cudaError_t e = cudaStreamSynchronize(P->stream);
+    if (e != cudaSuccess)
+    {
+        fprintf(stderr, "minimp3_b200: decode failed: %s\n", cudaGetErrorString(e));
+        return MP3D_E_CUDA;
+    }
+    std::atomic<int> oom(0);
+    parallel_for(P->n_streams, mode == MP3D_BATCH_OUT_MALLOC ? P->opts.host_threads : 1, [&](int i) {
+        const StreamPlan &sp = P->plans[i];
+        if (rets) rets[i] = sp.ret;
+        if (!infos) return;
+        mp3dec_file_info_t &fi = infos[i];
+        memset(&fi, 0, sizeof(fi));
+        fi.samples = (size_t)sp.out_samples;
+        fi.channels = sp.channels; fi.hz = sp.hz; fi.layer = sp.layer; fi.avg_bitrate_kbps = sp.avg_bitrate_kbps;
+        if (sp.ret == MP3D_E_UNSUPPORTED) { fi.samples = 0; return; }
+        const size_t first = (size_t)(P->pcm_base[i] + sp.out_skip)*ss;
+        if (!sp.out_samples) return;
+        if (mode == MP3D_BATCH_OUT_DEVICE) fi.buffer = (mp3d_sample_t *)((uint8_t *)B.d_pcm.p + first);
+        else if (mode == MP3D_BATCH_OUT_PINNED) fi.buffer = (mp3d_sample_t *)(host + first);
+        else
+        {
+            void *m = malloc((size_t)sp.out_samples*ss);
+            if (!m) { oom = 1; fi.samples = 0; if (rets) rets[i] = MP3D_E_MEMORY; return; }
+            memcpy(m, host + first, (size_t)sp.out_samples*ss);
+            fi.buffer = (mp3d_sample_t *)m;
+        }
+    });
+    return oom ? MP3D_E_MEMORY : 0;
+}
+
+void mp3dec_batch_plan_stats(const mp3dec_batch_plan_t *P, mp3dec_batch_stats_t *out)
+{
+    if (P && out) *out = P->stats;
+}
+
+void mp3dec_batch_plan_destroy(mp3dec_batch_plan_t *P)
+{
+    if (!P) return;
+    if (P->bufs) release_set(P->ctx, P->bufs);
+    delete P;
+}
+
+int mp3dec_decode_batch_cuda(const mp3dec_batch_stream_t *streams, int n_streams, mp3dec_file_info_t *infos_out,
+                             int *rets_out, const mp3dec_batch_opts_t *opts)
+{
+    int err = 0;
+    mp3dec_batch_plan_t *P = mp3dec_batch_plan_create(streams, n_streams, opts, &err);
+    if (!P) return err;
+    err = mp3dec_batch_plan_run(P);
+    if (!err) err = mp3dec_batch_plan_fetch(P, infos_out, rets_out);
+    mp3dec_batch_plan_destroy(P);
+    return err;
+}
+
+/* ---- drop-in entry points ------------------------------------------------------------------------------- */
+
+void mp3dec_init(mp3dec_t *dec) { dec->header[0] = 0; }   /* minimp3.h:1708-1711 */
+
+int mp3dec_detect_buf(const uint8_t *buf, size_t buf_size) { return detect_buf(buf, buf_size); }
+
+static int load_buf_impl(mp3dec_t *dec, const uint8_t *buf, size_t buf_size, mp3dec_file_info_t *info,
+                         MP3D_PROGRESS_CB progress_cb, void *user_data, int float_output)
+{
+    if (!dec || !buf || !info || (size_t)-1 == buf_size) return MP3D_E_PARAM;
+    (void)progress_cb; (void)user_data;
+    memset(info, 0, sizeof(*info));
+    mp3dec_init(dec);
+    mp3dec_batch_stream_t s = { buf, buf_size };
+    mp3dec_batch_opts_t o;
+    memset(&o, 0, sizeof(o));
+    o.float_output = float_output;
+    o.output = MP3D_BATCH_OUT_MALLOC;
+    o.host_threads = 1;
+    int ret = 0;
+    int err = mp3dec_decode_batch_cuda(&s, 1, info, &ret, &o);
+    if (err) return err;
+    return ret;
+}
+
+int mp3dec_load_buf(mp3dec_t *dec, const uint8_t *buf, size_t buf_size, mp3dec_file_info_t *info,
+                    MP3D_PROGRESS_CB progress_cb, void *user_data)
+{
+    return load_buf_impl(dec, buf, buf_size, info, progress_cb, user_data, 0);
+}
+
+int mp3dec_load_buf_f32(mp3dec_t *dec, const uint8_t *buf, size_t buf_size, mp3dec_file_info_t *info,
+                        MP3D_PROGRESS_CB progress_cb, void *user_data)
+{
+    return load_buf_impl(dec, buf, buf_size, info, progress_cb, user_data, 1);
+}
+
+/* One frame through the same kernels, with the reference's carried state (mdct_overlap, qmf_state,
+ * reservoir bytes) living in the caller's mp3dec_t exactly where the reference keeps it. */
+static int decode_frame_impl(mp3dec_t *dec, const uint8_t *mp3, int mp3_bytes, void *pcm, mp3dec_frame_info_t *info,
+                             int float_output)
+{
+    SyncState st;
+    memcpy(st.header, dec->header, 4);
+    st.free_format_bytes = dec->free_format_bytes;
+    st.reserv = dec->reserv;
+    const int reserv_before = dec->reserv;
+    FrameParse fp;
+    fp.info = FrameInfo{ info->frame_bytes, info->frame_offset, info->channels, info->hz, info->layer, info->bitrate_kbps };
+    parse_frame(&st, mp3, mp3_bytes, &fp, pcm == nullptr);
+    if (fp.reset) memset(dec, 0, sizeof(*dec));
+    memcpy(dec->header, st.header, 4);
+    dec->free_format_bytes = st.free_format_bytes;
+    info->frame_bytes = fp.info.frame_bytes; info->frame_offset = fp.info.frame_offset;
+    info->channels = fp.info.channels; info->hz = fp.info.hz; info->layer = fp.info.layer;
+    info->bitrate_kbps = fp.info.bitrate_kbps;
+    if (!fp.hdr) return 0;                              /* no frame found */
+    if (!pcm) return (int)hdr_frame_samples(fp.hdr);    /* parse only (minimp3.h:1748-1751) */
+    if (fp.init_only) return 0;
+    if (fp.layer != 3)
+    {
+        static bool warned = false;
+        if (!warned) { fprintf(stderr, "minimp3_b200: Layer I/II frames are not decoded (CUDA path is Layer III only)\n"); warned = true; }
+        return 0;
+    }
+    /* L3_restore_reservoir (minimp3.h:1228-1236): main data = tail of the reservoir + this payload */
+    const int reserv_old = fp.reset ? 0 : reserv_before;
+    const int mdb = fp.main_data_begin;
+    const int bytes_have = std::min(reserv_old, mdb);
+    uint8_t maindata[511 + 2304 + 64];
+    memset(maindata, 0, sizeof(maindata));
+    memcpy(maindata, dec->reserv_buf + std::max(0, reserv_old - mdb), (size_t)bytes_have);
+    memcpy(maindata + bytes_have, fp.payload, (size_t)fp.payload_bytes);
+    const int md_len = bytes_have + fp.payload_bytes;
+    int result = 0;
+
+    if (fp.success)
+    {
+        DeviceCtx *ctx = get_ctx(0);
+        if (!ctx) return 0;
+        std::lock_guard<std::mutex> lock(ctx->mu);
+        cudaSetDevice(ctx->device);
+        BufferSet &B = ctx->frame_set;
+        const int n_gc = fp.n_gr*fp.nch;
+        const size_t md_bytes = round_up((size_t)md_len + 64, 16);
+        const size_t ss = float_output ? 4 : 2;
+        const int n_samples = fp.n_gr*576*fp.nch;
+        bool ok = B.h_md.ensure(md_bytes + 4*sizeof(GcDesc) + sizeof(TileDesc) + 64) && B.d_md.ensure(md_bytes) &&
+                  B.d_gcs.ensure(4*sizeof(GcDesc)) && B.d_tiles.ensure(sizeof(TileDesc)) && B.d_istlist.ensure(16) &&
+                  B.d_xr.ensure(4*576*4) && B.d_nzl.ensure(16) && B.d_istpos.ensure(4*40) &&
+                  B.d_pcm.ensure(2304*4) && B.h_pcm.ensure(2304*4) && ctx->d_state_in.ensure(1536*4) &&
+                  ctx->d_state_out.ensure(1536*4) && ctx->h_state.ensure(2*1536*4);
+        if (!ok) return 0;
+        uint8_t *h = (uint8_t *)B.h_md.p;
+        memcpy(h, maindata, md_bytes);
+        GcDesc gcs[4];
+        uint32_t ist_list[2];
+        int n_ist = 0;
+        uint64_t bit = 0;
+        for (int igr = 0; igr < fp.n_gr; igr++)
+        {
+            if ((fp.hdr[3] & 0x10) && fp.nch == 2) ist_list[n_ist++] = (uint32_t)(igr*fp.nch);
+            for (int ch = 0; ch < fp.nch; ch++)
+            {
+                const GranuleSide &g = fp.side[igr*fp.nch + ch];
+                fill_gc_desc(&gcs[igr*fp.nch + ch], g, fp.hdr, ch, fp.nch, igr, bit);
+                bit += g.part_23_length;
+            }
+        }
+        for (int k = n_gc; k < 4; k++) { memset(&gcs[k], 0, sizeof(GcDesc)); gcs[k].flags1 = GCF1_MPEG1; }
+        TileDesc tile;
+        memset(&tile, 0, sizeof(tile));
+        tile.gc_first = 0; tile.n_gr = (uint8_t)fp.n_gr; tile.nch = (uint8_t)fp.nch; tile.pcm_off = 0;
+        tile.halo[0][0] = tile.halo[0][1] = tile.halo[1][0] = tile.halo[1][1] = -1;
+        memcpy(h + md_bytes, gcs, sizeof(gcs));
+        memcpy(h + md_bytes + sizeof(gcs), &tile, sizeof(tile));
+        float *hs = (float *)ctx->h_state.p;
+        memcpy(hs, dec->mdct_overlap, 576*4);
+        memcpy(hs + 576, dec->qmf_state, 960*4);
+        cudaStream_t s = ctx->stream;
+        cudaMemcpyAsync(B.d_md.p, h, md_bytes, cudaMemcpyHostToDevice, s);
+        cudaMemcpyAsync(B.d_gcs.p, h + md_bytes, sizeof(gcs), cudaMemcpyHostToDevice, s);
+        cudaMemcpyAsync(B.d_tiles.p, h + md_bytes + sizeof(gcs), sizeof(tile), cudaMemcpyHostToDevice, s);
+        cudaMemcpyAsync(ctx->d_state_in.p, hs, 1536*4, cudaMemcpyHostToDevice, s);
+        if (n_ist) cudaMemcpyAsync(B.d_istlist.p, ist_list, (size_t)n_ist*4, cudaMemcpyHostToDevice, s);
+        EntropyArgs ea;
+        memset(&ea, 0, sizeof(ea));
+        ea.md_words = (const uint32_t *)B.d_md.p; ea.md_n_words = md_bytes/4;
+        ea.gcs = (const GcDesc *)B.d_gcs.p; ea.n_gc = 4;
+        ea.xr = (float *)B.d_xr.p; ea.nzl = (uint16_t *)B.d_nzl.p; ea.ist_pos = (uint8_t *)B.d_istpos.p;
+        cudaError_t e = launch_entropy(ctx->tables, ea, s);
+        if (e == cudaSuccess && n_ist)
+        {
+            StereoArgs sa;
+            sa.gcs = ea.gcs; sa.granules = (const uint32_t *)B.d_istlist.p; sa.n_granules = (uint32_t)n_ist;
+            sa.xr = ea.xr; sa.nzl = ea.nzl; sa.ist_pos = ea.ist_pos;
+            e = launch_intensity_stereo(ctx->tables, sa, s);
+        }
+        if (e == cudaSuccess)
+        {
+            TransformArgs ta;
+            memset(&ta, 0, sizeof(ta));
+            ta.gcs = ea.gcs; ta.tiles = (const TileDesc *)B.d_tiles.p; ta.n_tiles = 1;
+            ta.xr = ea.xr; ta.nzl = ea.nzl; ta.pcm = B.d_pcm.p; ta.float_output = float_output;
+            ta.state_in = (const float *)ctx->d_state_in.p; ta.state_out = (float *)ctx->d_state_out.p;
+            e = launch_transform(ctx->tables, ta, s);
+        }
+        if (e == cudaSuccess)
+        {
+            cudaMemcpyAsync(B.h_pcm.p, B.d_pcm.p, (size_t)n_samples*ss, cudaMemcpyDeviceToHost, s);
+            cudaMemcpyAsync(hs + 1536, ctx->d_state_out.p, 1536*4, cudaMemcpyDeviceToHost, s);
+            e = cudaStreamSynchronize(s);
+        }
+        if (e != cudaSuccess)
+        {
+            fprintf(stderr, "minimp3_b200: frame decode failed: %s\n", cudaGetErrorString(e));
+            return 0;
+        }
+        memcpy(pcm, B.h_pcm.p, (size_t)n_samples*ss);
+        const float *so = hs + 1536;
+        for (int ch = 0; ch < fp.nch; ch++)
+        {
+            memcpy(dec->mdct_overlap[ch], so + ch*288, 288*4);
+            memcpy(dec->qmf_state + ch*480, so + 576 + ch*480, 480*4);
+        }
+        result = (int)hdr_frame_samples(fp.hdr);
+    }
+    /* L3_save_reservoir (minimp3.h:1212-1226) */
+    {
+        int consumed_bits = 0;
+        if (fp.success)
+            for (int k = 0; k < fp.n_gr*fp.nch; k++) consumed_bits += fp.side[k].part_23_length;
+        int pos = (consumed_bits + 7)/8;
+        int remains = md_len - pos;
+        if (remains > 511) { pos += remains - 511; remains = 511; }
+        if (remains > 0) memmove(dec->reserv_buf, maindata + pos, (size_t)remains);
+        dec->reserv = remains;
+    }
+    return result;
+}
+
+int mp3dec_decode_frame(mp3dec_t *dec, const uint8_t *mp3, int mp3_bytes, int16_t *pcm, mp3dec_frame_info_t *info)
+{
+    return decode_frame_impl(dec, mp3, mp3_bytes, pcm, info, 0);
+}
+
+int mp3dec_decode_frame_f32(mp3dec_t *dec, const uint8_t *mp3, int mp3_bytes, float *pcm, mp3dec_frame_info_t *info)
+{
+    return decode_frame_impl(dec, mp3, mp3_bytes, pcm, info, 1);
+}
+
+}  // extern "C"
+
+/* ---- mp3dec_f32_to_s16 (minimp3.h:1808-1864) on the device ------------------------------------------------ */
+
+#include "l3_math.cuh"
+
+__global__ void k_f32_to_s16(const float *__restrict__ in, int16_t *__restrict__ out, int n, int n_simd)
+{
+    for (int i = blockIdx.x*blockDim.x + threadIdx.x; i < n; i += gridDim.x*blockDim.x)
+    {
+        const float v = in[i]*32768.0f;
+        out[i] = i < n_simd ? mp3b::pcm_round_simd(v) : mp3b::pcm_round_scalar(v);
+    }
+}
+
+extern "C" void mp3dec_f32_to_s16(const float *in, int16_t *out, int num_samples)
+{
+    if (num_samples <= 0) return;
+    DeviceCtx *ctx = get_ctx(0);
+    if (!ctx) return;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    cudaSetDevice(ctx->device);
+    static DevBuf d_in, d_out;
+    if (!d_in.ensure((size_t)num_samples*4) || !d_out.ensure((size_t)num_samples*2)) return;
+    cudaMemcpyAsync(d_in.p, in, (size_t)num_samples*4, cudaMemcpyHostToDevice, ctx->stream);
+    const int blocks = std::min((num_samples + 255)/256, 148*8);
+    k_f32_to_s16<<<blocks, 256, 0, ctx->stream>>>((const float *)d_in.p, (int16_t *)d_out.p, num_samples, num_samples & ~7);
+    cudaMemcpyAsync(out, d_out.p, (size_t)num_samples*2, cudaMemcpyDeviceToHost, ctx->stream);
+    cudaStreamSynchronize(ctx->stream);
+}

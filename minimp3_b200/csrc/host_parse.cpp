@@ -1,0 +1,636 @@
+/*
+ * host_parse.cpp -- see host_parse.h.  Integer-only host logic; every function names the reference
+ * lines whose behaviour it restates (paths relative to /root/reference).
+ */
+#include "host_parse.h"
+
+#include <limits.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "mp3_tables.h"
+
+namespace mp3b {
+
+static const int kHdrSize = 4;
+static const int kMaxFreeFormatFrame = 2304;   /* minimp3.h:49 */
+static const int kMaxSyncMatches = 10;         /* minimp3.h:50-52 */
+static const int kMaxReservoir = 511;          /* minimp3.h:56 */
+
+/* ---- header math (minimp3.h:264-314) ------------------------------------------------------- */
+
+bool hdr_valid(const uint8_t *h)
+{
+    if (h[0] != 0xff) return false;
+    bool sync = (h[1] & 0xF0) == 0xF0 || (h[1] & 0xFE) == 0xE2;   /* MPEG-1/2, or MPEG-2.5 Layer III */
+    int layer_bits = (h[1] >> 1) & 3, bitrate = h[2] >> 4, sr = (h[2] >> 2) & 3;
+    return sync && layer_bits != 0 && bitrate != 15 && sr != 3;
+}
+
+bool hdr_compare(const uint8_t *h1, const uint8_t *h2)
+{
+    /* same version/layer/protection-insensitive id bits, same sample rate, same free-format-ness */
+    if (!hdr_valid(h2)) return false;
+    if ((h1[1] ^ h2[1]) & 0xFE) return false;
+    if ((h1[2] ^ h2[2]) & 0x0C) return false;
+    bool ff1 = (h1[2] & 0xF0) == 0, ff2 = (h2[2] & 0xF0) == 0;
+    return ff1 == ff2;
+}
+
+unsigned hdr_bitrate_kbps(const uint8_t *h)
+{
+    /* ISO 11172-3 2.4.2.3 / 13818-3 2.4.2.3 bitrate index tables, kbit/s */
+    static const uint16_t kbps_lsf[3][15] = {
+        { 0, 8, 16, 24, 32, 40, 48, 56, 64, 80, 96, 112, 128, 144, 160 },         /* layer III */
+        { 0, 8, 16, 24, 32, 40, 48, 56, 64, 80, 96, 112, 128, 144, 160 },         /* layer II  */
+        { 0, 32, 48, 56, 64, 80, 96, 112, 128, 144, 160, 176, 192, 224, 256 } };  /* layer I   */
+    static const uint16_t kbps_m1[3][15] = {
+        { 0, 32, 40, 48, 56, 64, 80, 96, 112, 128, 160, 192, 224, 256, 320 },
+        { 0, 32, 48, 56, 64, 80, 96, 112, 128, 160, 192, 224, 256, 320, 384 },
+        { 0, 32, 64, 96, 128, 160, 192, 224, 256, 288, 320, 352, 384, 416, 448 } };
+    int row = ((h[1] >> 1) & 3) - 1;  /* layer bits: 1 = III, 2 = II, 3 = I */
+    int idx = h[2] >> 4;
+    return hdr_is_mpeg1(h) ? kbps_m1[row][idx] : kbps_lsf[row][idx];
+}
+
+unsigned hdr_sample_rate_hz(const uint8_t *h)
+{
+    static const unsigned base[3] = { 44100, 48000, 32000 };
+    unsigned hz = base[(h[2] >> 2) & 3];
+    if (!hdr_is_mpeg1(h)) hz >>= 1;          /* MPEG-2 */
+    if (!(h[1] & 0x10)) hz >>= 1;            /* MPEG-2.5 */
+    return hz;
+}
+
+unsigned hdr_frame_samples(const uint8_t *h)
+{
+    if ((h[1] & 6) == 6) return 384;                  /* layer I */
+    return ((h[1] & 14) == 2) ? 576 : 1152;           /* LSF layer III : everything else */
+}
+
+int hdr_frame_bytes(const uint8_t *h, int free_format_size)
+{
+    int bytes = (int)(hdr_frame_samples(h)*hdr_bitrate_kbps(h)*125/hdr_sample_rate_hz(h));
+    if ((h[1] & 6) == 6) bytes &= ~3;                 /* layer I slots are 4 bytes */
+    return bytes ? bytes : free_format_size;
+}
+
+int hdr_padding(const uint8_t *h)
+{
+    if (!(h[2] & 0x2)) return 0;
+    return ((h[1] & 6) == 6) ? 4 : 1;
+}
+
+/* ---- frame sync (minimp3.h:1657-1706) ------------------------------------------------------- */
+
+static int match_frame(const uint8_t *hdr, int mp3_bytes, int frame_bytes)
+{
+    int pos = 0;
+    for (int nmatch = 0; nmatch < kMaxSyncMatches; nmatch++)
+    {
+        pos += hdr_frame_bytes(hdr + pos, frame_bytes) + hdr_padding(hdr + pos);
+        if (pos + kHdrSize > mp3_bytes) return nmatch > 0;
+        if (!hdr_compare(hdr, hdr + pos)) return 0;
+    }
+    return 1;
+}
+
+int find_frame(const uint8_t *mp3, int mp3_bytes, int *free_format_bytes, int *ptr_frame_bytes)
+{
+    for (int i = 0; i < mp3_bytes - kHdrSize; i++, mp3++)
+    {
+        if (!hdr_valid(mp3)) continue;
+        int frame_bytes = hdr_frame_bytes(mp3, *free_format_bytes);
+        int frame_and_padding = frame_bytes + hdr_padding(mp3);
+
+        /* free format: the frame length is the distance to the next two compatible headers */
+        for (int k = kHdrSize; !frame_bytes && k < kMaxFreeFormatFrame && i + 2*k < mp3_bytes - kHdrSize; k++)
+        {
+            if (!hdr_compare(mp3, mp3 + k)) continue;
+            int fb = k - hdr_padding(mp3);
+            int nextfb = fb + hdr_padding(mp3 + k);
+            if (i + k + nextfb + kHdrSize > mp3_bytes || !hdr_compare(mp3, mp3 + k + nextfb)) continue;
+            frame_and_padding = k;
+            frame_bytes = fb;
+            *free_format_bytes = fb;
+        }
+        bool chain_ok = frame_bytes && i + frame_and_padding <= mp3_bytes && match_frame(mp3, mp3_bytes - i, frame_bytes);
+        bool exact_fit = !i && frame_and_padding == mp3_bytes;
+        if (chain_ok || exact_fit)
+        {
+            *ptr_frame_bytes = frame_and_padding;
+            return i;
+        }
+        *free_format_bytes = 0;
+    }
+    *ptr_frame_bytes = 0;
+    return mp3_bytes;
+}
+
+/* ---- bit reader (minimp3.h:248-262) ----------------------------------------------------------- */
+
+uint32_t BitReader::get(int n)
+{
+    int start = pos;
+    pos += n;
+    if (pos > limit) return 0;
+    uint32_t v = 0;
+    for (int b = start; b < start + n; )
+    {
+        int take = std::min(8 - (b & 7), start + n - b);
+        uint32_t byte = buf[b >> 3];
+        uint32_t piece = (byte >> (8 - (b & 7) - take)) & ((1u << take) - 1);
+        v = (v << take) | piece;
+        b += take;
+    }
+    return v;
+}
+
+/* ---- side info (minimp3.h:484-607) ------------------------------------------------------------- */
+
+int sample_rate_class(const uint8_t *hdr)
+{
+    /* MPEG-2.5: 0 (11025, 12000), 1 (8000); MPEG-2: 2, 3, 4; MPEG-1: 5, 6, 7 */
+    int version_steps = ((hdr[1] >> 3) & 1) + ((hdr[1] >> 4) & 1);
+    int idx = ((hdr[2] >> 2) & 3) + version_steps*3;
+    return idx - (idx != 0);
+}
+
+int read_side_info(BitReader *bs, GranuleSide *gr, const uint8_t *hdr)
+{
+    const bool mpeg1 = hdr_is_mpeg1(hdr), mono = hdr_is_mono(hdr);
+    int entries = mono ? 1 : 2;
+    unsigned scfsi = 0;
+    int main_data_begin, part_23_sum = 0;
+
+    if (mpeg1)
+    {
+        entries *= 2;
+        main_data_begin = (int)bs->get(9);
+        /* private bits are read together with scfsi and leak into granule 0 (quirk kept on purpose) */
+        scfsi = bs->get(7 + entries);
+    } else
+    {
+        main_data_begin = (int)(bs->get(8 + entries) >> entries);
+    }
+
+    for (int e = 0; e < entries; e++, gr++)
+    {
+        if (mono) scfsi <<= 4;
+        gr->part_23_length = (uint16_t)bs->get(12);
+        part_23_sum += gr->part_23_length;
+        gr->big_values = (uint16_t)bs->get(9);
+        if (gr->big_values > 288) return -1;
+        gr->global_gain = (uint8_t)bs->get(8);
+        gr->scalefac_compress = (uint16_t)bs->get(mpeg1 ? 4 : 9);
+        gr->n_long_sfb = 22;
+        gr->n_short_sfb = 0;
+        unsigned tables;
+        if (bs->get(1))   /* window switching */
+        {
+            gr->block_type = (uint8_t)bs->get(2);
+            if (!gr->block_type) return -1;
+            gr->mixed_block_flag = (uint8_t)bs->get(1);
+            gr->region_count[0] = 7;
+            gr->region_count[1] = 255;
+            gr->region_count[2] = 0;
+            if (gr->block_type == 2)
+            {
+                scfsi &= 0x0F0F;
+                if (!gr->mixed_block_flag)
+                {
+                    gr->region_count[0] = 8;
+                    gr->n_long_sfb = 0;
+                    gr->n_short_sfb = 39;
+                } else
+                {
+                    gr->n_long_sfb = mpeg1 ? 8 : 6;
+                    gr->n_short_sfb = 30;
+                }
+            }
+            tables = bs->get(10) << 5;
+            gr->subblock_gain[0] = (uint8_t)bs->get(3);
+            gr->subblock_gain[1] = (uint8_t)bs->get(3);
+            gr->subblock_gain[2] = (uint8_t)bs->get(3);
+        } else
+        {
+            gr->block_type = 0;
+            gr->mixed_block_flag = 0;
+            tables = bs->get(15);
+            gr->region_count[0] = (uint8_t)bs->get(4);
+            gr->region_count[1] = (uint8_t)bs->get(3);
+            gr->region_count[2] = 255;
+            gr->subblock_gain[0] = gr->subblock_gain[1] = gr->subblock_gain[2] = 0;
+        }
+        gr->table_select[0] = (uint8_t)(tables >> 10);
+        gr->table_select[1] = (uint8_t)((tables >> 5) & 31);
+        gr->table_select[2] = (uint8_t)(tables & 31);
+        gr->preflag = mpeg1 ? (uint8_t)bs->get(1) : (uint8_t)(gr->scalefac_compress >= 500);
+        gr->scalefac_scale = (uint8_t)bs->get(1);
+        gr->count1_table = (uint8_t)bs->get(1);
+        gr->scfsi = (uint8_t)((scfsi >> 12) & 15);
+        scfsi <<= 4;
+    }
+    if (part_23_sum + bs->pos > bs->limit + main_data_begin*8) return -1;
+    return main_data_begin;
+}
+
+void fill_gc_desc(GcDesc *d, const GranuleSide &g, const uint8_t *hdr, int ch, int nch, int igr, uint64_t bit_off)
+{
+    memset(d, 0, sizeof(*d));
+    d->bit_off = bit_off;
+    d->part_23_length = g.part_23_length;
+    d->big_values = g.big_values;
+    d->scalefac_compress = g.scalefac_compress;
+    d->global_gain = g.global_gain;
+    const bool ms = (hdr[3] & 0xE0) == 0x60;        /* joint stereo + MS bit (HDR_IS_MS_STEREO) */
+    const bool is = (hdr[3] & 0x10) != 0;           /* HDR_TEST_I_STEREO: bit is tested whatever the mode */
+    d->flags0 = (uint8_t)((g.block_type & 3) | (g.mixed_block_flag ? GCF_MIXED : 0) | (g.preflag ? GCF_PREFLAG : 0) |
+                          (g.scalefac_scale ? GCF_SCALEFAC_SCALE : 0) | (g.count1_table ? GCF_COUNT1_TABLE : 0) |
+                          (ms ? GCF_MS_STEREO : 0) | (is ? GCF_I_STEREO : 0));
+    for (int i = 0; i < 3; i++)
+    {
+        d->table_select[i] = g.table_select[i];
+        d->region_count[i] = g.region_count[i];
+        d->subblock_gain[i] = g.subblock_gain[i];
+    }
+    d->scfsi = g.scfsi;
+    d->n_long_sfb = g.n_long_sfb;
+    d->n_short_sfb = g.n_short_sfb;
+    d->sr_idx = (uint8_t)sample_rate_class(hdr);
+    d->flags1 = (uint8_t)((hdr_is_mpeg1(hdr) ? GCF1_MPEG1 : 0) | (ch ? GCF1_CH : 0) | (nch == 2 ? GCF1_STEREO : 0) |
+                          (igr ? GCF1_GR1 : 0) | ((ms && !is && nch == 2) ? GCF1_MS_PLAIN : 0) |
+                          ((hdr[3] & 0x20) ? GCF1_MS_TEST : 0));
+}
+
+/* ---- one mp3dec_decode_frame worth of parsing (minimp3.h:1713-1806) ---------------------------- */
+
+void parse_frame(SyncState *st, const uint8_t *mp3, int mp3_bytes, FrameParse *out, bool headers_only)
+{
+    int i = 0, frame_size = 0;
+    out->samples = 0;
+    out->reset = out->init_only = false;
+    out->layer = 0;
+    out->n_gr = out->nch = 0;
+    out->success = false;
+    out->hdr = nullptr;
+    out->payload = nullptr;
+    out->payload_bytes = 0;
+
+    if (mp3_bytes > 4 && st->header[0] == 0xff && hdr_compare(st->header, mp3))
+    {
+        frame_size = hdr_frame_bytes(mp3, st->free_format_bytes) + hdr_padding(mp3);
+        if (frame_size != mp3_bytes && (frame_size + kHdrSize > mp3_bytes || !hdr_compare(mp3, mp3 + frame_size)))
+            frame_size = 0;
+    }
+    if (!frame_size)
+    {
+        *st = SyncState();               /* memset(dec, 0): overlap, QMF history and reservoir are gone */
+        out->reset = true;
+        i = find_frame(mp3, mp3_bytes, &st->free_format_bytes, &frame_size);
+        if (!frame_size || i + frame_size > mp3_bytes)
+        {
+            out->info.frame_bytes = i;
+            return;
+        }
+    }
+    const uint8_t *hdr = mp3 + i;
+    memcpy(st->header, hdr, kHdrSize);
+    out->hdr = hdr;
+    out->info.frame_bytes = i + frame_size;
+    out->info.frame_offset = i;
+    out->info.channels = hdr_is_mono(hdr) ? 1 : 2;
+    out->info.hz = (int)hdr_sample_rate_hz(hdr);
+    out->info.layer = hdr_layer(hdr);
+    out->info.bitrate_kbps = (int)hdr_bitrate_kbps(hdr);
+    out->layer = out->info.layer;
+    out->nch = out->info.channels;
+    if (headers_only)
+    {
+        out->samples = (int)hdr_frame_samples(hdr);
+        return;
+    }
+
+    BitReader bs;
+    bs.init(hdr + kHdrSize, frame_size - kHdrSize);
+    if (hdr_is_crc(hdr)) bs.get(16);     /* CRC is skipped, never verified */
+
+    if (out->layer != 3)
+    {
+        /* Layer I/II payload is handled by the caller (not on the CUDA path yet) */
+        out->payload = bs.buf + bs.pos/8;
+        out->payload_bytes = (bs.limit - bs.pos)/8;
+        out->samples = (int)hdr_frame_samples(hdr);
+        return;
+    }
+
+    int mdb = read_side_info(&bs, out->side, hdr);
+    if (mdb < 0 || bs.pos > bs.limit)
+    {
+        st->header[0] = 0;               /* mp3dec_init: next call resyncs and clears all state */
+        out->init_only = true;
+        return;
+    }
+    out->main_data_begin = mdb;
+    out->n_gr = hdr_is_mpeg1(hdr) ? 2 : 1;
+    out->payload = bs.buf + bs.pos/8;
+    out->payload_bytes = (bs.limit - bs.pos)/8;
+
+    /* L3_restore_reservoir (minimp3.h:1228-1236) + L3_save_reservoir (:1212-1226), byte counts only */
+    const int bytes_have = std::min(st->reserv, mdb);
+    out->success = st->reserv >= mdb;
+    int consumed_bits = 0;
+    if (out->success)
+        for (int k = 0; k < out->n_gr*out->nch; k++) consumed_bits += out->side[k].part_23_length;
+    int remains = bytes_have + out->payload_bytes - (consumed_bits + 7)/8;
+    if (remains > kMaxReservoir) remains = kMaxReservoir;
+    st->reserv = remains;
+    out->samples = out->success ? (int)hdr_frame_samples(hdr) : 0;
+}
+
+/* ---- tags (minimp3_ex.h:137-263) ------------------------------------------------------------------ */
+
+void skip_id3v1(const uint8_t *buf, size_t *pbuf_size)
+{
+    size_t n = *pbuf_size;
+    if (n >= 128 && !memcmp(buf + n - 128, "TAG", 3))
+    {
+        n -= 128;
+        if (n >= 227 && !memcmp(buf + n - 227, "TAG+", 4)) n -= 227;
+    }
+    if (n > 32 && !memcmp(buf + n - 32, "APETAGEX", 8))
+    {
+        n -= 32;
+        const uint8_t *t = buf + n + 8 + 4;
+        uint32_t tag_size = ((uint32_t)t[3] << 24) | ((uint32_t)t[2] << 16) | ((uint32_t)t[1] << 8) | t[0];
+        if (n >= tag_size) n -= tag_size;
+    }
+    *pbuf_size = n;
+}
+
+size_t skip_id3v2(const uint8_t *buf, size_t buf_size)
+{
+    if (buf_size >= 10 && !memcmp(buf, "ID3", 3) &&
+        !((buf[5] & 15) || (buf[6] & 0x80) || (buf[7] & 0x80) || (buf[8] & 0x80) || (buf[9] & 0x80)))
+    {
+        size_t n = (((size_t)(buf[6] & 0x7f) << 21) | ((size_t)(buf[7] & 0x7f) << 14) | ((size_t)(buf[8] & 0x7f) << 7) |
+                    (size_t)(buf[9] & 0x7f)) + 10;
+        if (buf[5] & 16) n += 10;  /* footer */
+        return n;
+    }
+    return 0;
+}
+
+void skip_id3(const uint8_t **pbuf, size_t *pbuf_size)
+{
+    const uint8_t *buf = *pbuf;
+    size_t n = *pbuf_size;
+    size_t v2 = skip_id3v2(buf, n);
+    if (v2)
+    {
+        if (v2 >= n) v2 = n;
+        buf += v2;
+        n -= v2;
+    }
+    skip_id3v1(buf, &n);
+    *pbuf = buf;
+    *pbuf_size = n;
+}
+
+int check_vbrtag(const uint8_t *frame, int frame_size, uint32_t *frames, int *delay, int *padding)
+{
+    enum { FRAMES_FLAG = 1, BYTES_FLAG = 2, TOC_FLAG = 4, VBR_SCALE_FLAG = 8 };
+    if (frame_size < kHdrSize + 8) return 0;
+    BitReader bs;
+    GranuleSide side[4];
+    bs.init(frame + kHdrSize, frame_size - kHdrSize);
+    if (hdr_is_crc(frame)) bs.get(16);
+    if (read_side_info(&bs, side, frame) < 0) return 0;
+
+    size_t fsz = (size_t)frame_size;
+    size_t off = kHdrSize + bs.pos/8;
+    if (off > fsz || fsz - off < 8) return 0;
+    const uint8_t *tag = frame + off;
+    if (memcmp("Xing", tag, 4) && memcmp("Info", tag, 4)) return 0;
+    int flags = tag[7];
+    if (!(flags & FRAMES_FLAG)) return -1;
+    off += 8;
+    if (fsz - off < 4) return 0;
+    tag = frame + off;
+    *frames = ((uint32_t)tag[0] << 24) | ((uint32_t)tag[1] << 16) | ((uint32_t)tag[2] << 8) | tag[3];
+    off += 4;
+    if (flags & BYTES_FLAG) { if (fsz - off < 4) return 0; off += 4; }
+    if (flags & TOC_FLAG) { if (fsz - off < 100) return 0; off += 100; }
+    if (flags & VBR_SCALE_FLAG) { if (fsz - off < 4) return 0; off += 4; }
+    *delay = *padding = 0;
+    if (fsz - off < 1) return 0;
+    tag = frame + off;
+    if (*tag)
+    {   /* encoder extension (LAME, Lavc, ...) */
+        if (fsz - off <= 35) return 0;
+        off += 21;
+        tag = frame + off;
+        *delay = ((tag[0] << 4) | (tag[1] >> 4)) + (528 + 1);
+        *padding = (((tag[1] & 0xF) << 8) | tag[2]) - (528 + 1);
+    }
+    return 1;
+}
+
+int detect_buf(const uint8_t *buf, size_t buf_size)
+{
+    if (!buf || (size_t)-1 == buf_size) return -1;      /* MP3D_E_PARAM */
+    size_t filled = buf_size;
+    if (filled < 10) return -4;                          /* MP3D_E_USER: too small */
+    if (skip_id3v2(buf, filled)) return 0;
+    skip_id3v1(buf, &filled);
+    if (filled > 16*1024) filled = 16*1024;              /* MINIMP3_BUF_SIZE */
+    int free_format_bytes = 0, frame_size = 0;
+    find_frame(buf, (int)filled, &free_format_bytes, &frame_size);
+    return frame_size ? 0 : -4;
+}
+
+/* ---- whole-stream walk (minimp3_ex.h:308-525 in buffer mode) ----------------------------------------- */
+
+static void build_tiles(StreamPlan *plan, int tile_granules)
+{
+    int32_t chain[2][2] = { { -1, -1 }, { -1, -1 } };   /* [ch][0] = previous gc, [ch][1] = the one before */
+    uint64_t pcm_off = 0;
+    size_t n = plan->granules.size();
+    size_t g = 0;
+    while (g < n)
+    {
+        const GranuleRef &first = plan->granules[g];
+        if (first.reset)
+            chain[0][0] = chain[0][1] = chain[1][0] = chain[1][1] = -1;
+        TileDesc t;
+        memset(&t, 0, sizeof(t));
+        t.gc_first = first.gc;
+        t.nch = first.nch;
+        t.pcm_off = pcm_off;
+        for (int c = 0; c < 2; c++) { t.halo[c][0] = chain[c][0]; t.halo[c][1] = chain[c][1]; }
+        int cnt = 0;
+        while (g < n && cnt < tile_granules)
+        {
+            const GranuleRef &r = plan->granules[g];
+            if (cnt && (r.reset || r.nch != first.nch || r.gc != first.gc + (uint32_t)(cnt*first.nch))) break;
+            for (int c = 0; c < r.nch; c++)
+            {
+                chain[c][1] = chain[c][0];
+                chain[c][0] = (int32_t)(r.gc + c);
+            }
+            pcm_off += 576u*r.nch;
+            cnt++;
+            g++;
+        }
+        t.n_gr = (uint8_t)cnt;
+        plan->tiles.push_back(t);
+    }
+}
+
+void walk_stream(const uint8_t *buf, size_t size, uint8_t *md_dst, uint64_t md_base_bits,
+                 const WalkOptions &opt, StreamPlan *plan)
+{
+    *plan = StreamPlan();
+    uint64_t detected_samples = 0;
+    uint64_t to_skip = 0;
+    FrameInfo first{};
+    if (!opt.raw_frames)
+    {
+        skip_id3(&buf, &size);
+        if (!size) return;
+        /* first-frame probe: allocation guess in the reference, VBR-tag detection for us */
+        for (;;)
+        {
+            int free_format_bytes = 0, frame_size = 0;
+            int i = find_frame(buf, (int)std::min(size, (size_t)INT_MAX), &free_format_bytes, &frame_size);
+            buf += i;
+            size -= i;
+            if (i && !frame_size) continue;
+            if (!frame_size) return;
+            const uint8_t *hdr = buf;
+            first.channels = hdr_is_mono(hdr) ? 1 : 2;
+            first.hz = (int)hdr_sample_rate_hz(hdr);
+            first.layer = hdr_layer(hdr);
+            first.bitrate_kbps = (int)hdr_bitrate_kbps(hdr);
+            first.frame_bytes = frame_size;
+            int samples = (int)hdr_frame_samples(hdr)*first.channels;
+            if (first.layer != 3) break;
+            uint32_t frames = 0;
+            int delay = 0, padding = 0;
+            int r = check_vbrtag(hdr, frame_size, &frames, &delay, &padding);
+            if (r > 0)
+            {
+                padding *= first.channels;
+                to_skip = (uint64_t)((int64_t)delay*first.channels);
+                detected_samples = (uint64_t)samples*(uint64_t)frames;
+                if (detected_samples >= to_skip) detected_samples -= to_skip;
+                if (padding > 0 && detected_samples >= (uint64_t)padding) detected_samples -= (uint64_t)padding;
+                if (!detected_samples) return;
+            }
+            if (r)
+            {
+                buf += frame_size;
+                size -= frame_size;
+            }
+            break;
+        }
+        plan->channels = first.channels;
+        plan->hz = first.hz;
+        plan->layer = first.layer;
+    }
+
+    SyncState st;
+    FrameParse fp;
+    memset(&fp.info, 0, sizeof(fp.info));
+    uint64_t md_len = 0;                 /* bytes of main data written so far (|C|) */
+    uint64_t delivered = 0;              /* mp3dec_file_info_t.samples */
+    uint64_t skip_left = to_skip;
+    uint64_t bitrate_sum = 0, frames_counted = 0;
+    bool pending_reset = true;           /* first decoded granule starts from zero state */
+    do
+    {
+        parse_frame(&st, buf, (int)std::min(size, (size_t)INT_MAX), &fp);
+        plan->frames++;
+        if (fp.reset || fp.init_only) pending_reset = true;
+        if (fp.reset) { /* reservoir emptied: earlier main data can no longer be referenced */ }
+        if (fp.layer == 3 && fp.payload && !fp.init_only && fp.n_gr)
+        {
+            /* frame's main data begins main_data_begin bytes before its own payload in C */
+            if (fp.success)
+            {
+                uint64_t start_bits = (md_len - (uint64_t)fp.main_data_begin)*8u;
+                bool stop = false;
+                if (!opt.raw_frames)
+                {
+                    if (plan->hz != fp.info.hz || plan->layer != fp.info.layer) { plan->ret = -5; stop = true; }
+                    else if (plan->channels && plan->channels != fp.info.channels)
+                    {
+                        if (opt.allow_mono_stereo) plan->channels = 0;
+                        else { plan->ret = -5; stop = true; }
+                    }
+                }
+                if (stop) break;
+                uint64_t bit = md_base_bits + start_bits;
+                const bool istereo = (fp.hdr[3] & 0x10) && fp.nch == 2;
+                for (int igr = 0; igr < fp.n_gr; igr++)
+                {
+                    if (fp.nch == 2 && (plan->gcs.size() & 1))
+                    {
+                        /* keep stereo pairs on even indices (the entropy kernel pairs lanes 2k, 2k+1 for MS) */
+                        GcDesc pad;
+                        memset(&pad, 0, sizeof(pad));
+                        pad.flags1 = GCF1_MPEG1;
+                        plan->gcs.push_back(pad);
+                    }
+                    GranuleRef gref;
+                    gref.gc = (uint32_t)plan->gcs.size();
+                    gref.nch = (uint8_t)fp.nch;
+                    gref.reset = pending_reset ? 1 : 0;
+                    pending_reset = false;
+                    plan->granules.push_back(gref);
+                    if (istereo) plan->istereo_gcs.push_back(gref.gc);
+                    for (int ch = 0; ch < fp.nch; ch++)
+                    {
+                        GcDesc d;
+                        const GranuleSide &g = fp.side[igr*fp.nch + ch];
+                        fill_gc_desc(&d, g, fp.hdr, ch, fp.nch, igr, bit);
+                        bit += g.part_23_length;
+                        plan->gcs.push_back(d);
+                    }
+                }
+                plan->frames_decoded++;
+                if (opt.raw_frames && !plan->hz)
+                {
+                    plan->hz = fp.info.hz; plan->layer = 3; plan->channels = fp.info.channels;
+                }
+                uint64_t s = (uint64_t)fp.samples*(uint64_t)fp.info.channels;
+                plan->samples_decoded += s;
+                uint64_t skip = std::min(s, skip_left);
+                skip_left -= skip;
+                delivered += s - skip;
+                bitrate_sum += (uint64_t)fp.info.bitrate_kbps;
+                frames_counted++;
+            }
+            /* payload joins C whether or not the frame was decodable (L3_save_reservoir runs either way) */
+            memcpy(md_dst + md_len, fp.payload, (size_t)fp.payload_bytes);
+            md_len += (uint64_t)fp.payload_bytes;
+        } else if (fp.layer && fp.layer != 3 && fp.samples)
+        {
+            plan->has_layer12 = true;
+            plan->ret = -6;              /* MP3D_E_UNSUPPORTED: Layer I/II not on the CUDA path yet */
+            break;
+        }
+        buf += fp.info.frame_bytes;
+        size -= (size_t)fp.info.frame_bytes;
+    } while (fp.info.frame_bytes);
+
+    plan->main_data_bytes = md_len;
+    plan->out_skip = to_skip - skip_left;
+    if (detected_samples && delivered > detected_samples) delivered = detected_samples;
+    plan->out_samples = delivered;
+    if (frames_counted) plan->avg_bitrate_kbps = (int)(bitrate_sum/frames_counted);
+    build_tiles(plan, opt.tile_granules);
+}
+
+}  // namespace mp3b

@@ -1,0 +1,151 @@
+/*
+ * host_parse.h -- host side of the Layer III hot path (stays on the CPU):
+ * frame sync, header math, side-info parse, bit-reservoir resolution and tile planning.
+ *
+ * This restates, as a frame walker that never touches PCM, the control flow of
+ *   mp3dec_decode_frame      /root/reference/minimp3.h:1713-1806
+ *   mp3d_find_frame/match    /root/reference/minimp3.h:1657-1706
+ *   L3_read_side_info        /root/reference/minimp3.h:484-607
+ *   L3_restore/save_reservoir/root/reference/minimp3.h:1212-1236
+ * and, on top of it, the whole-file semantics of mp3dec_load_buf (minimp3_ex.h:308-525).
+ */
+#ifndef MP3B_HOST_PARSE_H
+#define MP3B_HOST_PARSE_H
+#include <stddef.h>
+#include <stdint.h>
+
+#include <vector>
+
+#include "l3_types.h"
+
+namespace mp3b {
+
+struct FrameInfo
+{
+    int frame_bytes, frame_offset, channels, hz, layer, bitrate_kbps;
+};
+
+/* header helpers (minimp3.h:61-78, 264-314) */
+bool hdr_valid(const uint8_t *h);
+bool hdr_compare(const uint8_t *h1, const uint8_t *h2);
+unsigned hdr_bitrate_kbps(const uint8_t *h);
+unsigned hdr_sample_rate_hz(const uint8_t *h);
+unsigned hdr_frame_samples(const uint8_t *h);
+int hdr_frame_bytes(const uint8_t *h, int free_format_size);
+int hdr_padding(const uint8_t *h);
+inline bool hdr_is_mono(const uint8_t *h) { return (h[3] & 0xC0) == 0xC0; }
+inline bool hdr_is_crc(const uint8_t *h) { return !(h[1] & 1); }
+inline bool hdr_is_mpeg1(const uint8_t *h) { return (h[1] & 0x8) != 0; }
+inline int hdr_layer(const uint8_t *h) { return 4 - ((h[1] >> 1) & 3); }
+
+int find_frame(const uint8_t *mp3, int mp3_bytes, int *free_format_bytes, int *ptr_frame_bytes);
+
+/* MSB-first bit reader over a byte buffer; reads past `limit` return 0 (minimp3.h:248-262) */
+struct BitReader
+{
+    const uint8_t *buf;
+    int pos, limit;
+    void init(const uint8_t *data, int bytes) { buf = data; pos = 0; limit = bytes*8; }
+    uint32_t get(int n);
+};
+
+/* One parsed granule-channel of side info. */
+struct GranuleSide
+{
+    uint16_t part_23_length, big_values, scalefac_compress;
+    uint8_t global_gain, block_type, mixed_block_flag, n_long_sfb, n_short_sfb;
+    uint8_t table_select[3], region_count[3], subblock_gain[3];
+    uint8_t preflag, scalefac_scale, count1_table, scfsi;
+};
+
+/* returns main_data_begin or -1 (minimp3.h:484-607) */
+int read_side_info(BitReader *bs, GranuleSide *gr, const uint8_t *hdr);
+int sample_rate_class(const uint8_t *hdr);   /* 0..7, row of the sfb tables */
+
+/* A decoded granule of the stream in output order. */
+struct GranuleRef
+{
+    uint32_t gc;       /* stream-relative index of channel 0's GcDesc */
+    uint8_t nch;
+    uint8_t reset;     /* decoder state was zeroed before this granule */
+};
+
+/* Everything the walker learns about one stream.  Indices are stream-relative until rebase(). */
+struct StreamPlan
+{
+    /* results mirrored into mp3dec_file_info_t */
+    int ret = 0;                 /* 0 or MP3D_E_* */
+    uint64_t samples_decoded = 0;/* channel-inclusive samples the kernels produce for this stream */
+    uint64_t out_skip = 0;       /* leading samples to drop (encoder delay, mp3dec_load_buf to_skip) */
+    uint64_t out_samples = 0;    /* samples delivered to the caller after skip/cut */
+    int channels = 0, hz = 0, layer = 0, avg_bitrate_kbps = 0;
+    /* device work */
+    std::vector<GcDesc> gcs;
+    std::vector<GranuleRef> granules;
+    std::vector<TileDesc> tiles;
+    uint64_t main_data_bytes = 0;
+    uint32_t frames = 0, frames_decoded = 0;
+    bool has_layer12 = false;
+    std::vector<uint32_t> istereo_gcs;  /* stream-relative gc index (channel 0) of granules needing intensity stereo */
+};
+
+struct WalkOptions
+{
+    bool raw_frames = false;            /* plain mp3dec_decode_frame loop: no tag skipping / VBR-tag trimming */
+    bool allow_mono_stereo = false;     /* MINIMP3_ALLOW_MONO_STEREO_TRANSITION */
+    int tile_granules = MP3B_TILE_GRANULES;
+};
+
+/*
+ * Walks one stream.  Main data (the concatenated payloads) is written to md_dst (capacity >= size + 16);
+ * GcDesc.bit_off = md_base_bits + offset inside md_dst.
+ */
+void walk_stream(const uint8_t *buf, size_t size, uint8_t *md_dst, uint64_t md_base_bits,
+                 const WalkOptions &opt, StreamPlan *plan);
+
+/* tag helpers (minimp3_ex.h:137-191) */
+void skip_id3(const uint8_t **pbuf, size_t *pbuf_size);
+size_t skip_id3v2(const uint8_t *buf, size_t buf_size);
+void skip_id3v1(const uint8_t *buf, size_t *pbuf_size);
+/* minimp3_ex.h:193-263 */
+int check_vbrtag(const uint8_t *frame, int frame_size, uint32_t *frames, int *delay, int *padding);
+
+/* mp3dec_detect_buf (minimp3_ex.h:265-306, buffer flavour) */
+int detect_buf(const uint8_t *buf, size_t buf_size);
+
+/*
+ * Incremental emulation of the decoder's bitstream-side state (header, free_format_bytes, reservoir fill)
+ * used by both walk_stream and the single-frame API.
+ */
+struct SyncState
+{
+    uint8_t header[4] = {0, 0, 0, 0};
+    int free_format_bytes = 0;
+    int reserv = 0;
+};
+
+struct FrameParse
+{
+    FrameInfo info{};
+    int samples = 0;            /* per channel; 0 when undecodable */
+    bool reset = false;         /* decoder state was cleared (memset) during this call */
+    bool init_only = false;     /* decoder was re-initialised (header[0]=0) during this call */
+    int layer = 0;
+    /* Layer III only */
+    int n_gr = 0, nch = 0;
+    int main_data_begin = 0;
+    const uint8_t *payload = nullptr;  /* bytes after the side info */
+    int payload_bytes = 0;
+    bool success = false;       /* reservoir holds main_data_begin bytes */
+    GranuleSide side[4];
+    const uint8_t *hdr = nullptr;
+};
+
+/* One mp3dec_decode_frame call worth of parsing (no PCM).  Updates st->header/free_format_bytes and, for
+ * Layer III, st->reserv exactly as L3_restore_reservoir / L3_save_reservoir would. */
+void parse_frame(SyncState *st, const uint8_t *mp3, int mp3_bytes, FrameParse *out, bool headers_only = false);
+
+void fill_gc_desc(GcDesc *d, const GranuleSide &g, const uint8_t *hdr, int ch, int nch, int igr, uint64_t bit_off);
+
+}  // namespace mp3b
+#endif

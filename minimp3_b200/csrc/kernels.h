@@ -1,0 +1,70 @@
+/*
+ * kernels.h -- launch interface of the sm_100a kernels (internal; the C ABI is include/minimp3_b200.h).
+ */
+#ifndef MP3B_KERNELS_H
+#define MP3B_KERNELS_H
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "l3_types.h"
+
+namespace mp3b {
+
+/* Device-resident constant tables (uploaded once per device by tables_upload). */
+struct DeviceTables
+{
+    uint16_t *reorder_map;   /* [16][576]: (sr_idx*2 + mixed) -> destination line of source line e */
+    float *fir_coef;         /* [32][16]: per output phase j the 16 signed window taps */
+};
+
+struct EntropyArgs
+{
+    const uint32_t *md_words;     /* main data, viewed as 32-bit words (byte order fixed in the kernel) */
+    uint64_t md_n_words;
+    const GcDesc *gcs;
+    uint32_t n_gc;                /* multiple of 2; stereo pairs start at even indices */
+    float *xr;                    /* [n_gc][576] */
+    uint16_t *nzl;                /* [n_gc] lines written per row (multiple of 32) */
+    uint8_t *ist_pos;             /* [n_gc][40] written for intensity-stereo frames (and in tap mode) */
+    /* optional taps for the parity tests (null in production) */
+    int16_t *tap_q;               /* [n_gc][576] */
+    float *tap_scf;               /* [n_gc][40]  */
+};
+
+struct StereoArgs
+{
+    const GcDesc *gcs;
+    const uint32_t *granules;     /* gc index of channel 0 of every granule that needs intensity stereo */
+    uint32_t n_granules;
+    float *xr;
+    uint16_t *nzl;
+    const uint8_t *ist_pos;
+};
+
+struct TransformArgs
+{
+    const GcDesc *gcs;
+    const TileDesc *tiles;
+    uint32_t n_tiles;
+    const float *xr;
+    const uint16_t *nzl;
+    void *pcm;                    /* int16 or float, interleaved */
+    int float_output;
+    /* optional carried state for the single-frame API (null in batch mode): mp3dec_t.mdct_overlap / qmf_state */
+    const float *state_in;        /* [2][288] tails + [2][15][32] synthesis history */
+    float *state_out;
+    /* optional tap (tests): subband samples after IMDCT + sign, [n_gc][576] */
+    float *tap_sub;
+};
+
+struct ImdctConsts;
+int tables_upload(DeviceTables *t);
+void host_build_tables(ImdctConsts *k, uint16_t *map, float *fir);
+void tables_free(DeviceTables *t);
+
+cudaError_t launch_entropy(const DeviceTables &t, const EntropyArgs &a, cudaStream_t s);
+cudaError_t launch_intensity_stereo(const DeviceTables &t, const StereoArgs &a, cudaStream_t s);
+cudaError_t launch_transform(const DeviceTables &t, const TransformArgs &a, cudaStream_t s);
+
+}  // namespace mp3b
+#endif

@@ -1,0 +1,66 @@
+/*
+ * l3_types.h -- records shared by the host bitstream stage and the CUDA kernels.
+ *
+ * Data layout in HBM:
+ *   main data   uint8  [total_bytes]      per stream: the frame payloads that follow the side info,
+ *                                         concatenated ("C" in SURVEY.md 8a-r2), 16-byte aligned start
+ *   GcDesc      32 B   [n_gc]             one per granule-channel, order = stream, frame, granule, channel
+ *   TileDesc    32 B   [n_tiles]          one per run of <= MP3B_TILE_GRANULES consecutive granules
+ *   xr          float  [n_gc][576]        requantised (+ MS stereo) spectra, written by the entropy kernel
+ *   pcm         int16 / float [n_samples] interleaved PCM, stream after stream
+ */
+#ifndef MP3B_L3_TYPES_H
+#define MP3B_L3_TYPES_H
+#include <stdint.h>
+
+#define MP3B_TILE_GRANULES 8
+
+/* GcDesc.flags0 */
+#define GCF_BLOCK_TYPE_MASK 0x03
+#define GCF_MIXED           0x04
+#define GCF_PREFLAG         0x08
+#define GCF_SCALEFAC_SCALE  0x10
+#define GCF_COUNT1_TABLE    0x20
+#define GCF_MS_STEREO       0x40   /* header: joint stereo with MS bit (HDR_IS_MS_STEREO / HDR_TEST_MS_STEREO) */
+#define GCF_I_STEREO        0x80   /* header: intensity stereo bit (HDR_TEST_I_STEREO) */
+/* GcDesc.flags1 */
+#define GCF1_MPEG1          0x01
+#define GCF1_CH             0x02   /* this is channel 1 */
+#define GCF1_STEREO         0x04   /* frame has two channels */
+#define GCF1_GR1            0x08   /* second granule of an MPEG-1 frame (scfsi source = gc - nch) */
+#define GCF1_MS_PLAIN       0x10   /* MS stereo handled by the entropy kernel (MS bit set, intensity bit clear) */
+#define GCF1_MS_TEST        0x20   /* raw MS bit of the header (HDR_TEST_MS_STEREO), whatever the channel mode */
+
+/* One granule-channel: the L3_gr_info_t of the reference (minimp3.h:223-230) with the sfb table pointer
+ * replaced by (sfb kind, sample-rate class) and the bit-reservoir position resolved to an absolute offset. */
+typedef struct
+{
+    uint64_t bit_off;            /* absolute bit offset of part 2 (scalefactors) in the main-data buffer */
+    uint16_t part_23_length;
+    uint16_t big_values;
+    uint16_t scalefac_compress;
+    uint8_t  global_gain;
+    uint8_t  flags0;
+    uint8_t  table_select[3];
+    uint8_t  region_count[3];
+    uint8_t  subblock_gain[3];
+    uint8_t  scfsi;
+    uint8_t  n_long_sfb, n_short_sfb;
+    uint8_t  sr_idx;             /* row of the sfb tables, 0..7 */
+    uint8_t  flags1;
+    uint8_t  pad[2];
+} GcDesc;
+
+/* One tile of the transform kernel: n_gr consecutive decoded granules of one stream that share the
+ * channel count and have no decoder reset between them.  halo[ch][0] / halo[ch][1] are the granule-channel
+ * indices of the previous / second previous granule of that channel since the last reset (-1: zero state).
+ * They replace the carried mdct_overlap / qmf_state of the reference (minimp3.h:18-23). */
+typedef struct
+{
+    uint32_t gc_first;           /* index of granule 0 channel 0 */
+    uint8_t  n_gr, nch, pad[2];
+    uint64_t pcm_off;            /* sample offset (channel-inclusive) of the tile's first PCM sample */
+    int32_t  halo[2][2];
+} TileDesc;
+
+#endif
