@@ -1,0 +1,273 @@
+"""minimp3_b200 -- B200 (sm_100a) batched MP3 Layer III decoder behind the lieff/minimp3 API.
+
+The product is the C-ABI shared library ``libminimp3_b200.so`` (include/minimp3_b200.h); this package
+is the thin ctypes mirror used by the tests and bench.py.  Names and argument meaning follow the
+reference (minimp3.h / minimp3_ex.h): ``mp3dec_init``, ``mp3dec_decode_frame``, ``mp3dec_load_buf``,
+``mp3dec_detect_buf`` plus the batch entry ``mp3dec_decode_batch_cuda``.
+
+There is no CPU decode path: if the CUDA library is missing or no device is usable, calls raise.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libminimp3_b200.so")
+
+MP3D_E_PARAM, MP3D_E_MEMORY, MP3D_E_IOERROR, MP3D_E_USER, MP3D_E_DECODE = -1, -2, -3, -4, -5
+MP3D_E_UNSUPPORTED, MP3D_E_CUDA = -6, -7
+OUT_MALLOC, OUT_PINNED, OUT_DEVICE = 0, 1, 2
+MINIMP3_MAX_SAMPLES_PER_FRAME = 1152*2
+
+
+class FrameInfo(C.Structure):
+    """mp3dec_frame_info_t (minimp3.h:13-16)"""
+    _fields_ = [(n, C.c_int) for n in ("frame_bytes", "frame_offset", "channels", "hz", "layer", "bitrate_kbps")]
+
+
+class Mp3Dec(C.Structure):
+    """mp3dec_t (minimp3.h:18-23), 6668 bytes"""
+    _fields_ = [("mdct_overlap", C.c_float*(2*9*32)), ("qmf_state", C.c_float*(15*2*32)), ("reserv", C.c_int),
+                ("free_format_bytes", C.c_int), ("header", C.c_ubyte*4), ("reserv_buf", C.c_ubyte*511)]
+
+
+class FileInfo(C.Structure):
+    """mp3dec_file_info_t (minimp3_ex.h:38-43)"""
+    _fields_ = [("buffer", C.c_void_p), ("samples", C.c_size_t), ("channels", C.c_int), ("hz", C.c_int),
+                ("layer", C.c_int), ("avg_bitrate_kbps", C.c_int)]
+
+
+class BatchStream(C.Structure):
+    _fields_ = [("buf", C.c_void_p), ("size", C.c_size_t)]
+
+
+class BatchOpts(C.Structure):
+    _fields_ = [("device", C.c_int), ("float_output", C.c_int), ("raw_frames", C.c_int),
+                ("allow_mono_stereo_transition", C.c_int), ("host_threads", C.c_int), ("output", C.c_int),
+                ("cuda_stream", C.c_void_p)]
+
+
+class BatchStats(C.Structure):
+    _fields_ = [("input_bytes", C.c_uint64), ("samples", C.c_uint64), ("n_granule_channels", C.c_uint64),
+                ("n_tiles", C.c_uint64), ("n_istereo_granules", C.c_uint64), ("n_frames", C.c_uint64),
+                ("kernels_per_run", C.c_int), ("host_parse_ms", C.c_double), ("h2d_ms", C.c_double)]
+
+
+EXPORTS = ["mp3dec_init", "mp3dec_decode_frame", "mp3dec_decode_frame_f32", "mp3dec_f32_to_s16", "mp3dec_detect_buf",
+           "mp3dec_load_buf", "mp3dec_load_buf_f32", "mp3dec_decode_batch_cuda", "mp3dec_batch_plan_create",
+           "mp3dec_batch_plan_run", "mp3dec_batch_plan_sync", "mp3dec_batch_plan_fetch", "mp3dec_batch_plan_stats",
+           "mp3dec_batch_plan_device_pcm", "mp3dec_batch_plan_destroy", "mp3dec_batch_plan_enable_taps",
+           "mp3dec_batch_plan_read_tap", "mp3dec_batch_shard", "mp3dec_b200_version"]
+
+_lib = None
+
+
+def load():
+    """Load libminimp3_b200.so (built in-tree by minimp3_b200/build.py).  Raises if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError("libminimp3_b200.so not built (run `python -m minimp3_b200.build`); "
+                           "there is no CPU fallback for the decode path")
+    L = C.CDLL(LIB_PATH)
+    vp = C.c_void_p
+    L.mp3dec_init.argtypes = [C.POINTER(Mp3Dec)]
+    L.mp3dec_init.restype = None
+    for fn in (L.mp3dec_decode_frame, L.mp3dec_decode_frame_f32):
+        fn.argtypes = [C.POINTER(Mp3Dec), vp, C.c_int, vp, C.POINTER(FrameInfo)]
+        fn.restype = C.c_int
+    L.mp3dec_f32_to_s16.argtypes = [vp, vp, C.c_int]
+    L.mp3dec_f32_to_s16.restype = None
+    L.mp3dec_detect_buf.argtypes = [vp, C.c_size_t]
+    for fn in (L.mp3dec_load_buf, L.mp3dec_load_buf_f32):
+        fn.argtypes = [C.POINTER(Mp3Dec), vp, C.c_size_t, C.POINTER(FileInfo), vp, vp]
+        fn.restype = C.c_int
+    L.mp3dec_decode_batch_cuda.argtypes = [C.POINTER(BatchStream), C.c_int, C.POINTER(FileInfo), C.POINTER(C.c_int),
+                                           C.POINTER(BatchOpts)]
+    L.mp3dec_batch_plan_create.argtypes = [C.POINTER(BatchStream), C.c_int, C.POINTER(BatchOpts), C.POINTER(C.c_int)]
+    L.mp3dec_batch_plan_create.restype = vp
+    for name in ("mp3dec_batch_plan_run", "mp3dec_batch_plan_sync", "mp3dec_batch_plan_enable_taps"):
+        getattr(L, name).argtypes = [vp]
+        getattr(L, name).restype = C.c_int
+    L.mp3dec_batch_plan_fetch.argtypes = [vp, C.POINTER(FileInfo), C.POINTER(C.c_int)]
+    L.mp3dec_batch_plan_stats.argtypes = [vp, C.POINTER(BatchStats)]
+    L.mp3dec_batch_plan_stats.restype = None
+    L.mp3dec_batch_plan_device_pcm.argtypes = [vp]
+    L.mp3dec_batch_plan_device_pcm.restype = vp
+    L.mp3dec_batch_plan_destroy.argtypes = [vp]
+    L.mp3dec_batch_plan_destroy.restype = None
+    L.mp3dec_batch_plan_read_tap.argtypes = [vp, C.c_int, vp, C.c_size_t]
+    L.mp3dec_batch_shard.argtypes = [C.POINTER(C.c_size_t), C.c_int, C.c_int, C.POINTER(C.c_int)]
+    L.mp3dec_batch_shard.restype = None
+    L.mp3dec_b200_version.restype = C.c_char_p
+    L.free = C.CDLL(None).free
+    L.free.argtypes = [vp]
+    _lib = L
+    return L
+
+
+def _as_u8(data):
+    if isinstance(data, np.ndarray):
+        return np.ascontiguousarray(data, dtype=np.uint8)
+    return np.frombuffer(bytes(data), dtype=np.uint8) if len(data) else np.zeros(1, np.uint8)
+
+
+def _opts(device=0, float_output=False, raw_frames=False, allow_mono_stereo=False, host_threads=0, output=OUT_PINNED,
+          cuda_stream=None):
+    return BatchOpts(int(device), int(bool(float_output)), int(bool(raw_frames)), int(bool(allow_mono_stereo)),
+                     int(host_threads), int(output), C.c_void_p(cuda_stream) if cuda_stream else None)
+
+
+def shard_streams(sizes, n_shards):
+    """Greedy LPT split of streams over GPUs (no collective on the data path)."""
+    L = load()
+    n = len(sizes)
+    arr = (C.c_size_t*n)(*[int(s) for s in sizes])
+    out = (C.c_int*n)()
+    L.mp3dec_batch_shard(arr, n, int(n_shards), out)
+    return list(out)
+
+
+class BatchPlan:
+    """Split form of mp3dec_decode_batch_cuda: parse + H2D at construction, ``run()`` launches the kernels,
+    ``fetch()`` copies PCM back.  Keeps references to the input buffers alive."""
+
+    def __init__(self, streams, **kw):
+        self.L = load()
+        self.float_output = bool(kw.get("float_output", False))
+        self._keep = [_as_u8(s) for s in streams]
+        n = len(self._keep)
+        self.n = n
+        self._streams = (BatchStream*max(1, n))()
+        for i, (a, s) in enumerate(zip(self._keep, streams)):
+            self._streams[i].buf = a.ctypes.data
+            self._streams[i].size = len(s)
+        self._opts = _opts(**kw)
+        err = C.c_int(0)
+        self.handle = self.L.mp3dec_batch_plan_create(self._streams, n, C.byref(self._opts), C.byref(err))
+        if not self.handle:
+            raise RuntimeError("mp3dec_batch_plan_create failed: %d" % err.value)
+        st = BatchStats()
+        self.L.mp3dec_batch_plan_stats(self.handle, C.byref(st))
+        self.stats = {f[0]: getattr(st, f[0]) for f in BatchStats._fields_}
+
+    def enable_taps(self):
+        r = self.L.mp3dec_batch_plan_enable_taps(self.handle)
+        if r:
+            raise RuntimeError("enable_taps failed: %d" % r)
+
+    def run(self):
+        r = self.L.mp3dec_batch_plan_run(self.handle)
+        if r:
+            raise RuntimeError("mp3dec_batch_plan_run failed: %d" % r)
+
+    def sync(self):
+        r = self.L.mp3dec_batch_plan_sync(self.handle)
+        if r:
+            raise RuntimeError("mp3dec_batch_plan_sync failed: %d" % r)
+
+    def fetch(self, copy=True):
+        """Returns (rets, list of per-stream dict(pcm ndarray, channels, hz, layer, avg_bitrate_kbps))."""
+        infos = (FileInfo*max(1, self.n))()
+        rets = (C.c_int*max(1, self.n))()
+        r = self.L.mp3dec_batch_plan_fetch(self.handle, infos, rets)
+        if r:
+            raise RuntimeError("mp3dec_batch_plan_fetch failed: %d" % r)
+        out = []
+        dt = np.float32 if self.float_output else np.int16
+        ct = C.c_float if self.float_output else C.c_int16
+        for i in range(self.n):
+            fi = infos[i]
+            if fi.buffer and fi.samples and self._opts.output != OUT_DEVICE:
+                arr = np.ctypeslib.as_array(C.cast(fi.buffer, C.POINTER(ct)), shape=(fi.samples,))
+                if copy or self._opts.output == OUT_MALLOC:
+                    arr = arr.copy()
+                if self._opts.output == OUT_MALLOC:
+                    self.L.free(fi.buffer)
+            else:
+                arr = np.zeros(0, dt)
+            out.append(dict(pcm=arr, samples=int(fi.samples), channels=fi.channels, hz=fi.hz, layer=fi.layer,
+                            avg_bitrate_kbps=fi.avg_bitrate_kbps, device_ptr=fi.buffer if self._opts.output == OUT_DEVICE else None))
+        return list(rets)[:self.n], out
+
+    def read_tap(self, which):
+        n = int(self.stats["n_granule_channels"])
+        shapes = {0: ((n, 576), np.int16), 1: ((n, 40), np.float32), 2: ((n, 576), np.float32), 3: ((n, 576), np.float32),
+                  4: ((n, 32), np.uint8), 5: ((n, 40), np.uint8), 6: ((n,), np.uint16)}
+        shape, dt = shapes[which]
+        a = np.zeros(shape, dt)
+        r = self.L.mp3dec_batch_plan_read_tap(self.handle, which, a.ctypes.data, a.nbytes)
+        if r:
+            raise RuntimeError("read_tap(%d) failed: %d" % (which, r))
+        return a
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.L.mp3dec_batch_plan_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def mp3dec_decode_batch_cuda(streams, **kw):
+    """Decode a list of byte buffers.  Per-stream results follow mp3dec_load_buf (minimp3_ex.h:308-525)."""
+    p = BatchPlan(streams, **kw)
+    try:
+        p.run()
+        return p.fetch(copy=True)
+    finally:
+        p.close()
+
+
+def mp3dec_load_buf(data, float_output=False):
+    """mp3dec_load_buf through the C entry point; returns (ret, pcm, info dict)."""
+    L = load()
+    dec = Mp3Dec()
+    fi = FileInfo()
+    buf = _as_u8(data)
+    fn = L.mp3dec_load_buf_f32 if float_output else L.mp3dec_load_buf
+    ret = fn(C.byref(dec), buf.ctypes.data, len(data), C.byref(fi), None, None)
+    ct = C.c_float if float_output else C.c_int16
+    if fi.buffer and fi.samples:
+        pcm = np.ctypeslib.as_array(C.cast(fi.buffer, C.POINTER(ct)), shape=(fi.samples,)).copy()
+    else:
+        pcm = np.zeros(0, np.float32 if float_output else np.int16)
+    if fi.buffer:
+        L.free(fi.buffer)
+    return ret, pcm, dict(channels=fi.channels, hz=fi.hz, layer=fi.layer, avg_bitrate_kbps=fi.avg_bitrate_kbps)
+
+
+def mp3dec_detect_buf(data):
+    L = load()
+    buf = _as_u8(data)
+    return L.mp3dec_detect_buf(buf.ctypes.data, len(data))
+
+
+def decode_frames(data, float_output=False):
+    """The README's frame loop over mp3dec_init / mp3dec_decode_frame.  Returns (pcm, frames)."""
+    L = load()
+    dec = Mp3Dec()
+    L.mp3dec_init(C.byref(dec))
+    info = FrameInfo()
+    buf = _as_u8(data)
+    dt = np.float32 if float_output else np.int16
+    tmp = np.zeros(MINIMP3_MAX_SAMPLES_PER_FRAME, dt)
+    fn = L.mp3dec_decode_frame_f32 if float_output else L.mp3dec_decode_frame
+    pos, out, frames = 0, [], []
+    n = len(data)
+    while True:
+        samples = fn(C.byref(dec), buf.ctypes.data + pos, min(n - pos, 2**31 - 1), tmp.ctypes.data, C.byref(info))
+        frames.append(dict(offset=pos, frame_bytes=info.frame_bytes, frame_offset=info.frame_offset, samples=samples,
+                           channels=info.channels, hz=info.hz, layer=info.layer, bitrate_kbps=info.bitrate_kbps))
+        if samples:
+            out.append(tmp[:samples*info.channels].copy())
+        pos += info.frame_bytes
+        if not info.frame_bytes:
+            break
+    return (np.concatenate(out) if out else np.zeros(0, dt)), frames

@@ -57,9 +57,7 @@ struct TransformArgs
     float *tap_sub;
 };
 
-struct ImdctConsts;
 int tables_upload(DeviceTables *t);
-void host_build_tables(ImdctConsts *k, uint16_t *map, float *fir);
 void tables_free(DeviceTables *t);
 
 cudaError_t launch_entropy(const DeviceTables &t, const EntropyArgs &a, cudaStream_t s);

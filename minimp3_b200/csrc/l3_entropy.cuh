@@ -1,0 +1,335 @@
+/*
+ * l3_entropy.cuh -- per-granule-channel entropy decode: part 2 (scalefactors) and part 3 (Huffman big
+ * values + count1 quads) with requantisation, written as a __host__ __device__ state machine so that
+ * the code one GPU lane executes can also be stepped on the CPU by the unit tests.
+ *
+ * Restates L3_read_scalefactors / L3_decode_scalefactors (minimp3.h:609-714) and L3_huffman
+ * (minimp3.h:742-877).  One call of GranuleDecoder::step() produces the next TWO spectral lines: a
+ * big-value pair, or half of a count1 quad -- this keeps all lanes of a warp on the same line index.
+ */
+#ifndef MP3B_L3_ENTROPY_CUH
+#define MP3B_L3_ENTROPY_CUH
+#include <stdint.h>
+
+#include "l3_math.cuh"
+#include "l3_types.h"
+
+namespace mp3b {
+
+/* pointers to the decode tables (shared memory on the device, plain arrays on the host) */
+struct EntropyTables
+{
+    const uint16_t *lut;        /* MP3T_HUFF_LUT */
+    const float *pow43;         /* MP3T_POW43 */
+    const uint32_t *tabinfo;    /* [32] base | rootw << 16 | linbits << 20 */
+    const uint8_t *count1a;     /* [64] */
+    const uint8_t *sfb_long, *sfb_short, *sfb_mixed;
+};
+
+/* MSB-first bit reader over big-endian bytes, fed by aligned 32-bit loads */
+struct BitRd
+{
+    const uint32_t *w;
+    uint64_t n_words, widx;
+    uint64_t buf;
+    int avail;
+    int pos;   /* bits consumed since init */
+
+    MP3_HD uint32_t word(uint64_t i) const
+    {
+        if (i >= n_words) return 0u;
+#if defined(__CUDA_ARCH__)
+        return __byte_perm(__ldg(w + i), 0, 0x0123);
+#else
+        return __builtin_bswap32(w[i]);
+#endif
+    }
+    MP3_HD void init(const uint32_t *words, uint64_t nw, uint64_t bit_off)
+    {
+        w = words; n_words = nw;
+        widx = bit_off >> 5;
+        const int sh = (int)(bit_off & 31);
+        buf = ((uint64_t)word(widx) << 32) | word(widx + 1);
+        buf <<= sh;
+        avail = 64 - sh;
+        widx += 2;
+        pos = 0;
+    }
+    MP3_HD void refill()
+    {
+        if (avail <= 32)
+        {
+            buf |= (uint64_t)word(widx++) << (32 - avail);
+            avail += 32;
+        }
+    }
+    MP3_HD uint32_t peek(int n) const { return n ? (uint32_t)(buf >> (64 - n)) : 0u; }
+    MP3_HD void skip(int n) { buf <<= n; avail -= n; pos += n; }
+    MP3_HD uint32_t get(int n)
+    {
+        refill();
+        const uint32_t v = peek(n);
+        skip(n);
+        return v;
+    }
+};
+
+struct ScfLayout
+{
+    uint8_t size[4];
+    uint8_t count[4];
+};
+
+/* partition sizes as four packed bytes (count[0] in the low byte); kind: 0 long, 1 mixed, 2 short.
+ * ISO 11172-3 2.4.2.7 (MPEG-1) and 13818-3 2.4.3.2 nr_of_sfb_block (LSF). */
+MP3_HD uint32_t scf_partition_mpeg1(int kind)
+{
+    return kind == 0 ? 0x05050506u : kind == 1 ? 0x0C060908u : 0x0C060909u;
+}
+
+MP3_HD uint32_t scf_partition_lsf(int tn, int kind)
+{
+    switch (tn*3 + kind)
+    {
+    case 0: return 0x05050506u; case 1: return 0x09090906u; case 2: return 0x09090909u;
+    case 3: return 0x03070506u; case 4: return 0x060C0906u; case 5: return 0x060C0909u;
+    case 6: return 0x00000A0Bu; case 7: return 0x0000120Fu; case 8: return 0x00001212u;
+    case 9: return 0x00070707u; case 10: return 0x000C0F06u; case 11: return 0x000C0C0Cu;
+    case 12: return 0x03060606u; case 13: return 0x06090C06u; case 14: return 0x0609090Cu;
+    case 15: return 0x00050808u; case 16: return 0x00091206u; default: return 0x00090C0Fu;
+    }
+}
+
+/* slen / partition selection (minimp3.h:666-687) */
+MP3_HD ScfLayout scf_layout(const GcDesc &d)
+{
+    ScfLayout L;
+    const int kind = d.n_short_sfb ? (d.n_long_sfb ? 1 : 2) : 0;
+    uint32_t part;
+    if (d.flags1 & GCF1_MPEG1)
+    {
+        /* ISO slen1 / slen2 per scalefac_compress, one nibble each */
+        const uint64_t slen1 = 0x4433322211130000ull, slen2 = 0x3232132132103210ull;
+        const int sh = (d.scalefac_compress & 15)*4;
+        const int s1 = (int)((slen1 >> sh) & 15), s2 = (int)((slen2 >> sh) & 15);
+        L.size[0] = L.size[1] = (uint8_t)s1;
+        L.size[2] = L.size[3] = (uint8_t)s2;
+        part = scf_partition_mpeg1(kind);
+    } else
+    {
+        const bool ist = (d.flags0 & GCF_I_STEREO) && (d.flags1 & GCF1_CH);
+        int sfc = d.scalefac_compress >> (ist ? 1 : 0);
+        int tn;
+        int s0, s1, s2, s3 = 0;
+        if (!ist)
+        {
+            if (sfc < 400)      { tn = 0; s0 = (sfc >> 4)/5; s1 = (sfc >> 4)%5; s2 = (sfc & 15) >> 2; s3 = sfc & 3; }
+            else if (sfc < 500) { tn = 1; sfc -= 400; s0 = (sfc >> 2)/5; s1 = (sfc >> 2)%5; s2 = sfc & 3; }
+            else                { tn = 2; sfc -= 500; s0 = sfc/3; s1 = sfc%3; s2 = 0; }
+        } else
+        {
+            if (sfc < 180)      { tn = 3; s0 = sfc/36; s1 = (sfc%36)/6; s2 = sfc%6; }
+            else if (sfc < 244) { tn = 4; sfc -= 180; s0 = (sfc & 63) >> 4; s1 = (sfc & 15) >> 2; s2 = sfc & 3; }
+            else                { tn = 5; sfc -= 244; s0 = sfc/3; s1 = sfc%3; s2 = 0; }
+        }
+        L.size[0] = (uint8_t)s0; L.size[1] = (uint8_t)s1; L.size[2] = (uint8_t)s2; L.size[3] = (uint8_t)s3;
+        part = scf_partition_lsf(tn, kind);
+    }
+    L.count[0] = (uint8_t)part; L.count[1] = (uint8_t)(part >> 8); L.count[2] = (uint8_t)(part >> 16); L.count[3] = (uint8_t)(part >> 24);
+    return L;
+}
+
+/* L3_read_scalefactors (minimp3.h:609-640).  dst/prev are byte arrays with element stride `st`.
+ * prev == nullptr means "no previous granule": copied partitions read as zero.  Returns bands read. */
+MP3_HD int read_scalefactors(BitRd &br, const ScfLayout &L, int scfsi, bool lsf, uint8_t *dst, const uint8_t *prev,
+                             int st, uint8_t *ist_out)
+{
+    int idx = 0;
+    for (int p = 0; p < 4 && L.count[p]; p++, scfsi *= 2)
+    {
+        const int cnt = L.count[p];
+        const int bits = L.size[p];
+        const bool copy = (scfsi & 8) != 0;
+        const int max_scf = lsf ? (1 << bits) - 1 : -1;
+        for (int k = 0; k < cnt; k++)
+        {
+            int s = 0, ist = 0;
+            if (copy) { s = prev ? prev[(idx + k)*st] : 0; ist = s; }
+            else if (bits) { s = (int)br.get(bits); ist = (s == max_scf) ? 255 : s; }
+            dst[(idx + k)*st] = (uint8_t)s;
+            if (ist_out) ist_out[idx + k] = (uint8_t)ist;
+        }
+        idx += cnt;
+    }
+    dst[(idx + 0)*st] = 0;
+    dst[(idx + 1)*st] = 0;
+    dst[(idx + 2)*st] = 0;
+    return idx;
+}
+
+enum { EMODE_BIG = 0, EMODE_C1A = 1, EMODE_C1B = 2, EMODE_DONE = 3 };
+
+struct GranuleDecoder
+{
+    BitRd br;
+    const uint8_t *sfbw;      /* band widths of this granule's partition */
+    const uint8_t *iscf;      /* final integer scalefactors, stride iscf_st */
+    int iscf_st;
+    float gain, one;
+    int scf_shift, limit;
+    int mode, big_left, band_left, band_idx, ireg, reg_left, pending, extent, line;
+    uint32_t tinfo;
+    uint8_t table_select[3], region_count[3];
+    bool count1_b;
+
+    /* scalefactors + set-up.  iscf_buf / prev_buf: 40 bytes each at stride st.  d0: descriptor of granule 0
+     * of the same frame/channel when this is granule 1 with scfsi != 0 (else nullptr).
+     * ist_out: optional [40] intensity positions. */
+    MP3_HD void init(const GcDesc &d, const GcDesc *d0, const uint32_t *words, uint64_t n_words, const EntropyTables &T,
+                     uint8_t *iscf_buf, uint8_t *prev_buf, int st, uint8_t *ist_out, int *n_ist)
+    {
+        const bool mpeg1 = (d.flags1 & GCF1_MPEG1) != 0;
+        const uint8_t *prev = nullptr;
+        if (d0)
+        {
+            /* scfsi: bands shared with granule 0 of the same channel -> re-read that granule's part 2 */
+            const ScfLayout L0 = scf_layout(*d0);
+            br.init(words, n_words, d0->bit_off);
+            read_scalefactors(br, L0, d0->scfsi, false, prev_buf, nullptr, st, nullptr);
+            prev = prev_buf;
+        }
+        const ScfLayout L = scf_layout(d);
+        br.init(words, n_words, d.bit_off);
+        const int n_read = read_scalefactors(br, L, mpeg1 ? d.scfsi : 0, !mpeg1, iscf_buf, prev, st, ist_out);
+        if (n_ist) *n_ist = n_read;
+        scf_shift = ((d.flags0 & GCF_SCALEFAC_SCALE) ? 1 : 0) + 1;
+        /* subblock gain / preemphasis (minimp3.h:690-706); uint8 arithmetic wraps like the reference's */
+        if (d.n_short_sfb)
+        {
+            const int sh = 3 - scf_shift;
+            for (int i = 0; i < d.n_short_sfb; i += 3)
+            {
+                iscf_buf[(d.n_long_sfb + i + 0)*st] = (uint8_t)(iscf_buf[(d.n_long_sfb + i + 0)*st] + (d.subblock_gain[0] << sh));
+                iscf_buf[(d.n_long_sfb + i + 1)*st] = (uint8_t)(iscf_buf[(d.n_long_sfb + i + 1)*st] + (d.subblock_gain[1] << sh));
+                iscf_buf[(d.n_long_sfb + i + 2)*st] = (uint8_t)(iscf_buf[(d.n_long_sfb + i + 2)*st] + (d.subblock_gain[2] << sh));
+            }
+        } else if (d.flags0 & GCF_PREFLAG)
+        {
+            /* ISO pretab for bands 11..20: 1 1 1 1 2 2 3 3 3 2, two bits each */
+            const uint32_t pretab = 0xBFA55u;
+            for (int i = 0; i < 10; i++)
+                iscf_buf[(11 + i)*st] = (uint8_t)(iscf_buf[(11 + i)*st] + ((pretab >> (2*i)) & 3));
+        }
+        iscf = iscf_buf;
+        iscf_st = st;
+        /* global gain (minimp3.h:708-709): BITS_DEQUANTIZER_OUT = -1, MAX_SCFI = 44 */
+        const int gain_exp = (int)d.global_gain - 4 - 210 - ((d.flags0 & GCF_MS_STEREO) ? 2 : 0);
+        gain = l3_ldexp_q2(2048.0f, 44 - gain_exp);
+
+        sfbw = d.n_short_sfb ? (d.n_long_sfb ? T.sfb_mixed + d.sr_idx*40 : T.sfb_short + d.sr_idx*40)
+                             : T.sfb_long + d.sr_idx*23;
+        limit = d.part_23_length;
+        mode = d.big_values ? EMODE_BIG : EMODE_C1A;
+        big_left = d.big_values;
+        band_left = 0; band_idx = 0;
+        ireg = 0;
+        for (int i = 0; i < 3; i++) { table_select[i] = d.table_select[i]; region_count[i] = d.region_count[i]; }
+        reg_left = region_count[0] + 1;
+        tinfo = T.tabinfo[table_select[0]];
+        one = 0.f;
+        pending = 0; extent = 0; line = 0;
+        count1_b = (d.flags0 & GCF_COUNT1_TABLE) != 0;
+    }
+
+    MP3_HD float band_scale(int b) const { return l3_ldexp_q2(gain, (int)iscf[b*iscf_st] << scf_shift); }
+
+    /* next two lines; q0/q1 receive the signed quantised values */
+    MP3_HD void step(const EntropyTables &T, float &v0, float &v1, int &q0, int &q1)
+    {
+        v0 = v1 = 0.f;
+        q0 = q1 = 0;
+        const int this_line = line;
+        line += 2;
+        if (mode == EMODE_DONE) return;
+        if (mode == EMODE_C1A)
+        {
+            /* count1 quad code; stop when it ends past the granule's bit budget (minimp3.h:852-864) */
+            br.refill();
+            int len, vwxy;
+            if (count1_b) { len = 4; vwxy = (int)((~br.peek(4)) & 15); }
+            else { const int e = T.count1a[br.peek(6)]; len = e >> 4; vwxy = e & 15; }
+            br.skip(len);
+            if (br.pos > limit) { mode = EMODE_DONE; return; }
+            pending = vwxy;
+        }
+        if (band_left == 0)
+        {
+            const int wd = sfbw[band_idx];
+            if (!wd) { mode = EMODE_DONE; return; }
+            band_left = wd >> 1;
+            one = band_scale(band_idx);
+            band_idx++;
+            if (mode == EMODE_BIG)
+            {
+                if (reg_left == 0)
+                {
+                    ireg++;
+                    const int ts = ireg == 1 ? table_select[1] : table_select[2];
+                    const int rc = ireg == 1 ? region_count[1] : region_count[2];
+                    tinfo = T.tabinfo[ts];
+                    reg_left = rc + 1;
+                }
+                reg_left--;
+            }
+        }
+        if (mode == EMODE_BIG)
+        {
+            const int base = (int)(tinfo & 0xFFFF), rootw = (int)((tinfo >> 16) & 15), linbits = (int)((tinfo >> 20) & 15);
+            int x = 0, y = 0;
+            br.refill();
+            if (rootw)
+            {
+                int e = T.lut[base + br.peek(rootw)];
+                int wcur = rootw;
+                while (e & 0x8000)
+                {
+                    br.skip(wcur);
+                    wcur = (e >> 11) & 15;
+                    e = T.lut[base + (e & 0x7FF) + br.peek(wcur)];
+                }
+                br.skip(e >> 8);
+                x = (e >> 4) & 15;
+                y = e & 15;
+            }
+            br.refill();
+            if (x == 15 && linbits) { x += (int)br.peek(linbits); br.skip(linbits); br.refill(); }
+            if (x)
+            {
+                const int neg = (int)br.peek(1); br.skip(1);
+                const float m = MP3_FMUL(one, l3_pow43(x, T.pow43));
+                v0 = neg ? -m : m; q0 = neg ? -x : x;
+            }
+            br.refill();
+            if (y == 15 && linbits) { y += (int)br.peek(linbits); br.skip(linbits); br.refill(); }
+            if (y)
+            {
+                const int neg = (int)br.peek(1); br.skip(1);
+                const float m = MP3_FMUL(one, l3_pow43(y, T.pow43));
+                v1 = neg ? -m : m; q1 = neg ? -y : y;
+            }
+            if (--big_left == 0) mode = EMODE_C1A;
+        } else
+        {
+            const int hi = (mode == EMODE_C1A) ? 8 : 2;
+            br.refill();
+            if (pending & hi) { const int neg = (int)br.peek(1); br.skip(1); v0 = neg ? -one : one; q0 = neg ? -1 : 1; }
+            if (pending & (hi >> 1)) { const int neg = (int)br.peek(1); br.skip(1); v1 = neg ? -one : one; q1 = neg ? -1 : 1; }
+            mode = (mode == EMODE_C1A) ? EMODE_C1B : EMODE_C1A;
+        }
+        band_left--;
+        extent = this_line + 2;
+    }
+};
+
+}  // namespace mp3b
+#endif
