@@ -127,6 +127,8 @@ typedef struct
 mp3dec_batch_plan_t *mp3dec_batch_plan_create(const mp3dec_batch_stream_t *streams, int n_streams,
                                               const mp3dec_batch_opts_t *opts, int *err);
 int mp3dec_batch_plan_run(mp3dec_batch_plan_t *plan);
+/* measurement aid: one stage only (0 entropy, 1 intensity stereo, 2 transform) */
+int mp3dec_batch_plan_run_stage(mp3dec_batch_plan_t *plan, int stage);
 int mp3dec_batch_plan_sync(mp3dec_batch_plan_t *plan);
 int mp3dec_batch_plan_fetch(mp3dec_batch_plan_t *plan, mp3dec_file_info_t *infos_out, int *rets_out);
 void mp3dec_batch_plan_stats(const mp3dec_batch_plan_t *plan, mp3dec_batch_stats_t *out);

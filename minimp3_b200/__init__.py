@@ -56,7 +56,7 @@ class BatchStats(C.Structure):
 
 EXPORTS = ["mp3dec_init", "mp3dec_decode_frame", "mp3dec_decode_frame_f32", "mp3dec_f32_to_s16", "mp3dec_detect_buf",
            "mp3dec_load_buf", "mp3dec_load_buf_f32", "mp3dec_decode_batch_cuda", "mp3dec_batch_plan_create",
-           "mp3dec_batch_plan_run", "mp3dec_batch_plan_sync", "mp3dec_batch_plan_fetch", "mp3dec_batch_plan_stats",
+           "mp3dec_batch_plan_run", "mp3dec_batch_plan_run_stage", "mp3dec_batch_plan_sync", "mp3dec_batch_plan_fetch", "mp3dec_batch_plan_stats",
            "mp3dec_batch_plan_device_pcm", "mp3dec_batch_plan_destroy", "mp3dec_batch_plan_enable_taps",
            "mp3dec_batch_plan_read_tap", "mp3dec_batch_shard", "mp3dec_b200_version"]
 
@@ -88,9 +88,11 @@ def load():
                                            C.POINTER(BatchOpts)]
     L.mp3dec_batch_plan_create.argtypes = [C.POINTER(BatchStream), C.c_int, C.POINTER(BatchOpts), C.POINTER(C.c_int)]
     L.mp3dec_batch_plan_create.restype = vp
-    for name in ("mp3dec_batch_plan_run", "mp3dec_batch_plan_sync", "mp3dec_batch_plan_enable_taps"):
+    for name in ("mp3dec_batch_plan_run", "mp3dec_batch_plan_run_stage", "mp3dec_batch_plan_sync", "mp3dec_batch_plan_enable_taps"):
         getattr(L, name).argtypes = [vp]
         getattr(L, name).restype = C.c_int
+    L.mp3dec_batch_plan_run_stage.argtypes = [vp, C.c_int]
+    L.mp3dec_batch_plan_run_stage.restype = C.c_int
     L.mp3dec_batch_plan_fetch.argtypes = [vp, C.POINTER(FileInfo), C.POINTER(C.c_int)]
     L.mp3dec_batch_plan_stats.argtypes = [vp, C.POINTER(BatchStats)]
     L.mp3dec_batch_plan_stats.restype = None
@@ -162,6 +164,11 @@ class BatchPlan:
         r = self.L.mp3dec_batch_plan_run(self.handle)
         if r:
             raise RuntimeError("mp3dec_batch_plan_run failed: %d" % r)
+
+    def run_stage(self, stage):
+        r = self.L.mp3dec_batch_plan_run_stage(self.handle, int(stage))
+        if r:
+            raise RuntimeError("mp3dec_batch_plan_run_stage failed: %d" % r)
 
     def sync(self):
         r = self.L.mp3dec_batch_plan_sync(self.handle)

@@ -364,7 +364,18 @@ int mp3dec_batch_plan_enable_taps(mp3dec_batch_plan_t *P)
     return 0;
 }
 
-int mp3dec_batch_plan_run(mp3dec_batch_plan_t *P)
+static int plan_run_stages(mp3dec_batch_plan_t *P, int stage_mask);
+
+int mp3dec_batch_plan_run(mp3dec_batch_plan_t *P) { return plan_run_stages(P, 7); }
+
+/* measurement aid: launch a single stage (0 entropy, 1 intensity stereo, 2 transform) on the plan's stream */
+int mp3dec_batch_plan_run_stage(mp3dec_batch_plan_t *P, int stage)
+{
+    if (stage < 0 || stage > 2) return MP3D_E_PARAM;
+    return plan_run_stages(P, 1 << stage);
+}
+
+static int plan_run_stages(mp3dec_batch_plan_t *P, int stage_mask)
 {
     if (!P) return MP3D_E_PARAM;
     cudaSetDevice(P->ctx->device);
@@ -387,8 +398,9 @@ int mp3dec_batch_plan_run(mp3dec_batch_plan_t *P)
     ea.ist_pos = (uint8_t *)B.d_istpos.p;
     ea.tap_q = P->taps ? (int16_t *)B.d_tap_q.p : nullptr;
     ea.tap_scf = P->taps ? (float *)B.d_tap_scf.p : nullptr;
-    cudaError_t e = launch_entropy(P->ctx->tables, ea, P->stream);
-    if (e == cudaSuccess && P->n_ist)
+    cudaError_t e = cudaSuccess;
+    if (stage_mask & 1) e = launch_entropy(P->ctx->tables, ea, P->stream);
+    if (e == cudaSuccess && P->n_ist && (stage_mask & 2))
     {
         StereoArgs sa;
         sa.gcs = ea.gcs;
@@ -399,7 +411,7 @@ int mp3dec_batch_plan_run(mp3dec_batch_plan_t *P)
         sa.ist_pos = ea.ist_pos;
         e = launch_intensity_stereo(P->ctx->tables, sa, P->stream);
     }
-    if (e == cudaSuccess)
+    if (e == cudaSuccess && (stage_mask & 4))
     {
         TransformArgs ta;
         memset(&ta, 0, sizeof(ta));
