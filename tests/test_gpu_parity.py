@@ -1,0 +1,208 @@
+"""Parity of the CUDA path (through the C ABI) with the unmodified reference, on a B200.
+
+Bar (BASELINE.json north_star): Huffman-decoded integer spectra and scalefactors bit-exact; PCM within
++-1 LSB int16 of minimp3's own output; FLOAT_OUTPUT within 1e-5 abs; PSNR > 96 dB on every bundled
+Layer III conformance vector.
+"""
+import ctypes as C
+import hashlib
+
+import numpy as np
+import pytest
+
+import conftest
+from conftest import L3_CONFORMANCE, L3_SMOKE, load_iso_pcm, load_vector, psnr
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def m():
+    import minimp3_b200
+    minimp3_b200.load()
+    return minimp3_b200
+
+
+def real_rows(desc):
+    body = desc[:, :28].astype(np.int64).sum(axis=1)
+    return np.where(~((body == 0) & (desc[:, 29] == 1)))[0]
+
+
+@pytest.mark.parametrize("name", L3_CONFORMANCE)
+def test_stage_taps_bit_exact_and_pcm_within_one_lsb(name, m, ref):
+    data = load_vector(name)
+    t = ref.tap_stream(data)
+    p = m.BatchPlan([data], raw_frames=True)
+    p.enable_taps()
+    p.run()
+    rets, outs = p.fetch()
+    desc, q, scf, xr, sub, nzl = (p.read_tap(k) for k in (4, 0, 1, 2, 3, 6))
+    p.close()
+    rows = real_rows(desc)
+    assert rets[0] == 0 and len(rows) == len(t["rec"])
+    assert np.array_equal(q[rows], t["q"])                                   # integer spectra
+    for i, r in enumerate(t["rec"]):
+        n = r.n_long_sfb + r.n_short_sfb
+        assert np.array_equal(scf[rows[i], :n].view(np.uint32), t["scf"][i, :n].view(np.uint32))   # scalefactors
+    xrz = xr[rows].copy()
+    for i, g in enumerate(rows):
+        xrz[i, nzl[g]:] = 0
+    assert np.array_equal(xrz.view(np.uint32), t["xr_stereo"].view(np.uint32))   # requantised + stereo, bitwise
+    scale = max(1.0, float(np.abs(t["sub"]).max()))
+    assert np.abs(sub[rows] - t["sub"]).max() <= 2e-6*scale                  # hybrid filterbank output
+    pcm = outs[0]["pcm"]
+    assert len(pcm) == len(t["pcm"])
+    d = np.abs(pcm.astype(np.int32) - t["pcm"].astype(np.int32))
+    assert d.max() <= 1 and (d != 0).mean() < 0.01
+
+
+@pytest.mark.parametrize("name", L3_CONFORMANCE)
+def test_conformance_psnr(name, m, manifest):
+    """minimp3_test.c:391-428 on the CUDA output: sample-count rule and PSNR >= 96 dB against the ISO PCM"""
+    data = load_vector(name)
+    rets, outs = m.mp3dec_decode_batch_cuda([data], allow_mono_stereo=True)
+    pcm = outs[0]["pcm"]
+    iso = load_iso_pcm(name)
+    assert rets[0] == 0
+    assert len(pcm) in (len(iso), len(iso) + 1152, len(iso) + 2304)
+    md, ps = psnr(pcm, iso)
+    assert ps >= 96.0 and md <= 2
+    assert abs(ps - manifest[name]["ref_psnr"]) < 0.5
+
+
+@pytest.mark.parametrize("name", ["l3-nonstandard-compl-sideinfo-bigvalues", "l3-nonstandard-compl-sideinfo-blocktype",
+                                  "l3-nonstandard-compl-sideinfo-size", "l3-nonstandard-he_44_48khz",
+                                  "l3-nonstandard-sin1k0db_lame_vbrtag", "l3-nonstandard-id3v1", "l3-nonstandard-id3v2",
+                                  "l3-nonstandard-apetag", "l3-nonstandard-vbrtag-only", "l3-nonstandard-small"])
+def test_load_buf_semantics_on_regression_vectors(name, m, ref):
+    """mp3dec_load_buf through the C entry point: return code, sample count, PCM (+-1 LSB) as the reference"""
+    data = load_vector(name)
+    want_ret, want_pcm, want_info = ref.load_buf(data)
+    L = m.load()
+    # the reference test binary allows mono/stereo transitions; none of these vectors has one
+    ret, pcm, info = m.mp3dec_load_buf(data)
+    assert ret == want_ret
+    assert len(pcm) == len(want_pcm)
+    if len(pcm):
+        assert np.abs(pcm.astype(np.int32) - want_pcm.astype(np.int32)).max() <= 1
+    for k in ("hz", "layer", "avg_bitrate_kbps", "channels"):
+        assert info[k] == want_info[k], k
+
+
+@pytest.mark.parametrize("name", ["l3-sin1k0db", "l3-he_mode", "M2L3_bitrate_22_all", "l3-si_block"])
+def test_float_output_within_1e5(name, m, ref_f32):
+    data = load_vector(name)
+    want, _ = ref_f32.decode_frames(data)
+    rets, outs = m.mp3dec_decode_batch_cuda([data], raw_frames=True, float_output=True)
+    got = outs[0]["pcm"]
+    assert got.dtype == np.float32 and len(got) == len(want)
+    assert np.abs(got - want).max() <= 1e-5
+
+
+@pytest.mark.parametrize("name", ["l3-compl", "l3-he_mode", "l3-si_block", "M2L3_compl24", "l3-he_free"])
+def test_frame_api_matches_reference(name, m, ref):
+    """mp3dec_init + mp3dec_decode_frame loop (README usage): per-call return value, frame_bytes, info and PCM"""
+    data = load_vector(name)
+    want_pcm, want_frames = ref.decode_frames(data)
+    pcm, frames = m.decode_frames(data)
+    assert len(frames) == len(want_frames)
+    for a, b in zip(frames, want_frames):
+        assert (a["samples"], a["frame_bytes"]) == (b.samples, b.frame_bytes)
+        if b.frame_bytes and b.samples:
+            assert (a["frame_offset"], a["channels"], a["hz"], a["layer"], a["bitrate_kbps"]) == \
+                   (b.frame_offset, b.channels, b.hz, b.layer, b.bitrate_kbps)
+    assert len(pcm) == len(want_pcm)
+    assert np.abs(pcm.astype(np.int32) - want_pcm.astype(np.int32)).max() <= 1
+
+
+def test_frame_api_parse_only(m):
+    L = m.load()
+    data = np.frombuffer(load_vector("l3-compl"), dtype=np.uint8)
+    dec, info = m.Mp3Dec(), m.FrameInfo()
+    L.mp3dec_init(C.byref(dec))
+    n = L.mp3dec_decode_frame(C.byref(dec), data.ctypes.data, len(data), None, C.byref(info))
+    assert n == 1152 and info.hz == 48000 and info.channels == 1 and info.layer == 3 and info.frame_bytes > 0
+
+
+def test_ragged_batch_matches_single_stream_decodes(m, ref):
+    """one call, streams of very different length / format, including empty and garbage buffers"""
+    names = ["l3-si_huff", "l3-sin1k0db", "l3-nonstandard-small", "M2L3_bitrate_16_all", "l3-he_mode", "l3-he_free",
+             "l3-nonstandard-id3v2-only", "l3-test46"]
+    datas = [load_vector(n) for n in names] + [b"", b"\xff"*777]
+    rets, outs = m.mp3dec_decode_batch_cuda(datas, raw_frames=True)
+    for d, r, o in zip(datas, rets, outs):
+        want, _ = ref.decode_frames(d)
+        assert r == 0 and len(o["pcm"]) == len(want)
+        if len(want):
+            assert np.abs(o["pcm"].astype(np.int32) - want.astype(np.int32)).max() <= 1
+
+
+def test_batch_is_deterministic_and_order_independent(m):
+    names = ["l3-si_block", "l3-compl", "l3-he_mode", "M2L3_noise"]
+    datas = [load_vector(n) for n in names]
+    _, a = m.mp3dec_decode_batch_cuda(datas, raw_frames=True)
+    _, b = m.mp3dec_decode_batch_cuda(datas[::-1], raw_frames=True)
+    for x, y in zip(a, b[::-1]):
+        assert np.array_equal(x["pcm"], y["pcm"])
+
+
+def test_full_size_batch_properties(m, ref):
+    """BASELINE.json configs[1] at full size: 1024 x l3-sin1k0db.  Every stream must produce the same PCM as a
+    single-stream decode (checksum of checksums), which in turn is within 1 LSB of the reference."""
+    data = load_vector("l3-sin1k0db")
+    want, _ = ref.decode_frames(data)
+    _, one = m.mp3dec_decode_batch_cuda([data])
+    assert np.abs(one[0]["pcm"].astype(np.int32) - want.astype(np.int32)).max() <= 1
+    h1 = hashlib.sha256(one[0]["pcm"].tobytes()).hexdigest()
+    rets, outs = m.mp3dec_decode_batch_cuda([data]*1024)
+    assert all(r == 0 for r in rets)
+    assert sum(o["samples"] for o in outs) == 1024*725760
+    assert {hashlib.sha256(o["pcm"].tobytes()).hexdigest() for o in outs} == {h1}
+
+
+def test_mixed_block_and_lsf_batches(m, ref):
+    """BASELINE.json configs[2] and [3], 64 streams each, cycled"""
+    for names in (["l3-si_block", "l3-he_mode", "l3-si_huff"],
+                  ["M2L3_bitrate_16_all", "M2L3_bitrate_22_all", "M2L3_bitrate_24_all", "M2L3_compl24", "l3-he_free"]):
+        datas = [load_vector(names[i % len(names)]) for i in range(64)]
+        wants = {n: ref.decode_frames(load_vector(n))[0] for n in names}
+        rets, outs = m.mp3dec_decode_batch_cuda(datas, raw_frames=True)
+        for i, o in enumerate(outs):
+            w = wants[names[i % len(names)]]
+            assert rets[i] == 0 and len(o["pcm"]) == len(w)
+            assert np.abs(o["pcm"].astype(np.int32) - w.astype(np.int32)).max() <= 1
+
+
+def test_sharding_is_invisible_in_the_output(m):
+    """multi-GPU path on one device: decode the shards of n_gpus in {1,2,4,8} separately, same bytes out"""
+    names = ["l3-si_block", "l3-compl", "l3-he_mode", "M2L3_noise", "l3-si_huff", "l3-he_free", "l3-si", "l3-hecommon",
+             "M2L3_compl24"]
+    datas = [load_vector(n) for n in names]
+    _, whole = m.mp3dec_decode_batch_cuda(datas, raw_frames=True)
+    for n_shards in (2, 4, 8):
+        shard_of = m.shard_streams([len(d) for d in datas], n_shards)
+        assert set(shard_of) <= set(range(n_shards))
+        for s in range(n_shards):
+            ids = [i for i, v in enumerate(shard_of) if v == s]
+            if not ids:
+                continue
+            _, part = m.mp3dec_decode_batch_cuda([datas[i] for i in ids], raw_frames=True)
+            for i, o in zip(ids, part):
+                assert np.array_equal(o["pcm"], whole[i]["pcm"])
+
+
+def test_layer12_is_refused_loudly(m):
+    rets, outs = m.mp3dec_decode_batch_cuda([load_vector("l2-fl10"), load_vector("l3-si_huff")])
+    assert rets[0] == m.MP3D_E_UNSUPPORTED and outs[0]["samples"] == 0
+    assert rets[1] == 0 and outs[1]["samples"] == 86400
+
+
+def test_f32_to_s16(m, ref_f32):
+    rng = np.random.default_rng(3)
+    x = np.concatenate([rng.uniform(-1.2, 1.2, 10007), np.array([0.5/32768, -0.5/32768, 1.5/32768, -1.5/32768, 1.0, -1.0])]).astype(np.float32)
+    out = np.zeros(len(x), np.int16)
+    m.load().mp3dec_f32_to_s16(x.ctypes.data, out.ctypes.data, len(x))
+    want = np.zeros(len(x), np.int16)
+    ref_f32.lib.mp3dec_f32_to_s16.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    ref_f32.lib.mp3dec_f32_to_s16(x.ctypes.data, want.ctypes.data, len(x))
+    assert np.array_equal(out, want)
