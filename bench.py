@@ -246,7 +246,7 @@ def main():
         t1 = time.perf_counter()
         if i >= 2:
             e2e_ms.append((t1 - t0)*1e3)
-        h2d = int(p.stats["input_bytes"]) + 32*int(p.stats["n_granule_channels"]) + 32*int(p.stats["n_tiles"])
+        h2d = int(p.stats["h2d_bytes"])
         parse_ms, h2d_ms = p.stats["host_parse_ms"], p.stats["h2d_ms"]
         n_out = sum(o["samples"] for o in outs)
         p.close()

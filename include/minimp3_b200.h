@@ -120,6 +120,7 @@ typedef struct
     uint64_t input_bytes;        /* bytes of frame payload staged to the device */
     uint64_t samples;            /* channel-inclusive samples the kernels write */
     uint64_t n_granule_channels, n_tiles, n_istereo_granules, n_frames;
+    uint64_t h2d_bytes;          /* bytes copied host to device by plan creation */
     int kernels_per_run;         /* kernel launches one mp3dec_batch_plan_run() issues */
     double host_parse_ms, h2d_ms;
 } mp3dec_batch_stats_t;

@@ -51,6 +51,7 @@ class BatchOpts(C.Structure):
 class BatchStats(C.Structure):
     _fields_ = [("input_bytes", C.c_uint64), ("samples", C.c_uint64), ("n_granule_channels", C.c_uint64),
                 ("n_tiles", C.c_uint64), ("n_istereo_granules", C.c_uint64), ("n_frames", C.c_uint64),
+                ("h2d_bytes", C.c_uint64),
                 ("kernels_per_run", C.c_int), ("host_parse_ms", C.c_double), ("h2d_ms", C.c_double)]
 
 

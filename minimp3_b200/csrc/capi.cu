@@ -96,13 +96,13 @@ struct PinBuf
 /* all device + pinned memory of one in-flight batch; recycled between calls */
 struct BufferSet
 {
-    PinBuf h_md, h_gcs, h_tiles, h_ist, h_pcm;
-    DevBuf d_md, d_gcs, d_tiles, d_istlist, d_xr, d_nzl, d_istpos, d_pcm;
+    PinBuf h_md, h_gcs, h_tiles, h_ist, h_order, h_pcm;
+    DevBuf d_md, d_gcs, d_tiles, d_istlist, d_order, d_xr, d_nzl, d_istpos, d_pcm;
     DevBuf d_tap_q, d_tap_scf, d_tap_sub;
     void release()
     {
-        h_md.release(); h_gcs.release(); h_tiles.release(); h_ist.release(); h_pcm.release();
-        d_md.release(); d_gcs.release(); d_tiles.release(); d_istlist.release(); d_xr.release(); d_nzl.release();
+        h_md.release(); h_gcs.release(); h_tiles.release(); h_ist.release(); h_order.release(); h_pcm.release();
+        d_md.release(); d_gcs.release(); d_tiles.release(); d_istlist.release(); d_order.release(); d_xr.release(); d_nzl.release();
         d_istpos.release(); d_pcm.release(); d_tap_q.release(); d_tap_scf.release(); d_tap_sub.release();
     }
 };
@@ -180,8 +180,8 @@ struct mp3dec_batch_plan
     cudaStream_t stream = nullptr;
     int n_streams = 0;
     std::vector<StreamPlan> plans;
-    std::vector<uint64_t> md_base, gc_base, tile_base, pcm_base, ist_base;
-    uint64_t md_bytes = 0, n_gc = 0, n_tiles = 0, n_samples = 0, n_ist = 0, n_frames = 0, input_bytes = 0;
+    std::vector<uint64_t> md_base, gc_base, tile_base, pcm_base, ist_base, order_base;
+    uint64_t md_bytes = 0, n_gc = 0, n_tiles = 0, n_samples = 0, n_ist = 0, n_order = 0, n_frames = 0, input_bytes = 0;
     size_t sample_size = 2;
     bool taps = false;
     bool fetched_pinned = false;
@@ -262,12 +262,13 @@ mp3dec_batch_plan_t *mp3dec_batch_plan_create(const mp3dec_batch_stream_t *strea
 
     /* ---- host stage 2: prefix sums and rebasing into the shared tables ---- */
     P->gc_base.resize(n_streams + 1); P->tile_base.resize(n_streams + 1);
-    P->pcm_base.resize(n_streams + 1); P->ist_base.resize(n_streams + 1);
-    uint64_t gcs = 0, tiles = 0, samples = 0, ists = 0;
+    P->pcm_base.resize(n_streams + 1); P->ist_base.resize(n_streams + 1); P->order_base.resize(n_streams + 1);
+    uint64_t gcs = 0, tiles = 0, samples = 0, ists = 0, orders = 0;
     for (int i = 0; i < n_streams; i++)
     {
         const StreamPlan &sp = P->plans[i];
-        P->gc_base[i] = gcs; P->tile_base[i] = tiles; P->pcm_base[i] = samples; P->ist_base[i] = ists;
+        P->gc_base[i] = gcs; P->tile_base[i] = tiles; P->pcm_base[i] = samples; P->ist_base[i] = ists; P->order_base[i] = orders;
+        orders += sp.order.size();
         gcs += round_up(sp.gcs.size(), 2);
         tiles += sp.tiles.size();
         samples += sp.samples_decoded;
@@ -276,15 +277,16 @@ mp3dec_batch_plan_t *mp3dec_batch_plan_create(const mp3dec_batch_stream_t *strea
         P->input_bytes += sp.main_data_bytes;
     }
     P->gc_base[n_streams] = gcs; P->tile_base[n_streams] = tiles; P->pcm_base[n_streams] = samples; P->ist_base[n_streams] = ists;
-    P->n_gc = gcs; P->n_tiles = tiles; P->n_samples = samples; P->n_ist = ists;
+    P->n_gc = gcs; P->n_tiles = tiles; P->n_samples = samples; P->n_ist = ists; P->n_order = orders;
     if (gcs >= (1ull << 31)) { *err = MP3D_E_PARAM; mp3dec_batch_plan_destroy(P); return nullptr; }
 
     bool ok = B.h_gcs.ensure((size_t)gcs*sizeof(GcDesc) + 64) && B.h_tiles.ensure((size_t)tiles*sizeof(TileDesc) + 64) &&
-              B.h_ist.ensure((size_t)ists*4 + 64);
+              B.h_ist.ensure((size_t)ists*4 + 64) && B.h_order.ensure((size_t)orders*4 + 64);
     if (!ok) { *err = MP3D_E_MEMORY; mp3dec_batch_plan_destroy(P); return nullptr; }
     GcDesc *h_gcs = (GcDesc *)B.h_gcs.p;
     TileDesc *h_tiles = (TileDesc *)B.h_tiles.p;
     uint32_t *h_ist = (uint32_t *)B.h_ist.p;
+    uint32_t *h_order = (uint32_t *)B.h_order.p;
     parallel_for(n_streams, opts.host_threads, [&](int i) {
         StreamPlan &sp = P->plans[i];
         const uint64_t gb = P->gc_base[i];
@@ -307,6 +309,8 @@ mp3dec_batch_plan_t *mp3dec_batch_plan_create(const mp3dec_batch_stream_t *strea
             h_tiles[P->tile_base[i] + k] = t;
         }
         for (size_t k = 0; k < sp.istereo_gcs.size(); k++) h_ist[P->ist_base[i] + k] = sp.istereo_gcs[k] + (uint32_t)gb;
+        for (size_t k = 0; k < sp.order.size(); k++) h_order[P->order_base[i] + k] = sp.order[k] + (uint32_t)gb;
+        std::vector<uint32_t>().swap(sp.order);
         /* descriptor vectors are no longer needed on the host */
         std::vector<GcDesc>().swap(sp.gcs);
         std::vector<TileDesc>().swap(sp.tiles);
@@ -318,6 +322,7 @@ mp3dec_batch_plan_t *mp3dec_batch_plan_create(const mp3dec_batch_stream_t *strea
     /* ---- device buffers + H2D ---- */
     ok = B.d_md.ensure(P->md_bytes) && B.d_gcs.ensure((size_t)gcs*sizeof(GcDesc) + 64) &&
          B.d_tiles.ensure((size_t)tiles*sizeof(TileDesc) + 64) && B.d_istlist.ensure((size_t)ists*4 + 64) &&
+         B.d_order.ensure((size_t)orders*4 + 64) &&
          B.d_xr.ensure((size_t)gcs*576*sizeof(float) + 64) && B.d_nzl.ensure((size_t)gcs*2 + 64) &&
          B.d_istpos.ensure((size_t)gcs*40 + 64) && B.d_pcm.ensure((size_t)samples*P->sample_size + 64);
     if (!ok) { *err = MP3D_E_MEMORY; mp3dec_batch_plan_destroy(P); return nullptr; }
@@ -328,6 +333,7 @@ mp3dec_batch_plan_t *mp3dec_batch_plan_create(const mp3dec_batch_stream_t *strea
     if (gcs) cudaMemcpyAsync(B.d_gcs.p, B.h_gcs.p, (size_t)gcs*sizeof(GcDesc), cudaMemcpyHostToDevice, P->stream);
     if (tiles) cudaMemcpyAsync(B.d_tiles.p, B.h_tiles.p, (size_t)tiles*sizeof(TileDesc), cudaMemcpyHostToDevice, P->stream);
     if (ists) cudaMemcpyAsync(B.d_istlist.p, B.h_ist.p, (size_t)ists*4, cudaMemcpyHostToDevice, P->stream);
+    if (orders) cudaMemcpyAsync(B.d_order.p, B.h_order.p, (size_t)orders*4, cudaMemcpyHostToDevice, P->stream);
     cudaEventRecord(e1, P->stream);
     if (cudaStreamSynchronize(P->stream) != cudaSuccess)
     {
@@ -347,6 +353,7 @@ mp3dec_batch_plan_t *mp3dec_batch_plan_create(const mp3dec_batch_stream_t *strea
     P->stats.n_tiles = tiles;
     P->stats.n_istereo_granules = ists;
     P->stats.n_frames = P->n_frames;
+    P->stats.h2d_bytes = P->md_bytes + gcs*sizeof(GcDesc) + tiles*sizeof(TileDesc) + ists*4 + orders*4;
     P->stats.kernels_per_run = (gcs ? 1 : 0) + (ists ? 1 : 0) + (tiles ? 1 : 0);
     P->stats.host_parse_ms = t1 - t0;
     P->stats.h2d_ms = h2d;
@@ -393,6 +400,8 @@ static int plan_run_stages(mp3dec_batch_plan_t *P, int stage_mask)
     ea.md_n_words = P->md_bytes/4;
     ea.gcs = (const GcDesc *)B.d_gcs.p;
     ea.n_gc = (uint32_t)P->n_gc;
+    ea.order = (const uint32_t *)B.d_order.p;
+    ea.n_order = (uint32_t)P->n_order;
     ea.xr = (float *)B.d_xr.p;
     ea.nzl = (uint16_t *)B.d_nzl.p;
     ea.ist_pos = (uint8_t *)B.d_istpos.p;
@@ -632,7 +641,7 @@ static int decode_frame_impl(mp3dec_t *dec, const uint8_t *mp3, int mp3_bytes, v
         const size_t ss = float_output ? 4 : 2;
         const int n_samples = fp.n_gr*576*fp.nch;
         bool ok = B.h_md.ensure(md_bytes + 4*sizeof(GcDesc) + sizeof(TileDesc) + 64) && B.d_md.ensure(md_bytes) &&
-                  B.d_gcs.ensure(4*sizeof(GcDesc)) && B.d_tiles.ensure(sizeof(TileDesc)) && B.d_istlist.ensure(16) &&
+                  B.d_gcs.ensure(4*sizeof(GcDesc)) && B.d_tiles.ensure(sizeof(TileDesc)) && B.d_istlist.ensure(16) && B.d_order.ensure(16) &&
                   B.d_xr.ensure(4*576*4) && B.d_nzl.ensure(16) && B.d_istpos.ensure(4*40) &&
                   B.d_pcm.ensure(2304*4) && B.h_pcm.ensure(2304*4) && ctx->d_state_in.ensure(1536*4) &&
                   ctx->d_state_out.ensure(1536*4) && ctx->h_state.ensure(2*1536*4);
@@ -669,10 +678,13 @@ static int decode_frame_impl(mp3dec_t *dec, const uint8_t *mp3, int mp3_bytes, v
         cudaMemcpyAsync(B.d_tiles.p, h + md_bytes + sizeof(gcs), sizeof(tile), cudaMemcpyHostToDevice, s);
         cudaMemcpyAsync(ctx->d_state_in.p, hs, 1536*4, cudaMemcpyHostToDevice, s);
         if (n_ist) cudaMemcpyAsync(B.d_istlist.p, ist_list, (size_t)n_ist*4, cudaMemcpyHostToDevice, s);
+        static const uint32_t identity_order[4] = { 0, 1, 2, 3 };
+        cudaMemcpyAsync(B.d_order.p, identity_order, 16, cudaMemcpyHostToDevice, s);
         EntropyArgs ea;
         memset(&ea, 0, sizeof(ea));
         ea.md_words = (const uint32_t *)B.d_md.p; ea.md_n_words = md_bytes/4;
         ea.gcs = (const GcDesc *)B.d_gcs.p; ea.n_gc = 4;
+        ea.order = (const uint32_t *)B.d_order.p; ea.n_order = (uint32_t)n_gc;
         ea.xr = (float *)B.d_xr.p; ea.nzl = (uint16_t *)B.d_nzl.p; ea.ist_pos = (uint8_t *)B.d_istpos.p;
         cudaError_t e = launch_entropy(ctx->tables, ea, s);
         if (e == cudaSuccess && n_ist)

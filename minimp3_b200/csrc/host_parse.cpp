@@ -488,6 +488,24 @@ static void build_tiles(StreamPlan *plan, int tile_granules)
     }
 }
 
+/* Lane order of the entropy kernel: granule-channels of similar main-data size next to each other, so the
+ * 32 lanes of a warp run about the same number of Huffman iterations (counting sort on part_23_length). */
+static void build_order(StreamPlan *plan)
+{
+    const size_t n = plan->gcs.size();
+    std::vector<uint8_t> real(n, 0);
+    for (const GranuleRef &g : plan->granules)
+        for (int c = 0; c < g.nch; c++) real[g.gc + c] = 1;
+    uint32_t count[257];
+    memset(count, 0, sizeof(count));
+    for (size_t i = 0; i < n; i++)
+        if (real[i]) count[(plan->gcs[i].part_23_length >> 4) + 1]++;
+    for (int b = 0; b < 256; b++) count[b + 1] += count[b];
+    plan->order.resize(count[256]);
+    for (size_t i = 0; i < n; i++)
+        if (real[i]) plan->order[count[plan->gcs[i].part_23_length >> 4]++] = (uint32_t)i;
+}
+
 void walk_stream(const uint8_t *buf, size_t size, uint8_t *md_dst, uint64_t md_base_bits,
                  const WalkOptions &opt, StreamPlan *plan)
 {
@@ -631,6 +649,7 @@ void walk_stream(const uint8_t *buf, size_t size, uint8_t *md_dst, uint64_t md_b
     plan->out_samples = delivered;
     if (frames_counted) plan->avg_bitrate_kbps = (int)(bitrate_sum/frames_counted);
     build_tiles(plan, opt.tile_granules);
+    build_order(plan);
 }
 
 }  // namespace mp3b

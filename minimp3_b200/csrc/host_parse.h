@@ -87,6 +87,7 @@ struct StreamPlan
     uint32_t frames = 0, frames_decoded = 0;
     bool has_layer12 = false;
     std::vector<uint32_t> istereo_gcs;  /* stream-relative gc index (channel 0) of granules needing intensity stereo */
+    std::vector<uint32_t> order;        /* real granule-channels sorted by part_23_length: the entropy kernel's lane order */
 };
 
 struct WalkOptions

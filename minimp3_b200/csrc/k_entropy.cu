@@ -1,11 +1,12 @@
 /*
- * k_entropy.cu -- scalefactor decode + Huffman decode + requantisation (+ plain MS stereo).
+ * k_entropy.cu -- scalefactor decode + Huffman decode + requantisation.
  *
- * Restates L3_decode_scalefactors / L3_read_scalefactors (minimp3.h:609-714), L3_huffman
- * (minimp3.h:742-877) and L3_midside_stereo (minimp3.h:879-909) for sm_100a; the per-granule state
- * machine lives in l3_entropy.cuh.
+ * Restates L3_decode_scalefactors / L3_read_scalefactors (minimp3.h:609-714) and L3_huffman
+ * (minimp3.h:742-877) for sm_100a; the per-granule state machine lives in l3_entropy.cuh.  (MS stereo is
+ * applied by the transform kernel while it loads the spectra, intensity stereo by k_stereo.cu.)
  *
- * Mapping: one LANE per granule-channel, one warp per 32 consecutive granule-channels.  Huffman decode
+ * Mapping: one LANE per granule-channel; a warp takes 32 granule-channels of similar main-data size (the host
+ * sorts them, see build_order in host_parse.cpp) so that its lanes finish together.  Huffman decode
  * is serial inside a granule, so the parallelism is across granules; to keep the memory side coalesced
  * the warp runs a SIMT-uniform loop over line pairs (iteration k produces lines 2k, 2k+1 of all 32
  * granule-channels; a count1 quad takes two iterations), stages 64 lines x 32 rows in shared memory and
@@ -76,12 +77,13 @@ __global__ void __launch_bounds__(kWarpsPerBlock*32, 2) k_l3_entropy(EntropyArgs
     T.sfb_long = S.sfb_long; T.sfb_short = S.sfb_short; T.sfb_mixed = S.sfb_mixed;
 
     WarpScratch &W = scratch[warp];
-    const uint32_t n_groups = (a.n_gc + 31)/32;
+    const uint32_t n_groups = (a.n_order + 31)/32;
 
     for (uint32_t group = blockIdx.x*kWarpsPerBlock + warp; group < n_groups; group += gridDim.x*kWarpsPerBlock)
     {
-        const uint32_t gc = group*32 + lane;
-        const bool valid = gc < a.n_gc;
+        const uint32_t item = group*32 + lane;
+        const bool valid = item < a.n_order;
+        const uint32_t gc = valid ? __ldg(a.order + item) : 0u;
         GcDesc d;
         if (valid) d = load_desc(a.gcs + gc);
         else
@@ -137,26 +139,18 @@ __global__ void __launch_bounds__(kWarpsPerBlock*32, 2) k_l3_entropy(EntropyArgs
             {
                 /* ---- flush lines [flushed, 2*iter) of all 32 rows ---- */
                 __syncwarp();
-                const int my_ext = (dec.mode == EMODE_DONE) ? ((dec.extent + 31) & ~31) : 576;
-                const int my_ms = (d.flags1 & GCF1_MS_PLAIN) ? 1 : 0;
+                const int my_ext = !valid ? 0 : (dec.mode == EMODE_DONE) ? ((dec.extent + 31) & ~31) : 576;
                 const int n_lines = 2*iter - flushed;   /* 32 or 64 */
-                for (int r = 0; r < 32; r += 2)
+                for (int r = 0; r < 32; r++)
                 {
-                    int e0 = __shfl_sync(0xffffffffu, my_ext, r);
-                    int e1 = __shfl_sync(0xffffffffu, my_ext, r + 1);
-                    const int ms = __shfl_sync(0xffffffffu, my_ms, r);
-                    if (ms) e0 = e1 = max(e0, e1);
-                    if (flushed >= max(e0, e1)) continue;
-                    const size_t row0 = (size_t)(group*32 + r)*576;
+                    const int e = __shfl_sync(0xffffffffu, my_ext, r);
+                    const uint32_t g = __shfl_sync(0xffffffffu, gc, r);
+                    if (flushed >= e) continue;
+                    float *row = a.xr + (size_t)g*576;
                     for (int c = lane; c < n_lines; c += 32)
                     {
                         const int line = flushed + c;
-                        const int col = line & (kStageLines - 1);
-                        float l = W.stage[col*kStagePitch + r];
-                        float rr = W.stage[col*kStagePitch + r + 1];
-                        if (ms) { const float s = l + rr, dd = l - rr; l = s; rr = dd; }
-                        if (line < e0) a.xr[row0 + line] = l;
-                        if (line < e1) a.xr[row0 + 576 + line] = rr;
+                        if (line < e) row[line] = W.stage[(line & (kStageLines - 1))*kStagePitch + r];
                     }
                 }
                 flushed = 2*iter;
@@ -165,12 +159,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock*32, 2) k_l3_entropy(EntropyArgs
             if (finished) break;
         }
         /* ---- per-row extent for the consumer ---- */
-        {
-            int e = (dec.extent + 31) & ~31;
-            const int other = __shfl_xor_sync(0xffffffffu, e, 1);
-            if (d.flags1 & GCF1_MS_PLAIN) e = max(e, other);
-            if (valid) a.nzl[gc] = (uint16_t)e;
-        }
+        if (valid) a.nzl[gc] = (uint16_t)((dec.extent + 31) & ~31);
         __syncwarp();
     }
 }
@@ -179,14 +168,14 @@ __global__ void __launch_bounds__(kWarpsPerBlock*32, 2) k_l3_entropy(EntropyArgs
 
 cudaError_t launch_entropy(const DeviceTables &, const EntropyArgs &a, cudaStream_t s)
 {
-    if (!a.n_gc) return cudaSuccess;
+    if (!a.n_order) return cudaSuccess;
     const size_t smem = ((sizeof(SharedTables) + 15) & ~15) + sizeof(WarpScratch)*kWarpsPerBlock;
     cudaError_t e = cudaFuncSetAttribute(k_l3_entropy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const uint32_t n_groups = (a.n_gc + 31)/32;
+    const uint32_t n_groups = (a.n_order + 31)/32;
     uint32_t blocks = (n_groups + kWarpsPerBlock - 1)/kWarpsPerBlock;
     const uint32_t max_blocks = (uint32_t)sms*2;
     if (blocks > max_blocks) blocks = max_blocks;

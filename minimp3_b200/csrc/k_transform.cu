@@ -45,6 +45,7 @@ constexpr int kYFloats = 2*kRows*kYPitch;   /* 10494, aliases XS */
 constexpr int kTFloats = kSlots*288;
 static_assert(kYFloats <= kXFloats, "Y must fit in the X region");
 static_assert(GT*32 <= kThreads, "one FIR job per thread");
+static_assert(kXFloats - kYFloats >= GT*2*18*2, "slack behind Y holds the specially rounded outputs");
 
 __constant__ ImdctConsts c_k;
 
@@ -56,6 +57,8 @@ struct SlotMeta
     int n_long;      /* leading subbands that always use the normal long window when mixed_block_flag is
                         set -- for ANY block type, as in minimp3.h:1260 (0, 2, 4) */
     int map;         /* reorder map row or -1 */
+    int ms;          /* plain MS stereo applied on load: 0 none, 1 this row = L + R, 2 this row = L - R */
+    int nzl_other;   /* extent of the partner channel's row (ms != 0) */
 };
 
 struct Smem
@@ -65,25 +68,114 @@ struct Smem
     SlotMeta meta[kSlots];
 };
 
-template <bool FLOAT_OUT>
-__device__ __forceinline__ void store_pcm(void *pcm, uint64_t idx, float l, float r, int nch, bool scalar_round)
+/* saturating round-to-nearest-even float -> int16 in one instruction: what the reference's
+ * min/max + cvtps2dq + packssdw sequence computes (minimp3.h:1541-1542) */
+__device__ __forceinline__ uint32_t f2s16_rn_sat(float x)
 {
+    short r;
+    asm("cvt.rni.sat.s16.f32 %0, %1;" : "=h"(r) : "f"(x));
+    return (uint32_t)(uint16_t)r;
+}
+
+/* ---- phase 5: 512-tap window as a 16-tap FIR per output phase (ISO 11172-3 fig. A.2 restated) ----
+ * pcm[32 t + j] = sum_m  D[64m + j] V_{t-2m}[j] + D[64m + 32 + j] V_{t-2m-1}[32 + j];  V_t[j] = +-y_t[ia],
+ * V_t[32 + j] = -y_t[ib] (signs folded into the taps).  One thread = one output phase j of one granule, both
+ * channels; the 16-slot history lives in registers.  The two phases the reference rounds with its scalar
+ * helper (j = 0, 16) are parked in shared memory and finished by a separate pass. */
+template <bool FLOAT_OUT, int NCH>
+__device__ __forceinline__ void fir_phase(const float *ybase, const float *__restrict__ fir_coef, float *special,
+                                          void *pcm, uint64_t pcm_off, int n_gr, int tid)
+{
+    const int i = tid >> 5, j = tid & 31;
+    if (i >= n_gr) return;
+    float c[16];
+#pragma unroll
+    for (int k = 0; k < 16; k += 4)
+    {
+        const float4 q = __ldg(reinterpret_cast<const float4 *>(fir_coef + j*16 + k));
+        c[k] = q.x; c[k + 1] = q.y; c[k + 2] = q.z; c[k + 3] = q.w;
+    }
+    const int ia = j < 16 ? 16 + j : (j == 16 ? 0 : 48 - j);
+    const int ib = j <= 16 ? 16 - j : j - 16;
+    const bool is_special = !FLOAT_OUT && ((j & 15) == 0);
+    float res[NCH][18];
+#pragma unroll
+    for (int ch = 0; ch < NCH; ch++)
+    {
+        const float *ya = ybase + (ch*kRows + i*18)*kYPitch + ia;
+        const float *yb = ybase + (ch*kRows + i*18)*kYPitch + ib;
+        float A[16], B[16];
+#pragma unroll
+        for (int h = 0; h < 15; h++)
+        {
+            A[h] = ya[h*kYPitch];
+            B[h] = yb[h*kYPitch];
+        }
+#pragma unroll
+        for (int tt = 0; tt < 18; tt++)
+        {
+            const int cur = (15 + tt) & 15;
+            A[cur] = ya[(15 + tt)*kYPitch];
+            B[cur] = yb[(15 + tt)*kYPitch];
+            float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+            for (int m = 0; m < 8; m++)
+            {
+                acc0 = fmaf(c[2*m], A[(15 + tt - 2*m) & 15], acc0);
+                acc1 = fmaf(c[2*m + 1], B[(15 + tt - 2*m - 1) & 15], acc1);
+            }
+            res[ch][tt] = acc0 + acc1;
+        }
+    }
     if (FLOAT_OUT)
     {
-        float *p = reinterpret_cast<float *>(pcm);
+        float *p = reinterpret_cast<float *>(pcm) + pcm_off + (size_t)(i*576 + j)*NCH;
         const float k = 1.0f/32768.0f;
-        if (nch == 2) *reinterpret_cast<float2 *>(p + idx) = make_float2(l*k, r*k);
-        else p[idx] = l*k;
+#pragma unroll
+        for (int tt = 0; tt < 18; tt++)
+        {
+            if (NCH == 2) *reinterpret_cast<float2 *>(p + tt*64) = make_float2(res[0][tt]*k, res[NCH - 1][tt]*k);
+            else p[tt*32] = res[0][tt]*k;
+        }
+    } else if (is_special)
+    {
+        float *sp = special + ((i*2 + (j >> 4))*18)*NCH;
+#pragma unroll
+        for (int tt = 0; tt < 18; tt++)
+        {
+            sp[tt*NCH] = res[0][tt];
+            if (NCH == 2) sp[tt*NCH + 1] = res[NCH - 1][tt];
+        }
     } else
     {
-        int16_t *p = reinterpret_cast<int16_t *>(pcm);
-        const int16_t a = scalar_round ? pcm_round_scalar(l) : pcm_round_simd(l);
-        if (nch == 2)
+        int16_t *p = reinterpret_cast<int16_t *>(pcm) + pcm_off + (size_t)(i*576 + j)*NCH;
+#pragma unroll
+        for (int tt = 0; tt < 18; tt++)
         {
-            const int16_t b = scalar_round ? pcm_round_scalar(r) : pcm_round_simd(r);
-            *reinterpret_cast<uint32_t *>(p + idx) = (uint32_t)(uint16_t)a | ((uint32_t)(uint16_t)b << 16);
+            if (NCH == 2)
+                *reinterpret_cast<uint32_t *>(p + tt*64) = f2s16_rn_sat(res[0][tt]) | (f2s16_rn_sat(res[NCH - 1][tt]) << 16);
+            else
+                p[tt*32] = (int16_t)f2s16_rn_sat(res[0][tt]);
+        }
+    }
+}
+
+/* the 2-of-32 outputs the reference produces through mp3d_scale_pcm (truncate(x + .5) - (x < 0)) */
+template <int NCH>
+__device__ __forceinline__ void special_round_pass(const float *special, void *pcm, uint64_t pcm_off, int n_gr, int tid)
+{
+    const int n = n_gr*2*18;
+    for (int k = tid; k < n; k += kThreads)
+    {
+        const int tt = k % 18, ih = k/18, h = ih & 1, i = ih >> 1;
+        int16_t *p = reinterpret_cast<int16_t *>(pcm) + pcm_off + (size_t)(i*576 + tt*32 + h*16)*NCH;
+        const int16_t l = pcm_round_scalar(special[k*NCH]);
+        if (NCH == 2)
+        {
+            const int16_t r = pcm_round_scalar(special[k*NCH + 1]);
+            *reinterpret_cast<uint32_t *>(p) = (uint32_t)(uint16_t)l | ((uint32_t)(uint16_t)r << 16);
         } else
-            p[idx] = a;
+            *p = l;
     }
 }
 
@@ -103,7 +195,7 @@ k_l3_transform(TransformArgs a, const uint16_t *__restrict__ reorder_map, const 
     if (tid < kSlots)
     {
         SlotMeta m;
-        m.gc = -1; m.nzl = 0; m.block_type = 0; m.n_long = 0; m.map = -1;
+        m.gc = -1; m.nzl = 0; m.block_type = 0; m.n_long = 0; m.map = -1; m.ms = 0; m.nzl_other = 0;
         if (tid < n_slots)
         {
             const int i = tid/nch - 2, ch = tid%nch;
@@ -117,50 +209,72 @@ k_l3_transform(TransformArgs a, const uint16_t *__restrict__ reorder_map, const 
                 const bool mixed = d.flags0 & GCF_MIXED;
                 m.n_long = mixed ? (d.sr_idx == 1 ? 4 : 2) : 0;   /* 8 kHz MPEG-2.5 keeps 4 long subbands */
                 if (m.block_type == 2) m.map = d.sr_idx*2 + (mixed ? 1 : 0);
+                if (d.flags1 & GCF1_MS_PLAIN)
+                {
+                    /* L3_midside_stereo (minimp3.h:879-909): stereo pairs sit on descriptor indices (2k, 2k+1) */
+                    m.ms = (d.flags1 & GCF1_CH) ? 2 : 1;
+                    m.nzl_other = a.nzl[gc ^ 1];
+                }
             }
         }
         S.meta[tid] = m;
     }
     __syncthreads();
 
-    /* ---- phase 1: spectra -> shared (short blocks: [window][freq] -> [freq][window] on the fly) ---- */
+    /* ---- phase 1: spectra -> shared (short blocks: [window][freq] -> [freq][window] on the fly).
+     * Lines at or beyond nzl were never written by the entropy kernel and are zero by definition. ---- */
     for (int slot = warp; slot < n_slots; slot += kThreads/32)
     {
         const SlotMeta m = S.meta[slot];
         float *dst = S.x + slot*kXSlot;
-        const float *src = m.gc >= 0 ? a.xr + (size_t)m.gc*576 : nullptr;
-        const uint16_t *map = m.map >= 0 ? reorder_map + m.map*576 : nullptr;
+        if (m.map < 0)
+        {
+            const float *src = a.xr + (size_t)(m.gc >= 0 ? m.gc : 0)*576 + lane;
+            const int n_live = (m.nzl + 31) >> 5;     /* 32-line chunks holding data */
+            float v[18];
 #pragma unroll
-        for (int k = 0; k < 18; k++)
+            for (int k = 0; k < 18; k++) v[k] = k < n_live ? __ldg(src + 32*k) : 0.f;
+            if (m.ms)
+            {
+                const float *oth = a.xr + (size_t)(m.gc ^ 1)*576 + lane;
+                const int n_oth = (m.nzl_other + 31) >> 5;
+#pragma unroll
+                for (int k = 0; k < 18; k++)
+                {
+                    const float o = k < n_oth ? __ldg(oth + 32*k) : 0.f;
+                    v[k] = m.ms == 1 ? v[k] + o : o - v[k];
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 18; k++)
+            {
+                const int e = lane + 32*k;
+                dst[e + ((e*3641) >> 16)] = v[k];     /* e + e/18: row pitch 19 */
+            }
+        } else
         {
-            const int e = lane + 32*k;
-            const float v = e < m.nzl ? __ldg(src + e) : 0.f;
-            const int dl = map ? (int)__ldg(map + e) : e;
-            const int sb = dl/18;
-            dst[sb*kXPitch + (dl - sb*18)] = v;
+            const float *src = a.xr + (size_t)m.gc*576;
+            const float *oth = a.xr + (size_t)(m.gc ^ 1)*576;
+            const uint16_t *map = reorder_map + m.map*576;
+#pragma unroll 6
+            for (int k = 0; k < 18; k++)
+            {
+                const int e = lane + 32*k;
+                float v = e < m.nzl ? __ldg(src + e) : 0.f;
+                if (m.ms)
+                {
+                    const float o = e < m.nzl_other ? __ldg(oth + e) : 0.f;
+                    v = m.ms == 1 ? v + o : o - v;
+                }
+                const int dl = (int)__ldg(map + e);
+                dst[dl + ((dl*3641) >> 16)] = v;
+            }
         }
     }
     __syncthreads();
 
-    /* ---- phase 2: antialias (minimp3.h:1012-1045): 8 butterflies across each long/long subband boundary ---- */
-    for (int slot = 0; slot < n_slots; slot++)
-    {
-        const SlotMeta m = S.meta[slot];
-        if (m.gc < 0) continue;
-        const int aa_bands = m.block_type == 2 ? m.n_long - 1 : 31;
-        const int b = tid >> 3, i = tid & 7;
-        if (b < aa_bands)
-        {
-            float *x = S.x + slot*kXSlot;
-            const float u = x[(b + 1)*kXPitch + i];
-            const float dn = x[b*kXPitch + 17 - i];
-            x[(b + 1)*kXPitch + i] = u*c_k.aa_cs[i] - dn*c_k.aa_ca[i];
-            x[b*kXPitch + 17 - i] = u*c_k.aa_ca[i] + dn*c_k.aa_cs[i];
-        }
-    }
-    __syncthreads();
-
-    /* ---- phase 3a: per (slot, subband): tail and own half ---- */
+    /* ---- phases 2+3a: per (slot, subband): antialias butterflies against both neighbours (minimp3.h:1012-1045,
+     * recomputed on the fly instead of a separate in-place pass), then IMDCT tail and own half ---- */
     constexpr int kJobs3 = (kSlots*32 + kThreads - 1)/kThreads;   /* 3 */
     float own[kJobs3][9];
 #pragma unroll
@@ -175,6 +289,19 @@ k_l3_transform(TransformArgs a, const uint16_t *__restrict__ reorder_map, const 
             const float *src = S.x + slot*kXSlot + sb*kXPitch;
 #pragma unroll
             for (int k = 0; k < 18; k++) x[k] = src[k];
+            const int aa_bands = m.block_type == 2 ? m.n_long - 1 : 31;
+            if (sb >= 1 && sb - 1 < aa_bands)
+            {
+                /* boundary below: this subband holds the "u" side */
+#pragma unroll
+                for (int i = 0; i < 8; i++) x[i] = x[i]*c_k.aa_cs[i] - src[-kXPitch + 17 - i]*c_k.aa_ca[i];
+            }
+            if (sb < aa_bands)
+            {
+                /* boundary above: this subband holds the "d" side */
+#pragma unroll
+                for (int i = 0; i < 8; i++) x[17 - i] = src[kXPitch + i]*c_k.aa_ca[i] + x[17 - i]*c_k.aa_cs[i];
+            }
             if (m.block_type == 2 && sb >= m.n_long) imdct_short_core(x, own[r], tail, c_k.twid3);
             else imdct36_core(x, own[r], tail, c_k.twid9);
             float *t = S.t + slot*288 + sb;
@@ -241,7 +368,7 @@ k_l3_transform(TransformArgs a, const uint16_t *__restrict__ reorder_map, const 
         const int n_jobs = rows_ch*nch;
         for (int job = tid; job < n_jobs; job += kThreads)
         {
-            const int ch = job/rows_ch, row = job - ch*rows_ch;
+            const int ch = job >= rows_ch ? 1 : 0, row = job - ch*rows_ch;
             float *y = S.x + (ch*kRows + row)*kYPitch;
             if (stateful && row < 15)
             {
@@ -259,56 +386,15 @@ k_l3_transform(TransformArgs a, const uint16_t *__restrict__ reorder_map, const 
     }
     __syncthreads();
 
-    /* ---- phase 5: 512-tap window as a 16-tap FIR per output phase (ISO 11172-3 fig. A.2 restated) ---- */
+    /* ---- phase 5: window FIR + PCM conversion ---- */
+    float *special = S.x + kYFloats;     /* slack behind Y: n_gr*2*18*nch floats */
+    if (nch == 2) fir_phase<FLOAT_OUT, 2>(S.x, fir_coef, special, a.pcm, tile.pcm_off, n_gr, tid);
+    else fir_phase<FLOAT_OUT, 1>(S.x, fir_coef, special, a.pcm, tile.pcm_off, n_gr, tid);
+    if (!FLOAT_OUT)
     {
-        const int i = tid >> 5, j = tid & 31;
-        if (i < n_gr)
-        {
-            float c[16];
-#pragma unroll
-            for (int k = 0; k < 16; k += 4)
-            {
-                const float4 q = __ldg(reinterpret_cast<const float4 *>(fir_coef + j*16 + k));
-                c[k] = q.x; c[k + 1] = q.y; c[k + 2] = q.z; c[k + 3] = q.w;
-            }
-            /* V_t[j] = +-y[ia], V_t[32+j] = -y[ib]; signs are folded into c[] */
-            const int ia = j < 16 ? 16 + j : (j == 16 ? 0 : 48 - j);
-            const int ib = j <= 16 ? 16 - j : j - 16;
-            const bool scalar_round = (j == 0) || (j == 16);
-            float res0[18];
-            for (int ch = 0; ch < nch; ch++)
-            {
-                const float *y = S.x + (ch*kRows + i*18)*kYPitch;
-                float A[16], B[16];
-#pragma unroll
-                for (int h = 0; h < 15; h++)
-                {
-                    A[h] = y[h*kYPitch + ia];
-                    B[h] = y[h*kYPitch + ib];
-                }
-#pragma unroll
-                for (int tt = 0; tt < 18; tt++)
-                {
-                    const int cur = (15 + tt) & 15;
-                    A[cur] = y[(15 + tt)*kYPitch + ia];
-                    B[cur] = y[(15 + tt)*kYPitch + ib];
-                    float acc = 0.f;
-#pragma unroll
-                    for (int m = 0; m < 8; m++)
-                    {
-                        acc = fmaf(c[2*m], A[(15 + tt - 2*m) & 15], acc);
-                        acc = fmaf(c[2*m + 1], B[(15 + tt - 2*m - 1) & 15], acc);
-                    }
-                    if (nch == 2 && ch == 0) res0[tt] = acc;
-                    else
-                    {
-                        const uint64_t idx = tile.pcm_off + (uint64_t)((i*576 + tt*32 + j)*nch);
-                        if (nch == 2) store_pcm<FLOAT_OUT>(a.pcm, idx, res0[tt], acc, 2, scalar_round);
-                        else store_pcm<FLOAT_OUT>(a.pcm, idx, acc, 0.f, 1, scalar_round);
-                    }
-                }
-            }
-        }
+        __syncthreads();
+        if (nch == 2) special_round_pass<2>(special, a.pcm, tile.pcm_off, n_gr, tid);
+        else special_round_pass<1>(special, a.pcm, tile.pcm_off, n_gr, tid);
     }
 
     /* ---- carried state out (single-frame API): tails of the last granule + last 15 transformed slots ---- */

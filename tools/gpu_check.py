@@ -54,10 +54,9 @@ def main():
             xrz = xr[real].copy()
             for i, g in enumerate(real):
                 xrz[i, nzl[g]:] = 0
-            msg += ["xr_stereo", bool(np.array_equal(xrz.view(np.uint32), t["xr_stereo"].view(np.uint32)))]
-            if not np.array_equal(xrz.view(np.uint32), t["xr_stereo"].view(np.uint32)):
-                bad = np.argwhere(xrz.view(np.uint32) != t["xr_stereo"].view(np.uint32))
-                msg += ["badxr", bad[:3].tolist(), float(np.abs(xrz - t["xr_stereo"]).max())]
+            ms_plain = (desc[real, 29] & 0x10) != 0
+            want = np.where(ms_plain[:, None], t["xr"], t["xr_stereo"])
+            msg += ["xr", bool(np.array_equal(xrz.view(np.uint32), want.view(np.uint32)))]
             scale = max(1.0, float(np.abs(t["sub"]).max()))
             msg += ["sub_relerr", float(np.abs(sub[real] - t["sub"]).max()/scale)]
         if len(pcm) == len(t["pcm"]):
