@@ -60,6 +60,27 @@ def test_stage_taps_bit_exact_and_pcm_within_one_lsb(name, m, ref):
     assert d.max() <= 1 and (d != 0).mean() < 0.01
 
 
+@pytest.mark.parametrize("name", L3_SMOKE)
+def test_cuda_against_oracle_port(name, m):
+    """same inputs through the plain-C restatement (oracle/mp3_oracle.c): integers bit-exact, filterbank tight"""
+    from oracle import port
+    data = load_vector(name)
+    o = port.decode_stream(data, taps=True)
+    p = m.BatchPlan([data], raw_frames=True)
+    p.enable_taps()
+    p.run()
+    rets, outs = p.fetch()
+    desc, q, sub = p.read_tap(4), p.read_tap(0), p.read_tap(3)
+    p.close()
+    rows = real_rows(desc)
+    assert len(rows) == o["n_gc"]
+    assert np.array_equal(q[rows], o["q"])
+    scale = max(1.0, float(np.abs(o["sub"]).max()))
+    assert np.abs(sub[rows] - o["sub"]).max() <= 2e-6*scale
+    d = np.abs(outs[0]["pcm"].astype(np.int32) - o["pcm"].astype(np.int32))
+    assert len(d) == len(o["pcm"]) and d.max() <= 1
+
+
 @pytest.mark.parametrize("name", L3_CONFORMANCE)
 def test_conformance_psnr(name, m, manifest):
     """minimp3_test.c:391-428 on the CUDA output: sample-count rule and PSNR >= 96 dB against the ISO PCM"""
