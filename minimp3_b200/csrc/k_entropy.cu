@@ -9,7 +9,7 @@
  * sorts them, see build_order in host_parse.cpp) so that its lanes finish together.  Huffman decode
  * is serial inside a granule, so the parallelism is across granules; to keep the memory side coalesced
  * the warp runs a SIMT-uniform loop over line pairs (iteration k produces lines 2k, 2k+1 of all 32
- * granule-channels; a count1 quad takes two iterations), stages 64 lines x 32 rows in shared memory and
+ * granule-channels; a count1 quad takes two iterations), stages 32 lines x 32 rows in shared memory and
  * flushes them as full 128-byte row segments.  Code books, |q|^(4/3) and band widths sit in shared memory.
  * Rows are only written up to the last decoded line (rounded up to 32); nzl[] tells the consumer.
  */
@@ -25,15 +25,15 @@ namespace mp3b {
 namespace {
 
 constexpr int kWarpsPerBlock = 8;
-constexpr int kStageLines = 64;
+constexpr int kStageLines = 32;
+constexpr int kC1Base = MP3T_HUFF_LUT_SIZE;          /* count1 table A (64 entries) then B (16) */
 constexpr int kStagePitch = 33;
 
 struct SharedTables
 {
-    uint16_t lut[(MP3T_HUFF_LUT_SIZE + 7) & ~7];
+    uint16_t lut[(MP3T_HUFF_LUT_SIZE + 80 + 7) & ~7];
     float pow43[148];
     uint32_t tabinfo[32];
-    uint8_t count1a[64];
     uint8_t sfb_long[8*23];
     uint8_t sfb_short[8*40];
     uint8_t sfb_mixed[8*40];
@@ -55,7 +55,7 @@ __device__ __forceinline__ GcDesc load_desc(const GcDesc *p)
     return d;
 }
 
-__global__ void __launch_bounds__(kWarpsPerBlock*32, 2) k_l3_entropy(EntropyArgs a)
+__global__ void __launch_bounds__(kWarpsPerBlock*32, 3) k_l3_entropy(EntropyArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SharedTables &S = *reinterpret_cast<SharedTables *>(smem_raw);
@@ -67,13 +67,16 @@ __global__ void __launch_bounds__(kWarpsPerBlock*32, 2) k_l3_entropy(EntropyArgs
     for (int i = tid; i < MP3T_HUFF_LUT_SIZE; i += blockDim.x) S.lut[i] = MP3T_HUFF_LUT[i];
     for (int i = tid; i < 145; i += blockDim.x) S.pow43[i] = MP3T_POW43[i];
     if (tid < 32) S.tabinfo[tid] = (uint32_t)MP3T_HUFF_BASE[tid] | ((uint32_t)MP3T_HUFF_ROOTW[tid] << 16) | ((uint32_t)MP3T_HUFF_LINBITS[tid] << 20);
-    if (tid < 64) S.count1a[tid] = MP3T_COUNT1A[tid];
+    if (tid < 64) S.lut[kC1Base + tid] = (uint16_t)(((MP3T_COUNT1A[tid] >> 4) << 8) | (MP3T_COUNT1A[tid] & 15));
+    if (tid < 16) S.lut[kC1Base + 64 + tid] = (uint16_t)((4 << 8) | (~tid & 15));
     for (int i = tid; i < 8*23; i += blockDim.x) S.sfb_long[i] = MP3T_SFB_LONG[i];
     for (int i = tid; i < 8*40; i += blockDim.x) { S.sfb_short[i] = MP3T_SFB_SHORT[i]; S.sfb_mixed[i] = MP3T_SFB_MIXED[i]; }
     __syncthreads();
 
     EntropyTables T;
-    T.lut = S.lut; T.pow43 = S.pow43; T.tabinfo = S.tabinfo; T.count1a = S.count1a;
+    T.lut = S.lut; T.pow43 = S.pow43; T.tabinfo = S.tabinfo;
+    T.c1info[0] = (uint32_t)kC1Base | (6u << 16);
+    T.c1info[1] = (uint32_t)(kC1Base + 64) | (4u << 16);
     T.sfb_long = S.sfb_long; T.sfb_short = S.sfb_short; T.sfb_mixed = S.sfb_mixed;
 
     WarpScratch &W = scratch[warp];
@@ -135,12 +138,12 @@ __global__ void __launch_bounds__(kWarpsPerBlock*32, 2) k_l3_entropy(EntropyArgs
             iter++;
             bool finished = iter == 288;
             if ((iter & 15) == 0 && !finished) finished = __ballot_sync(0xffffffffu, dec.mode != EMODE_DONE) == 0;
-            if (finished || (iter & 31) == 0)
+            if (finished || (iter & 15) == 0)
             {
                 /* ---- flush lines [flushed, 2*iter) of all 32 rows ---- */
                 __syncwarp();
                 const int my_ext = !valid ? 0 : (dec.mode == EMODE_DONE) ? ((dec.extent + 31) & ~31) : 576;
-                const int n_lines = 2*iter - flushed;   /* 32 or 64 */
+                const int n_lines = 2*iter - flushed;   /* 32 */
                 for (int r = 0; r < 32; r++)
                 {
                     const int e = __shfl_sync(0xffffffffu, my_ext, r);
@@ -177,7 +180,7 @@ cudaError_t launch_entropy(const DeviceTables &, const EntropyArgs &a, cudaStrea
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const uint32_t n_groups = (a.n_order + 31)/32;
     uint32_t blocks = (n_groups + kWarpsPerBlock - 1)/kWarpsPerBlock;
-    const uint32_t max_blocks = (uint32_t)sms*2;
+    const uint32_t max_blocks = (uint32_t)sms*3;
     if (blocks > max_blocks) blocks = max_blocks;
     k_l3_entropy<<<blocks, kWarpsPerBlock*32, smem, s>>>(a);
     return cudaGetLastError();

@@ -180,7 +180,7 @@ __device__ __forceinline__ void special_round_pass(const float *special, void *p
 }
 
 template <bool FLOAT_OUT>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, 3)
 k_l3_transform(TransformArgs a, const uint16_t *__restrict__ reorder_map, const float *__restrict__ fir_coef)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -227,29 +227,40 @@ k_l3_transform(TransformArgs a, const uint16_t *__restrict__ reorder_map, const 
     {
         const SlotMeta m = S.meta[slot];
         float *dst = S.x + slot*kXSlot;
+        /* clear the slot with 128-bit stores, then write only the 32-line chunks that hold data */
+        {
+            float4 *z = reinterpret_cast<float4 *>(dst);
+#pragma unroll
+            for (int k = 0; k < 5; k++)
+                if (lane + 32*k < kXSlot/4) z[lane + 32*k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        __syncwarp();
         if (m.map < 0)
         {
             const float *src = a.xr + (size_t)(m.gc >= 0 ? m.gc : 0)*576 + lane;
-            const int n_live = (m.nzl + 31) >> 5;     /* 32-line chunks holding data */
-            float v[18];
-#pragma unroll
-            for (int k = 0; k < 18; k++) v[k] = k < n_live ? __ldg(src + 32*k) : 0.f;
-            if (m.ms)
+            const float *oth = a.xr + (size_t)((m.gc >= 0 ? m.gc : 0) ^ 1)*576 + lane;
+            const int n_own = (m.nzl + 31) >> 5, n_oth = m.ms ? (m.nzl_other + 31) >> 5 : 0;
+            const int n_live = max(n_own, n_oth);
+            for (int k0 = 0; k0 < n_live; k0 += 6)
             {
-                const float *oth = a.xr + (size_t)(m.gc ^ 1)*576 + lane;
-                const int n_oth = (m.nzl_other + 31) >> 5;
+                float v[6];
 #pragma unroll
-                for (int k = 0; k < 18; k++)
+                for (int k = 0; k < 6; k++) v[k] = k0 + k < n_own ? __ldg(src + 32*(k0 + k)) : 0.f;
+                if (m.ms)
                 {
-                    const float o = k < n_oth ? __ldg(oth + 32*k) : 0.f;
-                    v[k] = m.ms == 1 ? v[k] + o : o - v[k];
-                }
-            }
 #pragma unroll
-            for (int k = 0; k < 18; k++)
-            {
-                const int e = lane + 32*k;
-                dst[e + ((e*3641) >> 16)] = v[k];     /* e + e/18: row pitch 19 */
+                    for (int k = 0; k < 6; k++)
+                    {
+                        const float o = k0 + k < n_oth ? __ldg(oth + 32*(k0 + k)) : 0.f;
+                        v[k] = m.ms == 1 ? v[k] + o : o - v[k];
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 6; k++)
+                {
+                    const int e = lane + 32*(k0 + k);
+                    if (k0 + k < n_live) dst[e + ((e*3641) >> 16)] = v[k];     /* e + e/18: row pitch 19 */
+                }
             }
         } else
         {

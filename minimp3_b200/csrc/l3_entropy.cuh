@@ -22,16 +22,18 @@ struct EntropyTables
     const uint16_t *lut;        /* MP3T_HUFF_LUT */
     const float *pow43;         /* MP3T_POW43 */
     const uint32_t *tabinfo;    /* [32] base | rootw << 16 | linbits << 20 */
-    const uint8_t *count1a;     /* [64] */
+    uint32_t c1info[2];         /* count1 table A / B: LUT base | root width << 16 (entries: len << 8 | vwxy) */
     const uint8_t *sfb_long, *sfb_short, *sfb_mixed;
 };
 
-/* MSB-first bit reader over big-endian bytes, fed by aligned 32-bit loads */
+/* MSB-first bit reader over big-endian bytes, fed by aligned 32-bit loads.  `next` is fetched one refill
+ * ahead so the global-load latency overlaps with the decoding of the bits already in `buf`. */
 struct BitRd
 {
     const uint32_t *w;
     uint64_t n_words, widx;
     uint64_t buf;
+    uint32_t next;
     int avail;
     int pos;   /* bits consumed since init */
 
@@ -52,15 +54,17 @@ struct BitRd
         buf = ((uint64_t)word(widx) << 32) | word(widx + 1);
         buf <<= sh;
         avail = 64 - sh;
-        widx += 2;
+        next = word(widx + 2);
+        widx += 3;
         pos = 0;
     }
     MP3_HD void refill()
     {
         if (avail <= 32)
         {
-            buf |= (uint64_t)word(widx++) << (32 - avail);
+            buf |= (uint64_t)next << (32 - avail);
             avail += 32;
+            next = word(widx++);
         }
     }
     MP3_HD uint32_t peek(int n) const { return n ? (uint32_t)(buf >> (64 - n)) : 0u; }
@@ -243,7 +247,9 @@ struct GranuleDecoder
 
     MP3_HD float band_scale(int b) const { return l3_ldexp_q2(gain, (int)iscf[b*iscf_st] << scf_shift); }
 
-    /* next two lines; q0/q1 receive the signed quantised values */
+    /* next two lines; q0/q1 receive the signed quantised values.  Big-value pairs and count1 half-quads share
+     * one code path (a count1 line is a value of magnitude 0 or 1: one * pow43(1) == one exactly), so lanes in
+     * different regions of their granules do not serialise. */
     MP3_HD void step(const EntropyTables &T, float &v0, float &v1, int &q0, int &q1)
     {
         v0 = v1 = 0.f;
@@ -251,19 +257,9 @@ struct GranuleDecoder
         const int this_line = line;
         line += 2;
         if (mode == EMODE_DONE) return;
-        if (mode == EMODE_C1A)
-        {
-            /* count1 quad code; stop when it ends past the granule's bit budget (minimp3.h:852-864) */
-            br.refill();
-            int len, vwxy;
-            if (count1_b) { len = 4; vwxy = (int)((~br.peek(4)) & 15); }
-            else { const int e = T.count1a[br.peek(6)]; len = e >> 4; vwxy = e & 15; }
-            br.skip(len);
-            if (br.pos > limit) { mode = EMODE_DONE; return; }
-            pending = vwxy;
-        }
         if (band_left == 0)
         {
+            /* next scalefactor band (minimp3.h:788-790, 865); region / code-book switch only while in big values */
             const int wd = sfbw[band_idx];
             if (!wd) { mode = EMODE_DONE; return; }
             band_left = wd >> 1;
@@ -282,14 +278,17 @@ struct GranuleDecoder
                 reg_left--;
             }
         }
-        if (mode == EMODE_BIG)
+        int x, y, linbits = 0;
+        if (mode != EMODE_C1B)
         {
-            const int base = (int)(tinfo & 0xFFFF), rootw = (int)((tinfo >> 16) & 15), linbits = (int)((tinfo >> 20) & 15);
-            int x = 0, y = 0;
+            const bool big = mode == EMODE_BIG;
+            const uint32_t info = big ? tinfo : T.c1info[count1_b ? 1 : 0];
+            const int base = (int)(info & 0xFFFF), rootw = (int)((info >> 16) & 15);
+            int e = 0;
             br.refill();
             if (rootw)
             {
-                int e = T.lut[base + br.peek(rootw)];
+                e = T.lut[base + br.peek(rootw)];
                 int wcur = rootw;
                 while (e & 0x8000)
                 {
@@ -298,34 +297,43 @@ struct GranuleDecoder
                     e = T.lut[base + (e & 0x7FF) + br.peek(wcur)];
                 }
                 br.skip(e >> 8);
+            }
+            if (big)
+            {
                 x = (e >> 4) & 15;
                 y = e & 15;
-            }
-            br.refill();
-            if (x == 15 && linbits) { x += (int)br.peek(linbits); br.skip(linbits); br.refill(); }
-            if (x)
+                linbits = (int)((info >> 20) & 15);
+            } else
             {
-                const int neg = (int)br.peek(1); br.skip(1);
-                const float m = MP3_FMUL(one, l3_pow43(x, T.pow43));
-                v0 = neg ? -m : m; q0 = neg ? -x : x;
+                /* count1 quad: stop when its code ends past the granule's bit budget (minimp3.h:852-864) */
+                if (br.pos > limit) { mode = EMODE_DONE; return; }
+                x = (e >> 3) & 1;
+                y = (e >> 2) & 1;
+                pending = e & 3;
             }
-            br.refill();
-            if (y == 15 && linbits) { y += (int)br.peek(linbits); br.skip(linbits); br.refill(); }
-            if (y)
-            {
-                const int neg = (int)br.peek(1); br.skip(1);
-                const float m = MP3_FMUL(one, l3_pow43(y, T.pow43));
-                v1 = neg ? -m : m; q1 = neg ? -y : y;
-            }
-            if (--big_left == 0) mode = EMODE_C1A;
         } else
         {
-            const int hi = (mode == EMODE_C1A) ? 8 : 2;
-            br.refill();
-            if (pending & hi) { const int neg = (int)br.peek(1); br.skip(1); v0 = neg ? -one : one; q0 = neg ? -1 : 1; }
-            if (pending & (hi >> 1)) { const int neg = (int)br.peek(1); br.skip(1); v1 = neg ? -one : one; q1 = neg ? -1 : 1; }
-            mode = (mode == EMODE_C1A) ? EMODE_C1B : EMODE_C1A;
+            x = (pending >> 1) & 1;
+            y = pending & 1;
         }
+        br.refill();
+        if (x == 15 && linbits) { x += (int)br.peek(linbits); br.skip(linbits); br.refill(); }
+        if (x)
+        {
+            const int neg = (int)br.peek(1); br.skip(1);
+            const float m = MP3_FMUL(one, l3_pow43(x, T.pow43));
+            v0 = neg ? -m : m; q0 = neg ? -x : x;
+        }
+        br.refill();
+        if (y == 15 && linbits) { y += (int)br.peek(linbits); br.skip(linbits); br.refill(); }
+        if (y)
+        {
+            const int neg = (int)br.peek(1); br.skip(1);
+            const float m = MP3_FMUL(one, l3_pow43(y, T.pow43));
+            v1 = neg ? -m : m; q1 = neg ? -y : y;
+        }
+        if (mode == EMODE_BIG) { if (--big_left == 0) mode = EMODE_C1A; }
+        else mode = (mode == EMODE_C1A) ? EMODE_C1B : EMODE_C1A;
         band_left--;
         extent = this_line + 2;
     }

@@ -21,6 +21,7 @@ using namespace mp3b;
 
 static EntropyTables g_T;
 static uint32_t g_tabinfo[32];
+static uint16_t g_lut[MP3T_HUFF_LUT_SIZE + 80];
 static ImdctConsts g_K;
 static uint16_t g_map[16*576];
 static float g_fir[32*16];
@@ -31,7 +32,12 @@ static void ensure_tables()
     if (g_ready) return;
     for (int t = 0; t < 32; t++)
         g_tabinfo[t] = (uint32_t)MP3T_HUFF_BASE[t] | ((uint32_t)MP3T_HUFF_ROOTW[t] << 16) | ((uint32_t)MP3T_HUFF_LINBITS[t] << 20);
-    g_T.lut = MP3T_HUFF_LUT; g_T.pow43 = MP3T_POW43; g_T.tabinfo = g_tabinfo; g_T.count1a = MP3T_COUNT1A;
+    for (int i = 0; i < MP3T_HUFF_LUT_SIZE; i++) g_lut[i] = MP3T_HUFF_LUT[i];
+    for (int i = 0; i < 64; i++) g_lut[MP3T_HUFF_LUT_SIZE + i] = (uint16_t)(((MP3T_COUNT1A[i] >> 4) << 8) | (MP3T_COUNT1A[i] & 15));
+    for (int i = 0; i < 16; i++) g_lut[MP3T_HUFF_LUT_SIZE + 64 + i] = (uint16_t)((4 << 8) | (~i & 15));
+    g_T.lut = g_lut; g_T.pow43 = MP3T_POW43; g_T.tabinfo = g_tabinfo;
+    g_T.c1info[0] = (uint32_t)MP3T_HUFF_LUT_SIZE | (6u << 16);
+    g_T.c1info[1] = (uint32_t)(MP3T_HUFF_LUT_SIZE + 64) | (4u << 16);
     g_T.sfb_long = MP3T_SFB_LONG; g_T.sfb_short = MP3T_SFB_SHORT; g_T.sfb_mixed = MP3T_SFB_MIXED;
     build_consts(&g_K);
     build_reorder_map(g_map);
