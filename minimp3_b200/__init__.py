@@ -223,14 +223,53 @@ class BatchPlan:
             pass
 
 
+class _Batch:
+    """ctypes argument pack for the one-call entry point (reusable across calls for benchmarking)."""
+
+    def __init__(self, streams, **kw):
+        self.L = load()
+        self.float_output = bool(kw.get("float_output", False))
+        self.keep = [_as_u8(s) for s in streams]
+        self.n = len(self.keep)
+        self.streams = (BatchStream*max(1, self.n))()
+        for i, (a, s) in enumerate(zip(self.keep, streams)):
+            self.streams[i].buf = a.ctypes.data
+            self.streams[i].size = len(s)
+        self.opts = _opts(**kw)
+        self.infos = (FileInfo*max(1, self.n))()
+        self.rets = (C.c_int*max(1, self.n))()
+
+    def call(self):
+        err = self.L.mp3dec_decode_batch_cuda(self.streams, self.n, self.infos, self.rets, C.byref(self.opts))
+        if err:
+            raise RuntimeError("mp3dec_decode_batch_cuda failed: %d" % err)
+        return sum(self.infos[i].samples for i in range(self.n))
+
+    def results(self, copy=True):
+        dt = np.float32 if self.float_output else np.int16
+        ct = C.c_float if self.float_output else C.c_int16
+        out = []
+        for i in range(self.n):
+            fi = self.infos[i]
+            if fi.buffer and fi.samples and self.opts.output != OUT_DEVICE:
+                arr = np.ctypeslib.as_array(C.cast(fi.buffer, C.POINTER(ct)), shape=(fi.samples,))
+                if copy or self.opts.output == OUT_MALLOC:
+                    arr = arr.copy()
+                if self.opts.output == OUT_MALLOC:
+                    self.L.free(fi.buffer)
+            else:
+                arr = np.zeros(0, dt)
+            out.append(dict(pcm=arr, samples=int(fi.samples), channels=fi.channels, hz=fi.hz, layer=fi.layer,
+                            avg_bitrate_kbps=fi.avg_bitrate_kbps))
+        return list(self.rets)[:self.n], out
+
+
 def mp3dec_decode_batch_cuda(streams, **kw):
-    """Decode a list of byte buffers.  Per-stream results follow mp3dec_load_buf (minimp3_ex.h:308-525)."""
-    p = BatchPlan(streams, **kw)
-    try:
-        p.run()
-        return p.fetch(copy=True)
-    finally:
-        p.close()
+    """Decode a list of byte buffers through the C entry point mp3dec_decode_batch_cuda().  Per-stream results
+    follow mp3dec_load_buf (minimp3_ex.h:308-525).  Returns (rets, list of dict(pcm, samples, channels, ...))."""
+    b = _Batch(streams, **kw)
+    b.call()
+    return b.results(copy=True)
 
 
 def mp3dec_load_buf(data, float_output=False):

@@ -13,6 +13,8 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <functional>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -30,33 +32,105 @@ double now_ms()
     return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
+/* Persistent worker pool for the host stage (frame walk, rebasing, output copies). */
+class HostPool
+{
+public:
+    static HostPool &get()
+    {
+        static HostPool p;
+        return p;
+    }
+    /* runs f(i) for i in [0, n) on up to `threads` workers (0 = all) plus the calling thread */
+    void run(int n, int threads, const std::function<void(int)> &f)
+    {
+        if (n <= 0) return;
+        int want = threads <= 0 ? (int)workers_.size() + 1 : threads;
+        want = std::min(want, n);
+        if (want <= 1 || workers_.empty())
+        {
+            for (int i = 0; i < n; i++) f(i);
+            return;
+        }
+        std::unique_lock<std::mutex> call_lock(call_mu_);     /* one parallel region at a time */
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            fn_ = &f; n_ = n; next_.store(0); active_ = 0; helpers_ = std::min(want - 1, (int)workers_.size());
+            generation_++;
+        }
+        cv_.notify_all();
+        for (;;)
+        {
+            const int i = next_.fetch_add(1);
+            if (i >= n) break;
+            f(i);
+        }
+        std::unique_lock<std::mutex> lk(mu_);
+        done_cv_.wait(lk, [&] { return active_ == 0 && started_ == helpers_; });
+        fn_ = nullptr;
+        started_ = 0;
+    }
+
+private:
+    HostPool()
+    {
+        int n = (int)std::thread::hardware_concurrency();
+        if (n <= 0) n = 1;
+        for (int t = 0; t < n - 1; t++) workers_.emplace_back([this, t] { loop(t); });
+    }
+    ~HostPool()
+    {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            stop_ = true;
+            generation_++;
+        }
+        cv_.notify_all();
+        for (auto &w : workers_) w.join();
+    }
+    void loop(int id)
+    {
+        uint64_t seen = 0;
+        for (;;)
+        {
+            const std::function<void(int)> *fn;
+            int n;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [&] { return generation_ != seen; });
+                seen = generation_;
+                if (stop_) return;
+                if (id >= helpers_ || !fn_) continue;
+                fn = fn_; n = n_;
+                active_++; started_++;
+            }
+            for (;;)
+            {
+                const int i = next_.fetch_add(1);
+                if (i >= n) break;
+                (*fn)(i);
+            }
+            {
+                std::lock_guard<std::mutex> lk(mu_);
+                active_--;
+            }
+            done_cv_.notify_all();
+        }
+    }
+    std::vector<std::thread> workers_;
+    std::mutex mu_, call_mu_;
+    std::condition_variable cv_, done_cv_;
+    const std::function<void(int)> *fn_ = nullptr;
+    int n_ = 0, active_ = 0, started_ = 0, helpers_ = 0;
+    std::atomic<int> next_{0};
+    uint64_t generation_ = 0;
+    bool stop_ = false;
+};
+
 template <class F>
 void parallel_for(int n, int threads, F f)
 {
-    if (threads <= 0)
-    {
-        threads = (int)std::thread::hardware_concurrency();
-        if (threads <= 0) threads = 1;
-    }
-    threads = std::min(threads, n);
-    if (threads <= 1)
-    {
-        for (int i = 0; i < n; i++) f(i);
-        return;
-    }
-    std::atomic<int> next(0);
-    std::vector<std::thread> pool;
-    pool.reserve(threads);
-    for (int t = 0; t < threads; t++)
-        pool.emplace_back([&]() {
-            for (;;)
-            {
-                const int i = next.fetch_add(1);
-                if (i >= n) break;
-                f(i);
-            }
-        });
-    for (auto &th : pool) th.join();
+    HostPool::get().run(n, threads, std::function<void(int)>(f));
 }
 
 struct DevBuf
@@ -112,7 +186,8 @@ struct DeviceCtx
     int device = -1;
     bool ready = false;
     DeviceTables tables{};
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;      /* H2D + kernels */
+    cudaStream_t stream_d2h = nullptr;  /* PCM read-back, overlaps the next chunk's kernels */
     std::mutex mu;
     std::vector<BufferSet *> free_sets;
     /* single-frame API scratch */
@@ -138,7 +213,8 @@ DeviceCtx *get_ctx(int device)
     if (cudaSetDevice(device) != cudaSuccess) return nullptr;
     DeviceCtx *c = new DeviceCtx();
     c->device = device;
-    if (tables_upload(&c->tables) != 0 || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess)
+    if (tables_upload(&c->tables) != 0 || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&c->stream_d2h, cudaStreamNonBlocking) != cudaSuccess)
     {
         fprintf(stderr, "minimp3_b200: CUDA initialisation failed: %s\n", cudaGetErrorString(cudaGetLastError()));
         delete c;
@@ -164,7 +240,7 @@ BufferSet *acquire_set(DeviceCtx *c)
 void release_set(DeviceCtx *c, BufferSet *s)
 {
     std::lock_guard<std::mutex> lock(c->mu);
-    if (c->free_sets.size() < 2) c->free_sets.push_back(s);
+    if (c->free_sets.size() < 16) c->free_sets.push_back(s);
     else { s->release(); delete s; }
 }
 
@@ -184,7 +260,8 @@ struct mp3dec_batch_plan
     uint64_t md_bytes = 0, n_gc = 0, n_tiles = 0, n_samples = 0, n_ist = 0, n_order = 0, n_frames = 0, input_bytes = 0;
     size_t sample_size = 2;
     bool taps = false;
-    bool fetched_pinned = false;
+    cudaEvent_t ev_kernels = nullptr, ev_d2h = nullptr;
+    bool d2h_started = false;
     mp3dec_batch_stats_t stats{};
 };
 
@@ -209,8 +286,17 @@ void mp3dec_batch_shard(const size_t *sizes, int n_streams, int n_shards, int *s
     }
 }
 
+static mp3dec_batch_plan_t *plan_create_impl(const mp3dec_batch_stream_t *streams, int n_streams,
+                                             const mp3dec_batch_opts_t *opts_in, int *err, bool async);
+
 mp3dec_batch_plan_t *mp3dec_batch_plan_create(const mp3dec_batch_stream_t *streams, int n_streams,
                                               const mp3dec_batch_opts_t *opts_in, int *err)
+{
+    return plan_create_impl(streams, n_streams, opts_in, err, false);
+}
+
+static mp3dec_batch_plan_t *plan_create_impl(const mp3dec_batch_stream_t *streams, int n_streams,
+                                             const mp3dec_batch_opts_t *opts_in, int *err, bool async)
 {
     int dummy;
     if (!err) err = &dummy;
@@ -326,26 +412,28 @@ mp3dec_batch_plan_t *mp3dec_batch_plan_create(const mp3dec_batch_stream_t *strea
          B.d_xr.ensure((size_t)gcs*576*sizeof(float) + 64) && B.d_nzl.ensure((size_t)gcs*2 + 64) &&
          B.d_istpos.ensure((size_t)gcs*40 + 64) && B.d_pcm.ensure((size_t)samples*P->sample_size + 64);
     if (!ok) { *err = MP3D_E_MEMORY; mp3dec_batch_plan_destroy(P); return nullptr; }
-    cudaEvent_t e0, e1;
-    cudaEventCreate(&e0); cudaEventCreate(&e1);
-    cudaEventRecord(e0, P->stream);
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (!async) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, P->stream); }
     cudaMemcpyAsync(B.d_md.p, B.h_md.p, P->md_bytes, cudaMemcpyHostToDevice, P->stream);
     if (gcs) cudaMemcpyAsync(B.d_gcs.p, B.h_gcs.p, (size_t)gcs*sizeof(GcDesc), cudaMemcpyHostToDevice, P->stream);
     if (tiles) cudaMemcpyAsync(B.d_tiles.p, B.h_tiles.p, (size_t)tiles*sizeof(TileDesc), cudaMemcpyHostToDevice, P->stream);
     if (ists) cudaMemcpyAsync(B.d_istlist.p, B.h_ist.p, (size_t)ists*4, cudaMemcpyHostToDevice, P->stream);
     if (orders) cudaMemcpyAsync(B.d_order.p, B.h_order.p, (size_t)orders*4, cudaMemcpyHostToDevice, P->stream);
-    cudaEventRecord(e1, P->stream);
-    if (cudaStreamSynchronize(P->stream) != cudaSuccess)
-    {
-        fprintf(stderr, "minimp3_b200: H2D failed: %s\n", cudaGetErrorString(cudaGetLastError()));
-        *err = MP3D_E_CUDA;
-        cudaEventDestroy(e0); cudaEventDestroy(e1);
-        mp3dec_batch_plan_destroy(P);
-        return nullptr;
-    }
     float h2d = 0.f;
-    cudaEventElapsedTime(&h2d, e0, e1);
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (!async)
+    {
+        cudaEventRecord(e1, P->stream);
+        if (cudaStreamSynchronize(P->stream) != cudaSuccess)
+        {
+            fprintf(stderr, "minimp3_b200: H2D failed: %s\n", cudaGetErrorString(cudaGetLastError()));
+            *err = MP3D_E_CUDA;
+            cudaEventDestroy(e0); cudaEventDestroy(e1);
+            mp3dec_batch_plan_destroy(P);
+            return nullptr;
+        }
+        cudaEventElapsedTime(&h2d, e0, e1);
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+    }
 
     P->stats.input_bytes = P->input_bytes;
     P->stats.samples = samples;
@@ -483,22 +571,33 @@ int mp3dec_batch_plan_read_tap(mp3dec_batch_plan_t *P, int which, void *dst, siz
     return 0;
 }
 
-int mp3dec_batch_plan_fetch(mp3dec_batch_plan_t *P, mp3dec_file_info_t *infos, int *rets)
+/* starts the PCM read-back behind the kernels already queued on the plan's stream */
+static int plan_begin_fetch(mp3dec_batch_plan_t *P, cudaStream_t copy_stream)
 {
-    if (!P) return MP3D_E_PARAM;
-    cudaSetDevice(P->ctx->device);
+    BufferSet &B = *P->bufs;
+    const size_t ss = P->sample_size;
+    if (P->opts.output == MP3D_BATCH_OUT_DEVICE || !P->n_samples) { P->d2h_started = true; return 0; }
+    if (!B.h_pcm.ensure((size_t)P->n_samples*ss + 64)) return MP3D_E_MEMORY;
+    if (copy_stream != P->stream)
+    {
+        if (!P->ev_kernels) cudaEventCreateWithFlags(&P->ev_kernels, cudaEventDisableTiming);
+        cudaEventRecord(P->ev_kernels, P->stream);
+        cudaStreamWaitEvent(copy_stream, P->ev_kernels, 0);
+    }
+    cudaMemcpyAsync(B.h_pcm.p, B.d_pcm.p, (size_t)P->n_samples*ss, cudaMemcpyDeviceToHost, copy_stream);
+    if (!P->ev_d2h) cudaEventCreateWithFlags(&P->ev_d2h, cudaEventDisableTiming);
+    cudaEventRecord(P->ev_d2h, copy_stream);
+    P->d2h_started = true;
+    return 0;
+}
+
+static int plan_finish_fetch(mp3dec_batch_plan_t *P, mp3dec_file_info_t *infos, int *rets)
+{
     BufferSet &B = *P->bufs;
     const size_t ss = P->sample_size;
     const int mode = P->opts.output;
-    uint8_t *host = nullptr;
-    if (mode != MP3D_BATCH_OUT_DEVICE)
-    {
-        if (!B.h_pcm.ensure((size_t)P->n_samples*ss + 64)) return MP3D_E_MEMORY;
-        host = (uint8_t *)B.h_pcm.p;
-        if (P->n_samples)
-            cudaMemcpyAsync(host, B.d_pcm.p, (size_t)P->n_samples*ss, cudaMemcpyDeviceToHost, P->stream);
-    }
-    cudaError_t e = cudaStreamSynchronize(P->stream);
+    uint8_t *host = (uint8_t *)B.h_pcm.p;
+    cudaError_t e = P->ev_d2h ? cudaEventSynchronize(P->ev_d2h) : cudaStreamSynchronize(P->stream);
     if (e != cudaSuccess)
     {
         fprintf(stderr, "minimp3_b200: decode failed: %s\n", cudaGetErrorString(e));
@@ -529,6 +628,20 @@ int mp3dec_batch_plan_fetch(mp3dec_batch_plan_t *P, mp3dec_file_info_t *infos, i
     return oom ? MP3D_E_MEMORY : 0;
 }
 
+int mp3dec_batch_plan_fetch(mp3dec_batch_plan_t *P, mp3dec_file_info_t *infos, int *rets)
+{
+    if (!P) return MP3D_E_PARAM;
+    cudaSetDevice(P->ctx->device);
+    if (!P->d2h_started)
+    {
+        const int r = plan_begin_fetch(P, P->stream);
+        if (r) return r;
+    }
+    const int r = plan_finish_fetch(P, infos, rets);
+    P->d2h_started = false;
+    return r;
+}
+
 void mp3dec_batch_plan_stats(const mp3dec_batch_plan_t *P, mp3dec_batch_stats_t *out)
 {
     if (P && out) *out = P->stats;
@@ -537,19 +650,63 @@ void mp3dec_batch_plan_stats(const mp3dec_batch_plan_t *P, mp3dec_batch_stats_t 
 void mp3dec_batch_plan_destroy(mp3dec_batch_plan_t *P)
 {
     if (!P) return;
+    if (P->ev_kernels) cudaEventDestroy(P->ev_kernels);
+    if (P->ev_d2h) cudaEventDestroy(P->ev_d2h);
     if (P->bufs) release_set(P->ctx, P->bufs);
     delete P;
 }
 
+/* Whole batch in one call.  Large batches are cut into chunks of streams and pipelined: while chunk c is being
+ * decoded and its PCM travels back over PCIe (second stream), the host threads already walk chunk c+1 and its
+ * bitstream goes up.  Per-stream results are independent of the chunking. */
 int mp3dec_decode_batch_cuda(const mp3dec_batch_stream_t *streams, int n_streams, mp3dec_file_info_t *infos_out,
                              int *rets_out, const mp3dec_batch_opts_t *opts)
 {
+    if (!streams || n_streams < 0) return MP3D_E_PARAM;
     int err = 0;
-    mp3dec_batch_plan_t *P = mp3dec_batch_plan_create(streams, n_streams, opts, &err);
-    if (!P) return err;
-    err = mp3dec_batch_plan_run(P);
-    if (!err) err = mp3dec_batch_plan_fetch(P, infos_out, rets_out);
-    mp3dec_batch_plan_destroy(P);
+    const bool user_stream = opts && opts->cuda_stream;
+    int n_chunks = 1;
+    if (!user_stream && n_streams >= 64)
+    {
+        size_t total = 0;
+        for (int i = 0; i < n_streams; i++) total += streams[i].size;
+        n_chunks = (int)std::min<size_t>(8, std::max<size_t>(1, total/(8u << 20)));   /* >= 8 MB of input per chunk */
+        n_chunks = std::min(n_chunks, n_streams/32);
+        if (n_chunks < 1) n_chunks = 1;
+    }
+    if (n_chunks == 1)
+    {
+        mp3dec_batch_plan_t *P = mp3dec_batch_plan_create(streams, n_streams, opts, &err);
+        if (!P) return err;
+        err = mp3dec_batch_plan_run(P);
+        if (!err) err = mp3dec_batch_plan_fetch(P, infos_out, rets_out);
+        mp3dec_batch_plan_destroy(P);
+        return err;
+    }
+    std::vector<mp3dec_batch_plan_t *> plans(n_chunks, nullptr);
+    std::vector<int> first(n_chunks + 1);
+    for (int c = 0; c <= n_chunks; c++) first[c] = (int)((int64_t)n_streams*c/n_chunks);
+    for (int c = 0; c < n_chunks && !err; c++)
+    {
+        plans[c] = plan_create_impl(streams + first[c], first[c + 1] - first[c], opts, &err, true);
+        if (!plans[c]) break;
+        err = mp3dec_batch_plan_run(plans[c]);
+        if (!err) err = plan_begin_fetch(plans[c], plans[c]->ctx->stream_d2h);
+    }
+    for (int c = 0; c < n_chunks; c++)
+    {
+        if (!plans[c]) continue;
+        if (!err)
+            err = plan_finish_fetch(plans[c], infos_out ? infos_out + first[c] : nullptr, rets_out ? rets_out + first[c] : nullptr);
+        else
+            cudaStreamSynchronize(plans[c]->stream);
+    }
+    for (int c = 0; c < n_chunks; c++)
+        if (plans[c])
+        {
+            if (err) cudaStreamSynchronize(plans[c]->ctx->stream_d2h);
+            mp3dec_batch_plan_destroy(plans[c]);
+        }
     return err;
 }
 
