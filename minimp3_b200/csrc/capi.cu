@@ -170,12 +170,13 @@ struct PinBuf
 /* all device + pinned memory of one in-flight batch; recycled between calls */
 struct BufferSet
 {
-    PinBuf h_md, h_gcs, h_tiles, h_ist, h_order, h_pcm;
-    DevBuf d_md, d_gcs, d_tiles, d_istlist, d_order, d_xr, d_nzl, d_istpos, d_pcm;
+    PinBuf h_md, h_gcs, h_tiles, h_ist, h_order, h_pcm, h_l12, h_tiles12;
+    DevBuf d_md, d_gcs, d_tiles, d_istlist, d_order, d_xr, d_nzl, d_istpos, d_pcm, d_l12, d_tiles12, d_sub12;
     DevBuf d_tap_q, d_tap_scf, d_tap_sub;
     void release()
     {
-        h_md.release(); h_gcs.release(); h_tiles.release(); h_ist.release(); h_order.release(); h_pcm.release();
+        h_md.release(); h_gcs.release(); h_tiles.release(); h_ist.release(); h_order.release(); h_pcm.release(); h_l12.release(); h_tiles12.release();
+        d_l12.release(); d_tiles12.release(); d_sub12.release();
         d_md.release(); d_gcs.release(); d_tiles.release(); d_istlist.release(); d_order.release(); d_xr.release(); d_nzl.release();
         d_istpos.release(); d_pcm.release(); d_tap_q.release(); d_tap_scf.release(); d_tap_sub.release();
     }
@@ -256,7 +257,8 @@ struct mp3dec_batch_plan
     cudaStream_t stream = nullptr;
     int n_streams = 0;
     std::vector<StreamPlan> plans;
-    std::vector<uint64_t> md_base, gc_base, tile_base, pcm_base, ist_base, order_base;
+    std::vector<uint64_t> md_base, gc_base, tile_base, pcm_base, ist_base, order_base, l12_base, blk_base, tile12_base;
+    uint64_t n_l12 = 0, n_blk = 0, n_tiles12 = 0;
     uint64_t md_bytes = 0, n_gc = 0, n_tiles = 0, n_samples = 0, n_ist = 0, n_order = 0, n_frames = 0, input_bytes = 0;
     size_t sample_size = 2;
     bool taps = false;
@@ -349,12 +351,15 @@ static mp3dec_batch_plan_t *plan_create_impl(const mp3dec_batch_stream_t *stream
     /* ---- host stage 2: prefix sums and rebasing into the shared tables ---- */
     P->gc_base.resize(n_streams + 1); P->tile_base.resize(n_streams + 1);
     P->pcm_base.resize(n_streams + 1); P->ist_base.resize(n_streams + 1); P->order_base.resize(n_streams + 1);
-    uint64_t gcs = 0, tiles = 0, samples = 0, ists = 0, orders = 0;
+    P->l12_base.resize(n_streams + 1); P->blk_base.resize(n_streams + 1); P->tile12_base.resize(n_streams + 1);
+    uint64_t gcs = 0, tiles = 0, samples = 0, ists = 0, orders = 0, l12s = 0, blks = 0, tiles12 = 0;
     for (int i = 0; i < n_streams; i++)
     {
         const StreamPlan &sp = P->plans[i];
         P->gc_base[i] = gcs; P->tile_base[i] = tiles; P->pcm_base[i] = samples; P->ist_base[i] = ists; P->order_base[i] = orders;
         orders += sp.order.size();
+        P->l12_base[i] = l12s; P->blk_base[i] = blks; P->tile12_base[i] = tiles12;
+        l12s += sp.l12_frames.size(); blks += sp.n_blockch; tiles12 += sp.tiles12.size();
         gcs += round_up(sp.gcs.size(), 2);
         tiles += sp.tiles.size();
         samples += sp.samples_decoded;
@@ -364,15 +369,19 @@ static mp3dec_batch_plan_t *plan_create_impl(const mp3dec_batch_stream_t *stream
     }
     P->gc_base[n_streams] = gcs; P->tile_base[n_streams] = tiles; P->pcm_base[n_streams] = samples; P->ist_base[n_streams] = ists;
     P->n_gc = gcs; P->n_tiles = tiles; P->n_samples = samples; P->n_ist = ists; P->n_order = orders;
+    P->n_l12 = l12s; P->n_blk = blks; P->n_tiles12 = tiles12;
     if (gcs >= (1ull << 31)) { *err = MP3D_E_PARAM; mp3dec_batch_plan_destroy(P); return nullptr; }
 
     bool ok = B.h_gcs.ensure((size_t)gcs*sizeof(GcDesc) + 64) && B.h_tiles.ensure((size_t)tiles*sizeof(TileDesc) + 64) &&
-              B.h_ist.ensure((size_t)ists*4 + 64) && B.h_order.ensure((size_t)orders*4 + 64);
+              B.h_ist.ensure((size_t)ists*4 + 64) && B.h_order.ensure((size_t)orders*4 + 64) &&
+              B.h_l12.ensure((size_t)l12s*sizeof(L12FrameDesc) + 64) && B.h_tiles12.ensure((size_t)tiles12*sizeof(TileDesc) + 64);
     if (!ok) { *err = MP3D_E_MEMORY; mp3dec_batch_plan_destroy(P); return nullptr; }
     GcDesc *h_gcs = (GcDesc *)B.h_gcs.p;
     TileDesc *h_tiles = (TileDesc *)B.h_tiles.p;
     uint32_t *h_ist = (uint32_t *)B.h_ist.p;
     uint32_t *h_order = (uint32_t *)B.h_order.p;
+    L12FrameDesc *h_l12 = (L12FrameDesc *)B.h_l12.p;
+    TileDesc *h_tiles12 = (TileDesc *)B.h_tiles12.p;
     parallel_for(n_streams, opts.host_threads, [&](int i) {
         StreamPlan &sp = P->plans[i];
         const uint64_t gb = P->gc_base[i];
@@ -397,6 +406,25 @@ static mp3dec_batch_plan_t *plan_create_impl(const mp3dec_batch_stream_t *stream
         for (size_t k = 0; k < sp.istereo_gcs.size(); k++) h_ist[P->ist_base[i] + k] = sp.istereo_gcs[k] + (uint32_t)gb;
         for (size_t k = 0; k < sp.order.size(); k++) h_order[P->order_base[i] + k] = sp.order[k] + (uint32_t)gb;
         std::vector<uint32_t>().swap(sp.order);
+        const uint64_t bb = P->blk_base[i];
+        for (size_t k = 0; k < sp.l12_frames.size(); k++)
+        {
+            L12FrameDesc f = sp.l12_frames[k];
+            f.block_first += (uint32_t)bb;
+            h_l12[P->l12_base[i] + k] = f;
+        }
+        for (size_t k = 0; k < sp.tiles12.size(); k++)
+        {
+            TileDesc t = sp.tiles12[k];
+            t.gc_first += (uint32_t)bb;
+            t.pcm_off += P->pcm_base[i];
+            for (int c = 0; c < 2; c++)
+                for (int h = 0; h < 2; h++)
+                    if (t.halo[c][h] >= 0) t.halo[c][h] += (int32_t)bb;
+            h_tiles12[P->tile12_base[i] + k] = t;
+        }
+        std::vector<L12FrameDesc>().swap(sp.l12_frames);
+        std::vector<TileDesc>().swap(sp.tiles12);
         /* descriptor vectors are no longer needed on the host */
         std::vector<GcDesc>().swap(sp.gcs);
         std::vector<TileDesc>().swap(sp.tiles);
@@ -408,7 +436,8 @@ static mp3dec_batch_plan_t *plan_create_impl(const mp3dec_batch_stream_t *stream
     /* ---- device buffers + H2D ---- */
     ok = B.d_md.ensure(P->md_bytes) && B.d_gcs.ensure((size_t)gcs*sizeof(GcDesc) + 64) &&
          B.d_tiles.ensure((size_t)tiles*sizeof(TileDesc) + 64) && B.d_istlist.ensure((size_t)ists*4 + 64) &&
-         B.d_order.ensure((size_t)orders*4 + 64) &&
+         B.d_order.ensure((size_t)orders*4 + 64) && B.d_l12.ensure((size_t)l12s*sizeof(L12FrameDesc) + 64) &&
+         B.d_tiles12.ensure((size_t)tiles12*sizeof(TileDesc) + 64) && B.d_sub12.ensure((size_t)blks*384*sizeof(float) + 64) &&
          B.d_xr.ensure((size_t)gcs*576*sizeof(float) + 64) && B.d_nzl.ensure((size_t)gcs*2 + 64) &&
          B.d_istpos.ensure((size_t)gcs*40 + 64) && B.d_pcm.ensure((size_t)samples*P->sample_size + 64);
     if (!ok) { *err = MP3D_E_MEMORY; mp3dec_batch_plan_destroy(P); return nullptr; }
@@ -419,6 +448,8 @@ static mp3dec_batch_plan_t *plan_create_impl(const mp3dec_batch_stream_t *stream
     if (tiles) cudaMemcpyAsync(B.d_tiles.p, B.h_tiles.p, (size_t)tiles*sizeof(TileDesc), cudaMemcpyHostToDevice, P->stream);
     if (ists) cudaMemcpyAsync(B.d_istlist.p, B.h_ist.p, (size_t)ists*4, cudaMemcpyHostToDevice, P->stream);
     if (orders) cudaMemcpyAsync(B.d_order.p, B.h_order.p, (size_t)orders*4, cudaMemcpyHostToDevice, P->stream);
+    if (l12s) cudaMemcpyAsync(B.d_l12.p, B.h_l12.p, (size_t)l12s*sizeof(L12FrameDesc), cudaMemcpyHostToDevice, P->stream);
+    if (tiles12) cudaMemcpyAsync(B.d_tiles12.p, B.h_tiles12.p, (size_t)tiles12*sizeof(TileDesc), cudaMemcpyHostToDevice, P->stream);
     float h2d = 0.f;
     if (!async)
     {
@@ -441,8 +472,9 @@ static mp3dec_batch_plan_t *plan_create_impl(const mp3dec_batch_stream_t *stream
     P->stats.n_tiles = tiles;
     P->stats.n_istereo_granules = ists;
     P->stats.n_frames = P->n_frames;
-    P->stats.h2d_bytes = P->md_bytes + gcs*sizeof(GcDesc) + tiles*sizeof(TileDesc) + ists*4 + orders*4;
-    P->stats.kernels_per_run = (gcs ? 1 : 0) + (ists ? 1 : 0) + (tiles ? 1 : 0);
+    P->stats.h2d_bytes = P->md_bytes + gcs*sizeof(GcDesc) + tiles*sizeof(TileDesc) + ists*4 + orders*4 +
+                         l12s*sizeof(L12FrameDesc) + tiles12*sizeof(TileDesc);
+    P->stats.kernels_per_run = (orders ? 1 : 0) + (ists ? 1 : 0) + (tiles ? 1 : 0) + (l12s ? 1 : 0) + (tiles12 ? 1 : 0);
     P->stats.host_parse_ms = t1 - t0;
     P->stats.h2d_ms = h2d;
     return P;
@@ -461,12 +493,12 @@ int mp3dec_batch_plan_enable_taps(mp3dec_batch_plan_t *P)
 
 static int plan_run_stages(mp3dec_batch_plan_t *P, int stage_mask);
 
-int mp3dec_batch_plan_run(mp3dec_batch_plan_t *P) { return plan_run_stages(P, 7); }
+int mp3dec_batch_plan_run(mp3dec_batch_plan_t *P) { return plan_run_stages(P, 15); }
 
 /* measurement aid: launch a single stage (0 entropy, 1 intensity stereo, 2 transform) on the plan's stream */
 int mp3dec_batch_plan_run_stage(mp3dec_batch_plan_t *P, int stage)
 {
-    if (stage < 0 || stage > 2) return MP3D_E_PARAM;
+    if (stage < 0 || stage > 3) return MP3D_E_PARAM;
     return plan_run_stages(P, 1 << stage);
 }
 
@@ -521,6 +553,22 @@ static int plan_run_stages(mp3dec_batch_plan_t *P, int stage_mask)
         ta.float_output = P->opts.float_output;
         ta.tap_sub = P->taps ? (float *)B.d_tap_sub.p : nullptr;
         e = launch_transform(P->ctx->tables, ta, P->stream);
+    }
+    if (e == cudaSuccess && P->n_l12 && (stage_mask & 8))
+    {
+        Layer12Args la;
+        la.md_words = ea.md_words; la.md_n_words = ea.md_n_words;
+        la.frames = (const L12FrameDesc *)B.d_l12.p; la.n_frames = (uint32_t)P->n_l12;
+        la.sub12 = (float *)B.d_sub12.p;
+        e = launch_l12_dequant(la, P->stream);
+        if (e == cudaSuccess)
+        {
+            Synth12Args sa;
+            memset(&sa, 0, sizeof(sa));
+            sa.tiles = (const TileDesc *)B.d_tiles12.p; sa.n_tiles = (uint32_t)P->n_tiles12;
+            sa.sub12 = la.sub12; sa.pcm = B.d_pcm.p; sa.float_output = P->opts.float_output;
+            e = launch_l12_synth(P->ctx->tables, sa, P->stream);
+        }
     }
     if (e != cudaSuccess)
     {
@@ -612,7 +660,6 @@ static int plan_finish_fetch(mp3dec_batch_plan_t *P, mp3dec_file_info_t *infos, 
         memset(&fi, 0, sizeof(fi));
         fi.samples = (size_t)sp.out_samples;
         fi.channels = sp.channels; fi.hz = sp.hz; fi.layer = sp.layer; fi.avg_bitrate_kbps = sp.avg_bitrate_kbps;
-        if (sp.ret == MP3D_E_UNSUPPORTED) { fi.samples = 0; return; }
         const size_t first = (size_t)(P->pcm_base[i] + sp.out_skip)*ss;
         if (!sp.out_samples) return;
         if (mode == MP3D_BATCH_OUT_DEVICE) fi.buffer = (mp3d_sample_t *)((uint8_t *)B.d_pcm.p + first);

@@ -9,6 +9,7 @@
 
 #include <algorithm>
 
+#include "l12_decode.cuh"
 #include "mp3_tables.h"
 
 namespace mp3b {
@@ -318,9 +319,23 @@ void parse_frame(SyncState *st, const uint8_t *mp3, int mp3_bytes, FrameParse *o
 
     if (out->layer != 3)
     {
-        /* Layer I/II payload is handled by the caller (not on the CUDA path yet) */
+        /* Layer I/II (minimp3.h:1783-1802): the frame is dropped (and the decoder re-initialised) when its bit
+         * allocation asks for more bits than the frame holds */
         out->payload = bs.buf + bs.pos/8;
         out->payload_bytes = (bs.limit - bs.pos)/8;
+        BitReader pr;
+        pr.init(out->payload, out->payload_bytes);
+        L12Info sci;
+        l12_read_scale_info(hdr, hdr_bitrate_kbps(hdr), pr, &sci, false);
+        const int group = out->layer | 1;
+        const long total_bits = (long)pr.pos + 12L*l12_subblock_bits(sci, group);
+        out->success = total_bits <= (long)pr.limit;
+        if (!out->success)
+        {
+            st->header[0] = 0;
+            out->init_only = true;
+            return;
+        }
         out->samples = (int)hdr_frame_samples(hdr);
         return;
     }
@@ -458,11 +473,15 @@ static void build_tiles(StreamPlan *plan, int tile_granules)
     uint64_t pcm_off = 0;
     size_t n = plan->granules.size();
     size_t g = 0;
+    int last_kind = -1;
     while (g < n)
     {
         const GranuleRef &first = plan->granules[g];
-        if (first.reset)
+        /* a layer change always comes with a decoder reset (hdr_compare checks the layer bits) */
+        if (first.reset || first.kind != last_kind)
             chain[0][0] = chain[0][1] = chain[1][0] = chain[1][1] = -1;
+        last_kind = first.kind;
+        const uint32_t per_gr = first.kind ? 384u : 576u;
         TileDesc t;
         memset(&t, 0, sizeof(t));
         t.gc_first = first.gc;
@@ -473,18 +492,19 @@ static void build_tiles(StreamPlan *plan, int tile_granules)
         while (g < n && cnt < tile_granules)
         {
             const GranuleRef &r = plan->granules[g];
-            if (cnt && (r.reset || r.nch != first.nch || r.gc != first.gc + (uint32_t)(cnt*first.nch))) break;
+            if (cnt && (r.reset || r.kind != first.kind || r.nch != first.nch || r.gc != first.gc + (uint32_t)(cnt*first.nch))) break;
             for (int c = 0; c < r.nch; c++)
             {
                 chain[c][1] = chain[c][0];
                 chain[c][0] = (int32_t)(r.gc + c);
             }
-            pcm_off += 576u*r.nch;
+            pcm_off += per_gr*r.nch;
             cnt++;
             g++;
         }
         t.n_gr = (uint8_t)cnt;
-        plan->tiles.push_back(t);
+        if (first.kind) plan->tiles12.push_back(t);
+        else plan->tiles.push_back(t);
     }
 }
 
@@ -495,7 +515,8 @@ static void build_order(StreamPlan *plan)
     const size_t n = plan->gcs.size();
     std::vector<uint8_t> real(n, 0);
     for (const GranuleRef &g : plan->granules)
-        for (int c = 0; c < g.nch; c++) real[g.gc + c] = 1;
+        if (!g.kind)
+            for (int c = 0; c < g.nch; c++) real[g.gc + c] = 1;
     uint32_t count[257];
     memset(count, 0, sizeof(count));
     for (size_t i = 0; i < n; i++)
@@ -605,6 +626,7 @@ void walk_stream(const uint8_t *buf, size_t size, uint8_t *md_dst, uint64_t md_b
                     gref.gc = (uint32_t)plan->gcs.size();
                     gref.nch = (uint8_t)fp.nch;
                     gref.reset = pending_reset ? 1 : 0;
+                    gref.kind = 0;
                     pending_reset = false;
                     plan->granules.push_back(gref);
                     if (istereo) plan->istereo_gcs.push_back(gref.gc);
@@ -635,9 +657,51 @@ void walk_stream(const uint8_t *buf, size_t size, uint8_t *md_dst, uint64_t md_b
             md_len += (uint64_t)fp.payload_bytes;
         } else if (fp.layer && fp.layer != 3 && fp.samples)
         {
-            plan->has_layer12 = true;
-            plan->ret = -6;              /* MP3D_E_UNSUPPORTED: Layer I/II not on the CUDA path yet */
-            break;
+            bool stop = false;
+            if (!opt.raw_frames)
+            {
+                if (plan->hz != fp.info.hz || plan->layer != fp.info.layer) { plan->ret = -5; stop = true; }
+                else if (plan->channels && plan->channels != fp.info.channels)
+                {
+                    if (opt.allow_mono_stereo) plan->channels = 0;
+                    else { plan->ret = -5; stop = true; }
+                }
+            }
+            if (stop) break;
+            L12FrameDesc fd;
+            memset(&fd, 0, sizeof(fd));
+            fd.bit_off = md_base_bits + md_len*8u;
+            fd.block_first = plan->n_blockch;
+            memcpy(fd.hdr, fp.hdr, 4);
+            fd.kbps = (uint16_t)fp.info.bitrate_kbps;
+            fd.nch = (uint8_t)fp.nch;
+            fd.n_blocks = (uint8_t)(fp.layer == 1 ? 1 : 3);
+            plan->l12_frames.push_back(fd);
+            for (int b = 0; b < fd.n_blocks; b++)
+            {
+                GranuleRef gref;
+                gref.gc = plan->n_blockch;
+                gref.nch = (uint8_t)fp.nch;
+                gref.reset = pending_reset ? 1 : 0;
+                gref.kind = 1;
+                pending_reset = false;
+                plan->granules.push_back(gref);
+                plan->n_blockch += (uint32_t)fp.nch;
+            }
+            memcpy(md_dst + md_len, fp.payload, (size_t)fp.payload_bytes);
+            md_len += ((uint64_t)fp.payload_bytes + 3u) & ~3ull;     /* keep every frame payload word-aligned */
+            plan->frames_decoded++;
+            if (opt.raw_frames && !plan->hz)
+            {
+                plan->hz = fp.info.hz; plan->layer = fp.info.layer; plan->channels = fp.info.channels;
+            }
+            uint64_t s = (uint64_t)fp.samples*(uint64_t)fp.info.channels;
+            plan->samples_decoded += s;
+            uint64_t skip = std::min(s, skip_left);
+            skip_left -= skip;
+            delivered += s - skip;
+            bitrate_sum += (uint64_t)fp.info.bitrate_kbps;
+            frames_counted++;
         }
         buf += fp.info.frame_bytes;
         size -= (size_t)fp.info.frame_bytes;

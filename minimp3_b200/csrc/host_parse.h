@@ -65,9 +65,10 @@ int sample_rate_class(const uint8_t *hdr);   /* 0..7, row of the sfb tables */
 /* A decoded granule of the stream in output order. */
 struct GranuleRef
 {
-    uint32_t gc;       /* stream-relative index of channel 0's GcDesc */
+    uint32_t gc;       /* stream-relative index of channel 0's GcDesc (Layer III) or block-channel (Layer I/II) */
     uint8_t nch;
     uint8_t reset;     /* decoder state was zeroed before this granule */
+    uint8_t kind;      /* 0: Layer III granule (576 samples/channel), 1: Layer I/II block (384 samples/channel) */
 };
 
 /* Everything the walker learns about one stream.  Indices are stream-relative until rebase(). */
@@ -83,6 +84,9 @@ struct StreamPlan
     std::vector<GcDesc> gcs;
     std::vector<GranuleRef> granules;
     std::vector<TileDesc> tiles;
+    std::vector<L12FrameDesc> l12_frames;  /* Layer I/II frames; block indices stream-relative */
+    std::vector<TileDesc> tiles12;         /* synthesis tiles over Layer I/II blocks */
+    uint32_t n_blockch = 0;                /* Layer I/II block-channels */
     uint64_t main_data_bytes = 0;
     uint32_t frames = 0, frames_decoded = 0;
     bool has_layer12 = false;
@@ -137,7 +141,7 @@ struct FrameParse
     int main_data_begin = 0;
     const uint8_t *payload = nullptr;  /* bytes after the side info */
     int payload_bytes = 0;
-    bool success = false;       /* reservoir holds main_data_begin bytes */
+    bool success = false;       /* reservoir holds main_data_begin bytes (Layer III) / payload not overrun (I/II) */
     GranuleSide side[4];
     const uint8_t *hdr = nullptr;
 };

@@ -82,7 +82,7 @@ __device__ __forceinline__ uint32_t f2s16_rn_sat(float x)
  * V_t[32 + j] = -y_t[ib] (signs folded into the taps).  One thread = one output phase j of one granule, both
  * channels; the 16-slot history lives in registers.  The two phases the reference rounds with its scalar
  * helper (j = 0, 16) are parked in shared memory and finished by a separate pass. */
-template <bool FLOAT_OUT, int NCH>
+template <bool FLOAT_OUT, int NCH, int SLOTS, int ROWS>
 __device__ __forceinline__ void fir_phase(const float *ybase, const float *__restrict__ fir_coef, float *special,
                                           void *pcm, uint64_t pcm_off, int n_gr, int tid)
 {
@@ -98,12 +98,12 @@ __device__ __forceinline__ void fir_phase(const float *ybase, const float *__res
     const int ia = j < 16 ? 16 + j : (j == 16 ? 0 : 48 - j);
     const int ib = j <= 16 ? 16 - j : j - 16;
     const bool is_special = !FLOAT_OUT && ((j & 15) == 0);
-    float res[NCH][18];
+    float res[NCH][SLOTS];
 #pragma unroll
     for (int ch = 0; ch < NCH; ch++)
     {
-        const float *ya = ybase + (ch*kRows + i*18)*kYPitch + ia;
-        const float *yb = ybase + (ch*kRows + i*18)*kYPitch + ib;
+        const float *ya = ybase + (ch*ROWS + i*SLOTS)*kYPitch + ia;
+        const float *yb = ybase + (ch*ROWS + i*SLOTS)*kYPitch + ib;
         float A[16], B[16];
 #pragma unroll
         for (int h = 0; h < 15; h++)
@@ -112,7 +112,7 @@ __device__ __forceinline__ void fir_phase(const float *ybase, const float *__res
             B[h] = yb[h*kYPitch];
         }
 #pragma unroll
-        for (int tt = 0; tt < 18; tt++)
+        for (int tt = 0; tt < SLOTS; tt++)
         {
             const int cur = (15 + tt) & 15;
             A[cur] = ya[(15 + tt)*kYPitch];
@@ -129,28 +129,28 @@ __device__ __forceinline__ void fir_phase(const float *ybase, const float *__res
     }
     if (FLOAT_OUT)
     {
-        float *p = reinterpret_cast<float *>(pcm) + pcm_off + (size_t)(i*576 + j)*NCH;
+        float *p = reinterpret_cast<float *>(pcm) + pcm_off + (size_t)(i*SLOTS*32 + j)*NCH;
         const float k = 1.0f/32768.0f;
 #pragma unroll
-        for (int tt = 0; tt < 18; tt++)
+        for (int tt = 0; tt < SLOTS; tt++)
         {
             if (NCH == 2) *reinterpret_cast<float2 *>(p + tt*64) = make_float2(res[0][tt]*k, res[NCH - 1][tt]*k);
             else p[tt*32] = res[0][tt]*k;
         }
     } else if (is_special)
     {
-        float *sp = special + ((i*2 + (j >> 4))*18)*NCH;
+        float *sp = special + ((i*2 + (j >> 4))*SLOTS)*NCH;
 #pragma unroll
-        for (int tt = 0; tt < 18; tt++)
+        for (int tt = 0; tt < SLOTS; tt++)
         {
             sp[tt*NCH] = res[0][tt];
             if (NCH == 2) sp[tt*NCH + 1] = res[NCH - 1][tt];
         }
     } else
     {
-        int16_t *p = reinterpret_cast<int16_t *>(pcm) + pcm_off + (size_t)(i*576 + j)*NCH;
+        int16_t *p = reinterpret_cast<int16_t *>(pcm) + pcm_off + (size_t)(i*SLOTS*32 + j)*NCH;
 #pragma unroll
-        for (int tt = 0; tt < 18; tt++)
+        for (int tt = 0; tt < SLOTS; tt++)
         {
             if (NCH == 2)
                 *reinterpret_cast<uint32_t *>(p + tt*64) = f2s16_rn_sat(res[0][tt]) | (f2s16_rn_sat(res[NCH - 1][tt]) << 16);
@@ -161,14 +161,14 @@ __device__ __forceinline__ void fir_phase(const float *ybase, const float *__res
 }
 
 /* the 2-of-32 outputs the reference produces through mp3d_scale_pcm (truncate(x + .5) - (x < 0)) */
-template <int NCH>
+template <int NCH, int SLOTS>
 __device__ __forceinline__ void special_round_pass(const float *special, void *pcm, uint64_t pcm_off, int n_gr, int tid)
 {
-    const int n = n_gr*2*18;
+    const int n = n_gr*2*SLOTS;
     for (int k = tid; k < n; k += kThreads)
     {
-        const int tt = k % 18, ih = k/18, h = ih & 1, i = ih >> 1;
-        int16_t *p = reinterpret_cast<int16_t *>(pcm) + pcm_off + (size_t)(i*576 + tt*32 + h*16)*NCH;
+        const int tt = k % SLOTS, ih = k/SLOTS, h = ih & 1, i = ih >> 1;
+        int16_t *p = reinterpret_cast<int16_t *>(pcm) + pcm_off + (size_t)(i*SLOTS*32 + tt*32 + h*16)*NCH;
         const int16_t l = pcm_round_scalar(special[k*NCH]);
         if (NCH == 2)
         {
@@ -399,13 +399,13 @@ k_l3_transform(TransformArgs a, const uint16_t *__restrict__ reorder_map, const 
 
     /* ---- phase 5: window FIR + PCM conversion ---- */
     float *special = S.x + kYFloats;     /* slack behind Y: n_gr*2*18*nch floats */
-    if (nch == 2) fir_phase<FLOAT_OUT, 2>(S.x, fir_coef, special, a.pcm, tile.pcm_off, n_gr, tid);
-    else fir_phase<FLOAT_OUT, 1>(S.x, fir_coef, special, a.pcm, tile.pcm_off, n_gr, tid);
+    if (nch == 2) fir_phase<FLOAT_OUT, 2, 18, kRows>(S.x, fir_coef, special, a.pcm, tile.pcm_off, n_gr, tid);
+    else fir_phase<FLOAT_OUT, 1, 18, kRows>(S.x, fir_coef, special, a.pcm, tile.pcm_off, n_gr, tid);
     if (!FLOAT_OUT)
     {
         __syncthreads();
-        if (nch == 2) special_round_pass<2>(special, a.pcm, tile.pcm_off, n_gr, tid);
-        else special_round_pass<1>(special, a.pcm, tile.pcm_off, n_gr, tid);
+        if (nch == 2) special_round_pass<2, 18>(special, a.pcm, tile.pcm_off, n_gr, tid);
+        else special_round_pass<1, 18>(special, a.pcm, tile.pcm_off, n_gr, tid);
     }
 
     /* ---- carried state out (single-frame API): tails of the last granule + last 15 transformed slots ---- */
@@ -423,6 +423,77 @@ k_l3_transform(TransformArgs a, const uint16_t *__restrict__ reorder_map, const 
             a.state_out[576 + ch*480 + rem] = S.x[(ch*kRows + 18*n_gr + row)*kYPitch + col];
         }
     }
+}
+
+/* ---- Layer I/II synthesis (mp3d_synth_granule with 12 slots, minimp3.h:1793): the blocks already hold subband
+ * samples, so a tile is just: load rows (15 history slots from the two previous blocks), DCT-II, window. ---- */
+constexpr int kRows12 = 15 + 12*GT;
+constexpr int kY12Floats = 2*kRows12*kYPitch;
+
+template <bool FLOAT_OUT>
+__global__ void __launch_bounds__(kThreads, 3)
+k_l12_synth(Synth12Args a, const float *__restrict__ fir_coef)
+{
+    __shared__ float y[kY12Floats + GT*2*12*2];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const TileDesc tile = a.tiles[blockIdx.x];
+    const int nch = tile.nch, n_gr = tile.n_gr;
+    const bool stateful = a.state_in != nullptr;
+    const int rows_ch = 15 + 12*n_gr;
+
+    /* rows -> shared: row r of channel ch is slot (r - 15) of the tile; r < 15 comes from the halo blocks */
+    for (int job = warp; job < rows_ch*nch; job += kThreads/32)
+    {
+        const int ch = job >= rows_ch ? 1 : 0, r = job - ch*rows_ch;
+        float v = 0.f;
+        if (r >= 15)
+        {
+            const int b = (r - 15)/12, slot = (r - 15) - b*12;
+            v = __ldg(a.sub12 + (size_t)(tile.gc_first + b*nch + ch)*384 + slot*32 + lane);
+        } else if (stateful)
+        {
+            v = 0.f;     /* carried history is already transformed; filled after the DCT */
+        } else
+        {
+            const int blk = r >= 3 ? tile.halo[ch][0] : tile.halo[ch][1];
+            const int slot = r >= 3 ? r - 3 : 9 + r;
+            if (blk >= 0) v = __ldg(a.sub12 + (size_t)blk*384 + slot*32 + lane);
+        }
+        y[(ch*kRows12 + r)*kYPitch + lane] = v;
+    }
+    __syncthreads();
+    for (int job = tid; job < rows_ch*nch; job += kThreads)
+    {
+        const int ch = job >= rows_ch ? 1 : 0, r = job - ch*rows_ch;
+        float *row = y + (ch*kRows12 + r)*kYPitch;
+        if (stateful && r < 15)
+        {
+            for (int k = 0; k < 32; k++) row[k] = a.state_in[(ch*15 + r)*32 + k];
+            continue;
+        }
+        float v[32];
+#pragma unroll
+        for (int k = 0; k < 32; k++) v[k] = row[k];
+        dct2_32(v, c_k.dct_sec);
+#pragma unroll
+        for (int k = 0; k < 32; k++) row[k] = v[k];
+    }
+    __syncthreads();
+    float *special = y + kY12Floats;
+    if (nch == 2) fir_phase<FLOAT_OUT, 2, 12, kRows12>(y, fir_coef, special, a.pcm, tile.pcm_off, n_gr, tid);
+    else fir_phase<FLOAT_OUT, 1, 12, kRows12>(y, fir_coef, special, a.pcm, tile.pcm_off, n_gr, tid);
+    if (!FLOAT_OUT)
+    {
+        __syncthreads();
+        if (nch == 2) special_round_pass<2, 12>(special, a.pcm, tile.pcm_off, n_gr, tid);
+        else special_round_pass<1, 12>(special, a.pcm, tile.pcm_off, n_gr, tid);
+    }
+    if (a.state_out)
+        for (int k = tid; k < nch*15*32; k += kThreads)
+        {
+            const int ch = k/480, rem = k - ch*480, row = rem >> 5, col = rem & 31;
+            a.state_out[ch*480 + rem] = y[(ch*kRows12 + 12*n_gr + row)*kYPitch + col];
+        }
 }
 
 }  // namespace
@@ -467,6 +538,14 @@ cudaError_t launch_transform(const DeviceTables &t, const TransformArgs &a, cuda
         if (e != cudaSuccess) return e;
         k_l3_transform<false><<<a.n_tiles, kThreads, smem, s>>>(a, t.reorder_map, t.fir_coef);
     }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_l12_synth(const DeviceTables &t, const Synth12Args &a, cudaStream_t s)
+{
+    if (!a.n_tiles) return cudaSuccess;
+    if (a.float_output) k_l12_synth<true><<<a.n_tiles, kThreads, 0, s>>>(a, t.fir_coef);
+    else k_l12_synth<false><<<a.n_tiles, kThreads, 0, s>>>(a, t.fir_coef);
     return cudaGetLastError();
 }
 

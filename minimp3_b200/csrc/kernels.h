@@ -59,12 +59,35 @@ struct TransformArgs
     float *tap_sub;
 };
 
+struct Layer12Args
+{
+    const uint32_t *md_words;
+    uint64_t md_n_words;
+    const L12FrameDesc *frames;
+    uint32_t n_frames;
+    float *sub12;                 /* [n_blockch][12][32] scaled subband samples */
+};
+
+/* synthesis over Layer I/II blocks: TileDesc.gc_first / halo index block-channels of sub12 */
+struct Synth12Args
+{
+    const TileDesc *tiles;
+    uint32_t n_tiles;
+    const float *sub12;
+    void *pcm;
+    int float_output;
+    const float *state_in;        /* optional carried history [2][15][32] (single-frame API) */
+    float *state_out;
+};
+
 int tables_upload(DeviceTables *t);
 void tables_free(DeviceTables *t);
 
 cudaError_t launch_entropy(const DeviceTables &t, const EntropyArgs &a, cudaStream_t s);
 cudaError_t launch_intensity_stereo(const DeviceTables &t, const StereoArgs &a, cudaStream_t s);
 cudaError_t launch_transform(const DeviceTables &t, const TransformArgs &a, cudaStream_t s);
+cudaError_t launch_l12_dequant(const Layer12Args &a, cudaStream_t s);
+cudaError_t launch_l12_synth(const DeviceTables &t, const Synth12Args &a, cudaStream_t s);
 
 }  // namespace mp3b
 #endif

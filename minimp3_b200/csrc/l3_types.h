@@ -63,4 +63,17 @@ typedef struct
     int32_t  halo[2][2];
 } TileDesc;
 
+
+/* One Layer I / II frame (minimp3.h:1783-1802): payload position + header; its output is n_blocks blocks of
+ * 12 time slots x 32 subbands per channel in the subband buffer sub12[block-channel][12][32]. */
+typedef struct
+{
+    uint64_t bit_off;            /* payload (after header and optional CRC) in the main-data buffer */
+    uint32_t block_first;        /* index of block 0 channel 0 in sub12 */
+    uint8_t  hdr[4];
+    uint16_t kbps;               /* header bitrate, 0 = free format (selects the Layer II allocation table) */
+    uint8_t  nch, n_blocks;      /* n_blocks: 1 (Layer I, 384 samples) or 3 (Layer II, 1152 samples) */
+    uint8_t  pad[12];
+} L12FrameDesc;
+
 #endif

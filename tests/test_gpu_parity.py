@@ -11,7 +11,7 @@ import numpy as np
 import pytest
 
 import conftest
-from conftest import L3_CONFORMANCE, L3_SMOKE, load_iso_pcm, load_vector, psnr
+from conftest import L3_CONFORMANCE, L3_SMOKE, L12_CONFORMANCE, L12_REGRESSION, load_iso_pcm, load_vector, psnr
 
 pytestmark = pytest.mark.gpu
 
@@ -216,10 +216,45 @@ def test_sharding_is_invisible_in_the_output(m):
                 assert np.array_equal(o["pcm"], whole[i]["pcm"])
 
 
-def test_layer12_is_refused_loudly(m):
-    rets, outs = m.mp3dec_decode_batch_cuda([load_vector("l2-fl10"), load_vector("l3-si_huff")])
-    assert rets[0] == m.MP3D_E_UNSUPPORTED and outs[0]["samples"] == 0
-    assert rets[1] == 0 and outs[1]["samples"] == 86400
+@pytest.mark.parametrize("name", L12_CONFORMANCE + L12_REGRESSION)
+def test_layer12_pcm_within_one_lsb(name, m, ref):
+    """Layer I/II: dequantisation + 12-slot synthesis on the GPU against the reference"""
+    data = load_vector(name)
+    want, _ = ref.decode_frames(data)
+    rets, outs = m.mp3dec_decode_batch_cuda([data], raw_frames=True)
+    got = outs[0]["pcm"]
+    assert rets[0] == 0 and len(got) == len(want)
+    if len(want):
+        d = np.abs(got.astype(np.int32) - want.astype(np.int32))
+        assert d.max() <= 1 and (d != 0).mean() < 0.01
+
+
+@pytest.mark.parametrize("name", L12_CONFORMANCE)
+def test_layer12_conformance_psnr(name, m, manifest):
+    data = load_vector(name)
+    rets, outs = m.mp3dec_decode_batch_cuda([data], allow_mono_stereo=True)
+    iso = load_iso_pcm(name)
+    md, ps = psnr(outs[0]["pcm"], iso)
+    assert rets[0] == manifest[name]["load_ret"] and len(outs[0]["pcm"]) == manifest[name]["load_samples"]
+    assert ps >= 96.0 and ps >= manifest[name]["ref_psnr"] - 1.0
+
+
+def test_layer12_float_output(m, ref_f32):
+    data = load_vector("l2-fl12")
+    want, _ = ref_f32.decode_frames(data)
+    rets, outs = m.mp3dec_decode_batch_cuda([data], raw_frames=True, float_output=True)
+    assert np.abs(outs[0]["pcm"] - want).max() <= 1e-5
+
+
+def test_mixed_layer_corpus(m, ref):
+    """BASELINE.json configs[4] in small: one call over Layer I, II and III streams"""
+    names = L12_CONFORMANCE + ["l3-si_huff", "l3-he_mode", "M2L3_compl24", "l3-compl"]
+    datas = [load_vector(n) for n in names]*2
+    rets, outs = m.mp3dec_decode_batch_cuda(datas, raw_frames=True)
+    for d, r, o in zip(datas, rets, outs):
+        want, _ = ref.decode_frames(d)
+        assert r == 0 and len(o["pcm"]) == len(want)
+        assert np.abs(o["pcm"].astype(np.int32) - want.astype(np.int32)).max() <= 1
 
 
 def test_f32_to_s16(m, ref_f32):

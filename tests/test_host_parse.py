@@ -5,7 +5,7 @@ import pytest
 
 import conftest
 import harness
-from conftest import L3_CONFORMANCE, load_vector, real_gc_index
+from conftest import L3_CONFORMANCE, L12_CONFORMANCE, L12_REGRESSION, load_vector, real_gc_index
 
 NONSTD = ["l3-nonstandard-apetag", "l3-nonstandard-big-iscf", "l3-nonstandard-compl-sideinfo-bigvalues",
           "l3-nonstandard-compl-sideinfo-blocktype", "l3-nonstandard-compl-sideinfo-size", "l3-nonstandard-he_44_48khz",
@@ -15,7 +15,7 @@ NONSTD = ["l3-nonstandard-apetag", "l3-nonstandard-big-iscf", "l3-nonstandard-co
           "l3-nonstandard-vbrtag-only", "l3-nonstandard-vbrtag-oob-read"]
 
 
-@pytest.mark.parametrize("name", L3_CONFORMANCE + NONSTD + ["MIPSTest.mp3"])
+@pytest.mark.parametrize("name", L3_CONFORMANCE + NONSTD + ["MIPSTest.mp3"] + L12_CONFORMANCE + L12_REGRESSION)
 def test_raw_frame_walk_matches_reference(name, ref):
     """frames, decoded frames and sample count of the plain mp3dec_decode_frame loop (minimp3.h:1713-1806)"""
     data = load_vector(name)
@@ -27,7 +27,7 @@ def test_raw_frame_walk_matches_reference(name, ref):
     assert w["info"]["ret"] == 0
 
 
-@pytest.mark.parametrize("name", L3_CONFORMANCE + NONSTD)
+@pytest.mark.parametrize("name", L3_CONFORMANCE + NONSTD + L12_CONFORMANCE + L12_REGRESSION)
 def test_load_buf_bookkeeping_matches_reference(name, ref, manifest):
     """return code, delivered samples, channels/hz/layer/avg_bitrate of mp3dec_load_buf (minimp3_ex.h:308-525).
     The reference test binary is built with MINIMP3_ALLOW_MONO_STEREO_TRANSITION, so we compare with it on."""
@@ -119,6 +119,8 @@ def test_empty_and_garbage_inputs():
     assert w["info"]["ret"] in (0, -6)
 
 
-def test_layer12_streams_are_reported_unsupported():
-    w = harness.walk(load_vector("l1-fl1"), raw=False)
-    assert w["info"]["ret"] == -6 and w["info"]["layer"] == 1
+def test_layer12_streams_are_planned():
+    """Layer I/II frames become 384-sample blocks with their own synthesis tiles"""
+    w = harness.walk(load_vector("l2-fl10"), raw=True)
+    assert w["info"]["ret"] == 0 and w["info"]["layer"] == 2 and w["info"]["n_gc"] == 0
+    assert w["info"]["samples_decoded"] == 112896

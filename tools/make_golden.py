@@ -42,7 +42,13 @@ NONSTD = ["l3-nonstandard-apetag", "l3-nonstandard-big-iscf", "l3-nonstandard-co
           "l3-nonstandard-vbrtag-empty", "l3-nonstandard-vbrtag-noframes", "l3-nonstandard-vbrtag-only",
           "l3-nonstandard-vbrtag-oob-read"]
 L12 = ["l1-fl1", "l1-fl2", "l1-fl3", "l1-fl4", "l1-fl5", "l1-fl6", "l1-fl7", "l1-fl8",
-       "l2-fl10", "l2-fl11", "l2-fl12", "l2-fl13", "l2-fl14", "l2-fl15", "l2-fl16", "l2-test32"]
+       "l2-fl10", "l2-fl11", "l2-fl12", "l2-fl13", "l2-fl14", "l2-fl15", "l2-fl16", "l2-test32",
+       "l2-nonstandard-fl1_fl2_ff", "l2-nonstandard-free_format", "l2-nonstandard-test32-size",
+       "ILL2_center2", "ILL2_dual", "ILL2_dynx22", "ILL2_dynx31", "ILL2_dynx32", "ILL2_ext_switching", "ILL2_layer1",
+       "ILL2_layer3", "ILL2_mono", "ILL2_multilingual", "ILL2_overalloc1", "ILL2_overalloc2", "ILL2_prediction",
+       "ILL2_samples", "ILL2_scf63", "ILL2_tca21", "ILL2_tca30", "ILL2_tca30_PC", "ILL2_tca31_PC", "ILL2_tca31_mtx0",
+       "ILL2_tca31_mtx2", "ILL2_tca32_PC", "ILL2_wrongcrc", "ILL4_ext_id1", "ILL4_sync", "ILL4_wrong_length1",
+       "ILL4_wrong_length2", "ILL4_wrongcrc"]
 PERF = ["performance/MIPSTest.mp3"]
 
 
