@@ -21,7 +21,7 @@
 #define MP3D_E_USER    -4
 #define MP3D_E_DECODE  -5
 /* new codes of this library */
-#define MP3D_E_UNSUPPORTED -6   /* stream needs a decode stage that is not on the CUDA path yet (Layer I/II) */
+#define MP3D_E_UNSUPPORTED -6   /* reserved: stream needs a decode stage that is not on the CUDA path */
 #define MP3D_E_CUDA        -7   /* CUDA runtime error / no device */
 
 /* minimp3.h:13-16 */
@@ -66,7 +66,7 @@ extern "C" {
 /* ---- frame API: minimp3.h:29-36 ------------------------------------------------------------- */
 void mp3dec_init(mp3dec_t *dec);
 /* returns samples per channel (0 / 576 / 1152); info->frame_bytes = bytes to drop.  pcm may be NULL
- * (parse only).  Layer I/II frames return 0 samples with frame_bytes set. */
+ * (parse only).  Layers I, II and III are all decoded on the GPU. */
 int mp3dec_decode_frame(mp3dec_t *dec, const uint8_t *mp3, int mp3_bytes, mp3d_sample_t *pcm, mp3dec_frame_info_t *info);
 #ifndef MINIMP3_FLOAT_OUTPUT
 int mp3dec_decode_frame_f32(mp3dec_t *dec, const uint8_t *mp3, int mp3_bytes, float *pcm, mp3dec_frame_info_t *info);

@@ -818,9 +818,67 @@ static int decode_frame_impl(mp3dec_t *dec, const uint8_t *mp3, int mp3_bytes, v
     if (fp.init_only) return 0;
     if (fp.layer != 3)
     {
-        static bool warned = false;
-        if (!warned) { fprintf(stderr, "minimp3_b200: Layer I/II frames are not decoded (CUDA path is Layer III only)\n"); warned = true; }
-        return 0;
+        /* Layer I/II (minimp3.h:1783-1802): dequantise on the GPU, 12-slot synthesis with the carried history */
+        DeviceCtx *ctx = get_ctx(0);
+        if (!ctx) return 0;
+        std::lock_guard<std::mutex> lock(ctx->mu);
+        cudaSetDevice(ctx->device);
+        BufferSet &B = ctx->frame_set;
+        const size_t ss = float_output ? 4 : 2;
+        const int n_blocks = fp.layer == 1 ? 1 : 3, nch = fp.nch;
+        const int n_samples = n_blocks*384*nch;
+        const size_t md_bytes = round_up((size_t)fp.payload_bytes + 64, 16);
+        bool ok = B.h_md.ensure(md_bytes + 256) && B.d_md.ensure(md_bytes) && B.d_l12.ensure(64) && B.d_tiles12.ensure(64) &&
+                  B.d_sub12.ensure(6*384*4) && B.d_pcm.ensure(2304*4) && B.h_pcm.ensure(2304*4) &&
+                  ctx->d_state_in.ensure(1536*4) && ctx->d_state_out.ensure(1536*4) && ctx->h_state.ensure(2*1536*4);
+        if (!ok) return 0;
+        uint8_t *h = (uint8_t *)B.h_md.p;
+        memset(h, 0, md_bytes);
+        memcpy(h, fp.payload, (size_t)fp.payload_bytes);
+        L12FrameDesc fd;
+        memset(&fd, 0, sizeof(fd));
+        memcpy(fd.hdr, fp.hdr, 4);
+        fd.kbps = (uint16_t)fp.info.bitrate_kbps; fd.nch = (uint8_t)nch; fd.n_blocks = (uint8_t)n_blocks;
+        TileDesc tile;
+        memset(&tile, 0, sizeof(tile));
+        tile.n_gr = (uint8_t)n_blocks; tile.nch = (uint8_t)nch;
+        tile.halo[0][0] = tile.halo[0][1] = tile.halo[1][0] = tile.halo[1][1] = -1;
+        memcpy(h + md_bytes, &fd, sizeof(fd));
+        memcpy(h + md_bytes + 64, &tile, sizeof(tile));
+        float *hs = (float *)ctx->h_state.p;
+        memcpy(hs, dec->qmf_state, 960*4);
+        cudaStream_t s = ctx->stream;
+        cudaMemcpyAsync(B.d_md.p, h, md_bytes, cudaMemcpyHostToDevice, s);
+        cudaMemcpyAsync(B.d_l12.p, h + md_bytes, sizeof(fd), cudaMemcpyHostToDevice, s);
+        cudaMemcpyAsync(B.d_tiles12.p, h + md_bytes + 64, sizeof(tile), cudaMemcpyHostToDevice, s);
+        cudaMemcpyAsync(ctx->d_state_in.p, hs, 960*4, cudaMemcpyHostToDevice, s);
+        Layer12Args la;
+        la.md_words = (const uint32_t *)B.d_md.p; la.md_n_words = md_bytes/4;
+        la.frames = (const L12FrameDesc *)B.d_l12.p; la.n_frames = 1; la.sub12 = (float *)B.d_sub12.p;
+        cudaError_t e = launch_l12_dequant(la, s);
+        if (e == cudaSuccess)
+        {
+            Synth12Args sa;
+            memset(&sa, 0, sizeof(sa));
+            sa.tiles = (const TileDesc *)B.d_tiles12.p; sa.n_tiles = 1; sa.sub12 = la.sub12; sa.pcm = B.d_pcm.p;
+            sa.float_output = float_output;
+            sa.state_in = (const float *)ctx->d_state_in.p; sa.state_out = (float *)ctx->d_state_out.p;
+            e = launch_l12_synth(ctx->tables, sa, s);
+        }
+        if (e == cudaSuccess)
+        {
+            cudaMemcpyAsync(B.h_pcm.p, B.d_pcm.p, (size_t)n_samples*ss, cudaMemcpyDeviceToHost, s);
+            cudaMemcpyAsync(hs + 1536, ctx->d_state_out.p, 960*4, cudaMemcpyDeviceToHost, s);
+            e = cudaStreamSynchronize(s);
+        }
+        if (e != cudaSuccess)
+        {
+            fprintf(stderr, "minimp3_b200: frame decode failed: %s\n", cudaGetErrorString(e));
+            return 0;
+        }
+        memcpy(pcm, B.h_pcm.p, (size_t)n_samples*ss);
+        for (int ch = 0; ch < nch; ch++) memcpy(dec->qmf_state + ch*480, hs + 1536 + ch*480, 480*4);
+        return (int)hdr_frame_samples(fp.hdr);
     }
     /* L3_restore_reservoir (minimp3.h:1228-1236): main data = tail of the reservoir + this payload */
     const int reserv_old = fp.reset ? 0 : reserv_before;

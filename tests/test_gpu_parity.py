@@ -124,7 +124,8 @@ def test_float_output_within_1e5(name, m, ref_f32):
     assert np.abs(got - want).max() <= 1e-5
 
 
-@pytest.mark.parametrize("name", ["l3-compl", "l3-he_mode", "l3-si_block", "M2L3_compl24", "l3-he_free"])
+@pytest.mark.parametrize("name", ["l3-compl", "l3-he_mode", "l3-si_block", "M2L3_compl24", "l3-he_free", "l1-fl4", "l2-fl13",
+                                  "l2-fl10", "ILL2_layer3", "l2-nonstandard-fl1_fl2_ff"])
 def test_frame_api_matches_reference(name, m, ref):
     """mp3dec_init + mp3dec_decode_frame loop (README usage): per-call return value, frame_bytes, info and PCM"""
     data = load_vector(name)
