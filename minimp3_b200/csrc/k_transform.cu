@@ -59,6 +59,7 @@ struct SlotMeta
     int map;         /* reorder map row or -1 */
     int ms;          /* plain MS stereo applied on load: 0 none, 1 this row = L + R, 2 this row = L - R */
     int nzl_other;   /* extent of the partner channel's row (ms != 0) */
+    int act;         /* subbands that can hold non-zero lines after antialias (0..32) */
 };
 
 struct Smem
@@ -66,6 +67,8 @@ struct Smem
     float x[kXFloats];      /* spectra, later time/subband matrix Y */
     float t[kTFloats];      /* tails [slot][i][sb] */
     SlotMeta meta[kSlots];
+    int job_start[kSlots + 1];   /* compacted (slot, subband) job list: prefix sums of the per-slot job counts */
+    int njob[kSlots];
 };
 
 /* saturating round-to-nearest-even float -> int16 in one instruction: what the reference's
@@ -191,11 +194,15 @@ k_l3_transform(TransformArgs a, const uint16_t *__restrict__ reorder_map, const 
     const int n_slots = (n_gr + 2)*nch;
     const bool stateful = a.state_in != nullptr;
 
-    /* ---- phase 0: slot table ---- */
+    /* ---- phase 0: slot table; clear the tail region (only active subbands get written) ---- */
+    {
+        float4 *z = reinterpret_cast<float4 *>(S.t);
+        for (int k = tid; k < kTFloats/4; k += kThreads) z[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     if (tid < kSlots)
     {
         SlotMeta m;
-        m.gc = -1; m.nzl = 0; m.block_type = 0; m.n_long = 0; m.map = -1; m.ms = 0; m.nzl_other = 0;
+        m.gc = -1; m.nzl = 0; m.block_type = 0; m.n_long = 0; m.map = -1; m.ms = 0; m.nzl_other = 0; m.act = stateful ? 32 : 0;
         if (tid < n_slots)
         {
             const int i = tid/nch - 2, ch = tid%nch;
@@ -215,14 +222,30 @@ k_l3_transform(TransformArgs a, const uint16_t *__restrict__ reorder_map, const 
                     m.ms = (d.flags1 & GCF1_CH) ? 2 : 1;
                     m.nzl_other = a.nzl[gc ^ 1];
                 }
+                /* lines at or above the decoded extent are zero; antialias leaks 8 lines into the next subband */
+                const int ext = m.ms ? max(m.nzl, m.nzl_other) : m.nzl;
+                m.act = (stateful || m.block_type == 2) ? 32 : (ext ? min(32, (ext + 17)/18 + 1) : 0);
             }
         }
         S.meta[tid] = m;
     }
     __syncthreads();
 
-    /* ---- phase 1: spectra -> shared (short blocks: [window][freq] -> [freq][window] on the fly).
-     * Lines at or beyond nzl were never written by the entropy kernel and are zero by definition. ---- */
+    /* job list of the IMDCT phases: only subbands that are active in the granule itself or in the one before it
+     * (whose tail overlaps into this one) need work, everything else is exactly zero */
+    if (tid < n_slots)
+    {
+        int jobs_before = 0;
+        for (int sl = 0; sl < tid; sl++) jobs_before += max(S.meta[sl].act, sl >= nch ? S.meta[sl - nch].act : 0);
+        const int nj = max(S.meta[tid].act, tid >= nch ? S.meta[tid - nch].act : 0);
+        S.njob[tid] = nj;
+        S.job_start[tid] = jobs_before;
+        if (tid == n_slots - 1) S.job_start[n_slots] = jobs_before + nj;
+    }
+
+    /* ---- phase 1: spectra -> shared (short blocks: [window][freq] -> [freq][window] on the fly; plain MS
+     * stereo as L+R / L-R of the two rows).  Lines at or beyond nzl were never written by the entropy kernel
+     * and are zero by definition. ---- */
     for (int slot = warp; slot < n_slots; slot += kThreads/32)
     {
         const SlotMeta m = S.meta[slot];
@@ -284,37 +307,28 @@ k_l3_transform(TransformArgs a, const uint16_t *__restrict__ reorder_map, const 
     }
     __syncthreads();
 
-    /* ---- phases 2+3a: per (slot, subband): antialias butterflies against both neighbours (minimp3.h:1012-1045,
-     * recomputed on the fly instead of a separate in-place pass), then IMDCT tail and own half ---- */
+    /* ---- phases 2+3a: per active (slot, subband): antialias butterflies against both neighbours
+     * (minimp3.h:1012-1045, recomputed on the fly instead of a separate in-place pass), then IMDCT tail and
+     * own half ---- */
     constexpr int kJobs3 = (kSlots*32 + kThreads - 1)/kThreads;   /* 3 */
     float own[kJobs3][9];
+    const int n_jobs3 = S.job_start[n_slots];
+    int job_slot[kJobs3], job_sb[kJobs3];
 #pragma unroll
     for (int r = 0; r < kJobs3; r++)
     {
         const int job = tid + r*kThreads;
-        const int slot = job >> 5, sb = job & 31;
-        if (slot < n_slots)
+        int slot = 0;
+        if (job < n_jobs3)
+            while (job >= S.job_start[slot + 1]) slot++;
+        const int sb = job - S.job_start[slot];
+        job_slot[r] = job < n_jobs3 ? slot : -1;
+        job_sb[r] = sb;
+#pragma unroll
+        for (int k = 0; k < 9; k++) own[r][k] = 0.f;
+        if (job < n_jobs3)
         {
             const SlotMeta m = S.meta[slot];
-            float x[18], tail[9];
-            const float *src = S.x + slot*kXSlot + sb*kXPitch;
-#pragma unroll
-            for (int k = 0; k < 18; k++) x[k] = src[k];
-            const int aa_bands = m.block_type == 2 ? m.n_long - 1 : 31;
-            if (sb >= 1 && sb - 1 < aa_bands)
-            {
-                /* boundary below: this subband holds the "u" side */
-#pragma unroll
-                for (int i = 0; i < 8; i++) x[i] = x[i]*c_k.aa_cs[i] - src[-kXPitch + 17 - i]*c_k.aa_ca[i];
-            }
-            if (sb < aa_bands)
-            {
-                /* boundary above: this subband holds the "d" side */
-#pragma unroll
-                for (int i = 0; i < 8; i++) x[17 - i] = src[kXPitch + i]*c_k.aa_ca[i] + x[17 - i]*c_k.aa_cs[i];
-            }
-            if (m.block_type == 2 && sb >= m.n_long) imdct_short_core(x, own[r], tail, c_k.twid3);
-            else imdct36_core(x, own[r], tail, c_k.twid9);
             float *t = S.t + slot*288 + sb;
             if (stateful && slot < 2*nch)
             {
@@ -323,8 +337,27 @@ k_l3_transform(TransformArgs a, const uint16_t *__restrict__ reorder_map, const 
                 const bool newest = slot >= nch;
 #pragma unroll
                 for (int i = 0; i < 9; i++) t[i*32] = newest ? a.state_in[ch*288 + sb*9 + i] : 0.f;
-            } else
+            } else if (sb < m.act)
             {
+                float x[18], tail[9];
+                const float *src = S.x + slot*kXSlot + sb*kXPitch;
+#pragma unroll
+                for (int k = 0; k < 18; k++) x[k] = src[k];
+                const int aa_bands = m.block_type == 2 ? m.n_long - 1 : 31;
+                if (sb >= 1 && sb - 1 < aa_bands)
+                {
+                    /* boundary below: this subband holds the "u" side */
+#pragma unroll
+                    for (int i = 0; i < 8; i++) x[i] = x[i]*c_k.aa_cs[i] - src[-kXPitch + 17 - i]*c_k.aa_ca[i];
+                }
+                if (sb < aa_bands)
+                {
+                    /* boundary above: this subband holds the "d" side */
+#pragma unroll
+                    for (int i = 0; i < 8; i++) x[17 - i] = src[kXPitch + i]*c_k.aa_ca[i] + x[17 - i]*c_k.aa_cs[i];
+                }
+                if (m.block_type == 2 && sb >= m.n_long) imdct_short_core(x, own[r], tail, c_k.twid3);
+                else imdct36_core(x, own[r], tail, c_k.twid9);
 #pragma unroll
                 for (int i = 0; i < 9; i++) t[i*32] = tail[i];
             }
@@ -332,13 +365,19 @@ k_l3_transform(TransformArgs a, const uint16_t *__restrict__ reorder_map, const 
     }
     __syncthreads();
 
+    /* the spectra are consumed: clear the time/subband matrix that takes their place (inactive subbands stay 0) */
+    {
+        float4 *z = reinterpret_cast<float4 *>(S.x);
+        for (int k = tid; k < (kYFloats + 3)/4; k += kThreads) z[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncthreads();
+
     /* ---- phase 3b: overlap with the previous granule's tail, frequency inversion, write Y[time][subband] ---- */
 #pragma unroll
     for (int r = 0; r < kJobs3; r++)
     {
-        const int job = tid + r*kThreads;
-        const int slot = job >> 5, sb = job & 31;
-        if (slot < n_slots && slot >= nch)
+        const int slot = job_slot[r], sb = job_sb[r];
+        if (slot >= nch)
         {
             const SlotMeta m = S.meta[slot];
             const int i = slot/nch - 2, ch = slot%nch;

@@ -27,13 +27,13 @@ struct EntropyTables
 };
 
 /* MSB-first bit reader over big-endian bytes, fed by aligned 32-bit loads.  `next` is fetched one refill
- * ahead so the global-load latency overlaps with the decoding of the bits already in `buf`. */
+ * (two words) ahead so the global-load latency overlaps with the decoding of the bits already in `buf`. */
 struct BitRd
 {
     const uint32_t *w;
     uint64_t n_words, widx;
     uint64_t buf;
-    uint32_t next;
+    uint32_t next, next2;   /* two words of lookahead */
     int avail;
     int pos;   /* bits consumed since init */
 
@@ -55,7 +55,8 @@ struct BitRd
         buf <<= sh;
         avail = 64 - sh;
         next = word(widx + 2);
-        widx += 3;
+        next2 = word(widx + 3);
+        widx += 4;
         pos = 0;
     }
     MP3_HD void refill()
@@ -64,7 +65,8 @@ struct BitRd
         {
             buf |= (uint64_t)next << (32 - avail);
             avail += 32;
-            next = word(widx++);
+            next = next2;
+            next2 = word(widx++);
         }
     }
     MP3_HD uint32_t peek(int n) const { return n ? (uint32_t)(buf >> (64 - n)) : 0u; }
