@@ -24,7 +24,7 @@ namespace mp3b {
 
 namespace {
 
-constexpr int kWarpsPerBlock = 8;
+constexpr int kWarpsPerBlock = 16;
 constexpr int kStageLines = 32;
 constexpr int kC1Base = MP3T_HUFF_LUT_SIZE;          /* count1 table A (64 entries) then B (16) */
 constexpr int kStagePitch = 33;
@@ -41,9 +41,8 @@ struct SharedTables
 
 struct WarpScratch
 {
-    float stage[kStageLines*kStagePitch];
+    float stage[kStageLines*kStagePitch];   /* also holds the previous granule's scalefactors during set-up */
     uint8_t iscf[40*32];
-    uint8_t prev[40*32];
 };
 
 __device__ __forceinline__ GcDesc load_desc(const GcDesc *p)
@@ -55,7 +54,7 @@ __device__ __forceinline__ GcDesc load_desc(const GcDesc *p)
     return d;
 }
 
-__global__ void __launch_bounds__(kWarpsPerBlock*32, 3) k_l3_entropy(EntropyArgs a)
+__global__ void __launch_bounds__(kWarpsPerBlock*32, 2) k_l3_entropy(EntropyArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SharedTables &S = *reinterpret_cast<SharedTables *>(smem_raw);
@@ -106,7 +105,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock*32, 3) k_l3_entropy(EntropyArgs
             GcDesc d0;
             const bool use_d0 = valid && (d.flags1 & GCF1_GR1) && d.scfsi;
             if (use_d0) d0 = load_desc(a.gcs + (gc - ((d.flags1 & GCF1_STEREO) ? 2 : 1)));
-            dec.init(d, use_d0 ? &d0 : nullptr, a.md_words, a.md_n_words, T, W.iscf + lane, W.prev + lane, 32,
+            dec.init(d, use_d0 ? &d0 : nullptr, a.md_words, a.md_n_words, T, W.iscf + lane, reinterpret_cast<uint8_t *>(W.stage) + lane, 32,
                      want_ist ? ist_local : nullptr, &n_ist);
             if (want_ist)
             {
@@ -180,7 +179,7 @@ cudaError_t launch_entropy(const DeviceTables &, const EntropyArgs &a, cudaStrea
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const uint32_t n_groups = (a.n_order + 31)/32;
     uint32_t blocks = (n_groups + kWarpsPerBlock - 1)/kWarpsPerBlock;
-    const uint32_t max_blocks = (uint32_t)sms*3;
+    const uint32_t max_blocks = (uint32_t)sms*2;
     if (blocks > max_blocks) blocks = max_blocks;
     k_l3_entropy<<<blocks, kWarpsPerBlock*32, smem, s>>>(a);
     return cudaGetLastError();

@@ -26,16 +26,17 @@ struct EntropyTables
     const uint8_t *sfb_long, *sfb_short, *sfb_mixed;
 };
 
-/* MSB-first bit reader over big-endian bytes, fed by aligned 32-bit loads.  `next` is fetched one refill
- * (two words) ahead so the global-load latency overlaps with the decoding of the bits already in `buf`. */
+/* MSB-first bit reader over big-endian bytes, fed by aligned 32-bit loads.  The 64-bit window is kept as two
+ * 32-bit halves (funnel shifts instead of 64-bit shifts) and two more words are fetched ahead of need so the
+ * global-load latency overlaps with the decoding of the bits already in the window. */
 struct BitRd
 {
     const uint32_t *w;
     uint64_t n_words, widx;
-    uint64_t buf;
+    uint32_t hi, lo;        /* window, MSB-aligned: `avail` valid bits from bit 31 of hi downwards */
     uint32_t next, next2;   /* two words of lookahead */
     int avail;
-    int pos;   /* bits consumed since init */
+    int pos;                /* bits consumed since init */
 
     MP3_HD uint32_t word(uint64_t i) const
     {
@@ -46,13 +47,23 @@ struct BitRd
         return __builtin_bswap32(w[i]);
 #endif
     }
+    /* upper 32 bits of (h:l) << n, 0 <= n < 32 */
+    static MP3_HD uint32_t shl_hi(uint32_t h, uint32_t l, int n)
+    {
+#if defined(__CUDA_ARCH__)
+        return __funnelshift_l(l, h, n);
+#else
+        return n ? (h << n) | (l >> (32 - n)) : h;
+#endif
+    }
     MP3_HD void init(const uint32_t *words, uint64_t nw, uint64_t bit_off)
     {
         w = words; n_words = nw;
         widx = bit_off >> 5;
         const int sh = (int)(bit_off & 31);
-        buf = ((uint64_t)word(widx) << 32) | word(widx + 1);
-        buf <<= sh;
+        const uint32_t w0 = word(widx), w1 = word(widx + 1);
+        hi = shl_hi(w0, w1, sh);
+        lo = w1 << sh;
         avail = 64 - sh;
         next = word(widx + 2);
         next2 = word(widx + 3);
@@ -63,14 +74,23 @@ struct BitRd
     {
         if (avail <= 32)
         {
-            buf |= (uint64_t)next << (32 - avail);
+            /* lo holds no valid bits any more: append `next` right below the avail valid bits of hi */
+            const int sh = 32 - avail;            /* 0..31 */
+            hi |= shl_hi(0u, next, sh);
+            lo = next << sh;
             avail += 32;
             next = next2;
             next2 = word(widx++);
         }
     }
-    MP3_HD uint32_t peek(int n) const { return n ? (uint32_t)(buf >> (64 - n)) : 0u; }
-    MP3_HD void skip(int n) { buf <<= n; avail -= n; pos += n; }
+    MP3_HD uint32_t peek(int n) const { return n ? hi >> (32 - n) : 0u; }
+    MP3_HD void skip(int n)
+    {
+        hi = shl_hi(hi, lo, n);
+        lo <<= n;
+        avail -= n;
+        pos += n;
+    }
     MP3_HD uint32_t get(int n)
     {
         refill();
