@@ -238,7 +238,8 @@ def main():
     parse_ms, h2d_ms = plan.stats["host_parse_ms"], plan.stats["h2d_ms"]
     plan.close()
     e2e_ms = []
-    batch = m._Batch(streams, device=local_rank, raw_frames=False, output=m.OUT_PINNED)
+    host_threads = max(2, (os.cpu_count() or 2)//max(1, int(os.environ.get("LOCAL_WORLD_SIZE", world))))
+    batch = m._Batch(streams, device=local_rank, raw_frames=False, output=m.OUT_PINNED, host_threads=host_threads)
     n_out = 0
     for i in range(args.e2e_steps + 2):
         barrier()
@@ -276,6 +277,7 @@ def main():
                                  % ((st["input_bytes"] + 4*576*st["n_granule_channels"] + 2*samples_per_step)/1e6)},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 2*n_out,
                         "ms_per_step": float(te.item()), "host_parse_ms": parse_ms, "h2d_ms": h2d_ms,
+                        "host_threads_per_rank": host_threads,
                         "api": "mp3dec_decode_batch_cuda(host buffers) -> pinned host PCM, chunk-pipelined inside the call"},
                 "gpu_launches": int(st["kernels_per_run"])*args.steps,
                 "kernels_ms": kern,

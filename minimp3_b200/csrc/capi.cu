@@ -732,7 +732,19 @@ int mp3dec_decode_batch_cuda(const mp3dec_batch_stream_t *streams, int n_streams
     }
     std::vector<mp3dec_batch_plan_t *> plans(n_chunks, nullptr);
     std::vector<int> first(n_chunks + 1);
-    for (int c = 0; c <= n_chunks; c++) first[c] = (int)((int64_t)n_streams*c/n_chunks);
+    /* small first chunks get the PCIe read-back going early; the later ones amortise launch overheads */
+    {
+        double w = 1.0, total_w = 0.0;
+        std::vector<double> weight(n_chunks);
+        for (int c = 0; c < n_chunks; c++) { weight[c] = w; total_w += w; if (c < 3) w *= 2.0; }
+        double acc = 0.0;
+        first[0] = 0;
+        for (int c = 0; c < n_chunks; c++)
+        {
+            acc += weight[c];
+            first[c + 1] = c + 1 == n_chunks ? n_streams : std::max(first[c] + 1, (int)(n_streams*acc/total_w));
+        }
+    }
     for (int c = 0; c < n_chunks && !err; c++)
     {
         plans[c] = plan_create_impl(streams + first[c], first[c + 1] - first[c], opts, &err, true);

@@ -133,19 +133,16 @@ int find_frame(const uint8_t *mp3, int mp3_bytes, int *free_format_bytes, int *p
 
 uint32_t BitReader::get(int n)
 {
-    int start = pos;
+    const int start = pos;
     pos += n;
-    if (pos > limit) return 0;
-    uint32_t v = 0;
-    for (int b = start; b < start + n; )
-    {
-        int take = std::min(8 - (b & 7), start + n - b);
-        uint32_t byte = buf[b >> 3];
-        uint32_t piece = (byte >> (8 - (b & 7) - take)) & ((1u << take) - 1);
-        v = (v << take) | piece;
-        b += take;
-    }
-    return v;
+    if (pos > limit || n == 0) return 0;
+    /* gather the (at most 5) bytes that hold the field, then shift it out */
+    const uint8_t *p = buf + (start >> 3);
+    const int last = (pos - 1) >> 3, first = start >> 3;
+    uint64_t acc = 0;
+    for (int b = first; b <= last; b++) acc = (acc << 8) | *p++;
+    const int tail = 7 - ((pos - 1) & 7);
+    return (uint32_t)((acc >> tail) & ((n >= 32) ? 0xFFFFFFFFull : ((1ull << n) - 1)));
 }
 
 /* ---- side info (minimp3.h:484-607) ------------------------------------------------------------- */
