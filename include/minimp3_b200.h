@@ -82,6 +82,86 @@ int mp3dec_load_buf(mp3dec_t *dec, const uint8_t *buf, size_t buf_size, mp3dec_f
 int mp3dec_load_buf_f32(mp3dec_t *dec, const uint8_t *buf, size_t buf_size, mp3dec_file_info_t *info, MP3D_PROGRESS_CB progress_cb, void *user_data);
 #endif
 
+#ifdef __cplusplus
+}
+#endif
+
+/* ---- iterate / streaming / seek API: minimp3_ex.h:12-29, 45-124 ----------------------------------- */
+#define MP3D_SEEK_TO_BYTE   0
+#define MP3D_SEEK_TO_SAMPLE 1
+#define MP3D_DO_NOT_SCAN    2
+#define MP3D_ALLOW_MONO_STEREO_TRANSITION 4      /* always available here (run-time flag) */
+#define MP3D_FLAGS_MASK 7
+#define MINIMP3_PREDECODE_FRAMES 2
+#define MINIMP3_IO_SIZE (128*1024)
+#define MINIMP3_BUF_SIZE (16*1024)
+
+typedef struct { const uint8_t *buffer; size_t size; } mp3dec_map_info_t;
+typedef struct { uint64_t sample; uint64_t offset; } mp3dec_frame_t;
+typedef struct { mp3dec_frame_t *frames; size_t num_frames, capacity; } mp3dec_index_t;
+typedef size_t (*MP3D_READ_CB)(void *buf, size_t size, void *user_data);
+typedef int (*MP3D_SEEK_CB)(uint64_t position, void *user_data);
+typedef struct { MP3D_READ_CB read; void *read_data; MP3D_SEEK_CB seek; void *seek_data; } mp3dec_io_t;
+
+/* minimp3_ex.h:74-88, same field order */
+typedef struct
+{
+    mp3dec_t mp3d;
+    mp3dec_map_info_t file;
+    mp3dec_io_t *io;
+    mp3dec_index_t index;
+    uint64_t offset, samples, detected_samples, cur_sample, start_offset, end_offset;
+    mp3dec_frame_info_t info;
+    mp3d_sample_t buffer[MINIMP3_MAX_SAMPLES_PER_FRAME];
+    size_t input_consumed, input_filled;
+    int is_file, flags, vbr_tag_found, indexes_built;
+    int free_format_bytes;
+    int buffer_samples, buffer_consumed, to_skip, start_delay;
+    int last_error;
+} mp3dec_ex_t;
+
+typedef int (*MP3D_ITERATE_CB)(void *user_data, const uint8_t *frame, int frame_size, int free_format_bytes,
+                               size_t buf_size, uint64_t offset, mp3dec_frame_info_t *info);
+
+#ifdef MINIMP3_FLOAT_OUTPUT
+#define mp3dec_ex_open_buf mp3dec_ex_open_buf_f32
+#define mp3dec_ex_open_cb mp3dec_ex_open_cb_f32
+#define mp3dec_ex_open mp3dec_ex_open_f32
+#define mp3dec_ex_close mp3dec_ex_close_f32
+#define mp3dec_ex_seek mp3dec_ex_seek_f32
+#define mp3dec_ex_read_frame mp3dec_ex_read_frame_f32
+#define mp3dec_ex_read mp3dec_ex_read_f32
+#define mp3dec_load_cb mp3dec_load_cb_f32
+#define mp3dec_load mp3dec_load_f32
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+int mp3dec_detect_cb(mp3dec_io_t *io, uint8_t *buf, size_t buf_size);                                  /* minimp3_ex.h:99 */
+int mp3dec_load_cb(mp3dec_t *dec, mp3dec_io_t *io, uint8_t *buf, size_t buf_size, mp3dec_file_info_t *info,
+                   MP3D_PROGRESS_CB progress_cb, void *user_data);                                     /* :102 */
+int mp3dec_iterate_buf(const uint8_t *buf, size_t buf_size, MP3D_ITERATE_CB callback, void *user_data); /* :104 */
+int mp3dec_iterate_cb(mp3dec_io_t *io, uint8_t *buf, size_t buf_size, MP3D_ITERATE_CB callback, void *user_data); /* :105 */
+int mp3dec_ex_open_buf(mp3dec_ex_t *dec, const uint8_t *buf, size_t buf_size, int flags);              /* :107 */
+int mp3dec_ex_open_cb(mp3dec_ex_t *dec, mp3dec_io_t *io, int flags);                                   /* :108 */
+void mp3dec_ex_close(mp3dec_ex_t *dec);                                                                /* :109 */
+int mp3dec_ex_seek(mp3dec_ex_t *dec, uint64_t position);                                               /* :110 */
+size_t mp3dec_ex_read_frame(mp3dec_ex_t *dec, mp3d_sample_t **buf, mp3dec_frame_info_t *frame_info, size_t max_samples); /* :111 */
+size_t mp3dec_ex_read(mp3dec_ex_t *dec, mp3d_sample_t *buf, size_t samples);                           /* :112 */
+/* stdio flavours (:115-118): the file is read into memory and handed to the buffer flavours */
+int mp3dec_detect(const char *file_name);
+int mp3dec_load(mp3dec_t *dec, const char *file_name, mp3dec_file_info_t *info, MP3D_PROGRESS_CB progress_cb, void *user_data);
+int mp3dec_iterate(const char *file_name, MP3D_ITERATE_CB callback, void *user_data);
+int mp3dec_ex_open(mp3dec_ex_t *dec, const char *file_name, int flags);
+#ifdef __cplusplus
+}
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
 /* ---- batch API (new) --------------------------------------------------------------- */
 typedef struct
 {

@@ -59,7 +59,30 @@ EXPORTS = ["mp3dec_init", "mp3dec_decode_frame", "mp3dec_decode_frame_f32", "mp3
            "mp3dec_load_buf", "mp3dec_load_buf_f32", "mp3dec_decode_batch_cuda", "mp3dec_batch_plan_create",
            "mp3dec_batch_plan_run", "mp3dec_batch_plan_run_stage", "mp3dec_batch_plan_sync", "mp3dec_batch_plan_fetch", "mp3dec_batch_plan_stats",
            "mp3dec_batch_plan_device_pcm", "mp3dec_batch_plan_destroy", "mp3dec_batch_plan_enable_taps",
-           "mp3dec_batch_plan_read_tap", "mp3dec_batch_shard", "mp3dec_b200_version"]
+           "mp3dec_batch_plan_read_tap", "mp3dec_batch_shard", "mp3dec_b200_version",
+           "mp3dec_detect_cb", "mp3dec_load_cb", "mp3dec_iterate_buf", "mp3dec_iterate_cb", "mp3dec_ex_open_buf",
+           "mp3dec_ex_open_cb", "mp3dec_ex_close", "mp3dec_ex_seek", "mp3dec_ex_read_frame", "mp3dec_ex_read",
+           "mp3dec_detect", "mp3dec_load", "mp3dec_iterate", "mp3dec_ex_open"]
+
+
+class MapInfo(C.Structure):
+    _fields_ = [("buffer", C.c_void_p), ("size", C.c_size_t)]
+
+
+class IndexT(C.Structure):
+    _fields_ = [("frames", C.c_void_p), ("num_frames", C.c_size_t), ("capacity", C.c_size_t)]
+
+
+class Mp3DecEx(C.Structure):
+    """mp3dec_ex_t (minimp3_ex.h:74-88), int16 flavour"""
+    _fields_ = [("mp3d", Mp3Dec), ("file", MapInfo), ("io", C.c_void_p), ("index", IndexT),
+                ("offset", C.c_uint64), ("samples", C.c_uint64), ("detected_samples", C.c_uint64),
+                ("cur_sample", C.c_uint64), ("start_offset", C.c_uint64), ("end_offset", C.c_uint64),
+                ("info", FrameInfo), ("buffer", C.c_int16*MINIMP3_MAX_SAMPLES_PER_FRAME),
+                ("input_consumed", C.c_size_t), ("input_filled", C.c_size_t),
+                ("is_file", C.c_int), ("flags", C.c_int), ("vbr_tag_found", C.c_int), ("indexes_built", C.c_int),
+                ("free_format_bytes", C.c_int), ("buffer_samples", C.c_int), ("buffer_consumed", C.c_int),
+                ("to_skip", C.c_int), ("start_delay", C.c_int), ("last_error", C.c_int)]
 
 _lib = None
 
@@ -105,6 +128,15 @@ def load():
     L.mp3dec_batch_shard.argtypes = [C.POINTER(C.c_size_t), C.c_int, C.c_int, C.POINTER(C.c_int)]
     L.mp3dec_batch_shard.restype = None
     L.mp3dec_b200_version.restype = C.c_char_p
+    L.mp3dec_ex_open_buf.argtypes = [C.POINTER(Mp3DecEx), vp, C.c_size_t, C.c_int]
+    L.mp3dec_ex_open.argtypes = [C.POINTER(Mp3DecEx), C.c_char_p, C.c_int]
+    L.mp3dec_ex_close.argtypes = [C.POINTER(Mp3DecEx)]
+    L.mp3dec_ex_close.restype = None
+    L.mp3dec_ex_seek.argtypes = [C.POINTER(Mp3DecEx), C.c_uint64]
+    L.mp3dec_ex_read.argtypes = [C.POINTER(Mp3DecEx), vp, C.c_size_t]
+    L.mp3dec_ex_read.restype = C.c_size_t
+    L.mp3dec_load.argtypes = [C.POINTER(Mp3Dec), C.c_char_p, C.POINTER(FileInfo), vp, vp]
+    L.mp3dec_detect.argtypes = [C.c_char_p]
     L.free = C.CDLL(None).free
     L.free.argtypes = [vp]
     _lib = L

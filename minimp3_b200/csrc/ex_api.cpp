@@ -1,0 +1,505 @@
+/*
+ * ex_api.cpp -- the iterate / streaming / seek entry points of minimp3_ex.h on top of this library's frame API
+ * (every PCM sample still comes out of the CUDA kernels through mp3dec_decode_frame).
+ *
+ * Host control logic restated from /root/reference/minimp3_ex.h: mp3dec_iterate_buf (:527-564),
+ * mp3dec_load_index (:641-698), mp3dec_ex_open_buf (:700-717), mp3dec_ex_seek incl. the bit-reservoir pre-roll
+ * (:743-893), mp3dec_ex_read_frame / mp3dec_ex_read (:895-1013), the stdio flavours (:1199-1434).
+ * The *_cb flavours read the whole stream through the caller's callbacks into memory first and then run the
+ * buffer flavours (same results; I/O happens up front instead of lazily).
+ */
+#include <limits.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "host_parse.h"
+
+#include "../../include/minimp3_b200.h"
+
+using namespace mp3b;
+
+extern "C" int mp3dec_decode_frame_f32(mp3dec_t *dec, const uint8_t *mp3, int mp3_bytes, float *pcm, mp3dec_frame_info_t *info);
+
+namespace {
+
+template <class S>
+struct ExT   /* mp3dec_ex_t with sample type S (minimp3_ex.h:74-88) */
+{
+    mp3dec_t mp3d;
+    mp3dec_map_info_t file;
+    mp3dec_io_t *io;
+    mp3dec_index_t index;
+    uint64_t offset, samples, detected_samples, cur_sample, start_offset, end_offset;
+    mp3dec_frame_info_t info;
+    S buffer[MINIMP3_MAX_SAMPLES_PER_FRAME];
+    size_t input_consumed, input_filled;
+    int is_file, flags, vbr_tag_found, indexes_built;
+    int free_format_bytes;
+    int buffer_samples, buffer_consumed, to_skip, start_delay;
+    int last_error;
+};
+static_assert(sizeof(ExT<int16_t>) == sizeof(mp3dec_ex_t), "mp3dec_ex_t layout");
+
+inline int decode_frame(mp3dec_t *d, const uint8_t *p, int n, int16_t *pcm, mp3dec_frame_info_t *info)
+{
+    return mp3dec_decode_frame(d, p, n, pcm, info);
+}
+inline int decode_frame(mp3dec_t *d, const uint8_t *p, int n, float *pcm, mp3dec_frame_info_t *info)
+{
+    return mp3dec_decode_frame_f32(d, p, n, pcm, info);
+}
+
+void fill_info(mp3dec_frame_info_t *fi, const uint8_t *hdr, int frame_size)
+{
+    fi->channels = hdr_is_mono(hdr) ? 1 : 2;
+    fi->hz = (int)hdr_sample_rate_hz(hdr);
+    fi->layer = hdr_layer(hdr);
+    fi->bitrate_kbps = (int)hdr_bitrate_kbps(hdr);
+    fi->frame_bytes = frame_size;
+}
+
+/* index builder callback (minimp3_ex.h:641-698) */
+template <class S>
+int load_index(void *user_data, const uint8_t *frame, int frame_size, int free_format_bytes, size_t buf_size,
+               uint64_t offset, mp3dec_frame_info_t *info)
+{
+    ExT<S> *dec = (ExT<S> *)user_data;
+    if (!dec->index.frames && !dec->start_offset)
+    {   /* first frame: a VBR tag makes the full scan unnecessary */
+        uint32_t frames;
+        int delay, padding;
+        dec->info = *info;
+        dec->start_offset = dec->offset = offset;
+        dec->end_offset = offset + buf_size;
+        dec->free_format_bytes = free_format_bytes;
+        if (3 == dec->info.layer)
+        {
+            int ret = check_vbrtag(frame, frame_size, &frames, &delay, &padding);
+            if (ret) dec->start_offset = dec->offset = offset + frame_size;
+            if (ret > 0)
+            {
+                padding *= info->channels;
+                dec->start_delay = dec->to_skip = delay*info->channels;
+                dec->samples = (uint64_t)hdr_frame_samples(frame)*info->channels*(uint64_t)frames;
+                if (dec->samples >= (uint64_t)dec->start_delay) dec->samples -= dec->start_delay;
+                if (padding > 0 && dec->samples >= (uint64_t)padding) dec->samples -= padding;
+                dec->detected_samples = dec->samples;
+                dec->vbr_tag_found = 1;
+                return MP3D_E_USER;
+            } else if (ret < 0)
+                return 0;
+        }
+    }
+    if (dec->flags & MP3D_DO_NOT_SCAN) return MP3D_E_USER;
+    if (dec->index.num_frames + 1 > dec->index.capacity)
+    {
+        dec->index.capacity = dec->index.capacity ? dec->index.capacity*2 : 4096;
+        mp3dec_frame_t *grown = (mp3dec_frame_t *)realloc((void *)dec->index.frames, sizeof(mp3dec_frame_t)*dec->index.capacity);
+        if (!grown) return MP3D_E_MEMORY;
+        dec->index.frames = grown;
+    }
+    mp3dec_frame_t *e = &dec->index.frames[dec->index.num_frames++];
+    e->offset = offset;
+    e->sample = dec->samples;
+    if (!dec->buffer_samples && dec->index.num_frames < 256)
+    {   /* cut files: the first frames may be undecodable until the reservoir fills */
+        dec->buffer_samples = decode_frame(&dec->mp3d, frame, (int)std::min(buf_size, (size_t)INT_MAX), dec->buffer, info);
+        dec->samples += (uint64_t)dec->buffer_samples*info->channels;
+    } else
+        dec->samples += (uint64_t)hdr_frame_samples(frame)*info->channels;
+    return 0;
+}
+
+size_t idx_search(mp3dec_index_t *idx, uint64_t position)   /* minimp3_ex.h:720-740 */
+{
+    size_t end = idx->num_frames, start = 0, index = 0;
+    while (start <= end)
+    {
+        size_t mid = (start + end)/2;
+        if (idx->frames[mid].sample >= position)
+        {
+            if (idx->frames[mid].sample == position) return mid;
+            end = mid - 1;
+        } else
+        {
+            index = mid;
+            start = mid + 1;
+            if (start == idx->num_frames) break;
+        }
+    }
+    return index;
+}
+
+template <class S>
+int ex_open_buf(ExT<S> *dec, const uint8_t *buf, size_t buf_size, int flags)
+{
+    if (!dec || !buf || (size_t)-1 == buf_size || (flags & (~MP3D_FLAGS_MASK))) return MP3D_E_PARAM;
+    memset(dec, 0, sizeof(*dec));
+    dec->file.buffer = buf;
+    dec->file.size = buf_size;
+    dec->flags = flags;
+    mp3dec_init(&dec->mp3d);
+    int ret = mp3dec_iterate_buf(dec->file.buffer, dec->file.size, load_index<S>, dec);
+    if (ret && MP3D_E_USER != ret) return ret;
+    mp3dec_init(&dec->mp3d);
+    dec->buffer_samples = 0;
+    dec->indexes_built = !(dec->vbr_tag_found || (flags & MP3D_DO_NOT_SCAN));
+    dec->flags &= (~MP3D_DO_NOT_SCAN);
+    return 0;
+}
+
+template <class S>
+int ex_seek(ExT<S> *dec, uint64_t position)
+{
+    size_t i;
+    if (!dec) return MP3D_E_PARAM;
+    if (!(dec->flags & MP3D_SEEK_TO_SAMPLE))
+    {
+        dec->offset = std::min<uint64_t>(position, dec->file.size);
+        dec->cur_sample = 0;
+        goto do_exit;
+    }
+    if (dec->samples && position > dec->samples) position = dec->samples;
+    dec->cur_sample = position;
+    if (position > (UINT64_MAX - (uint64_t)dec->start_delay)) position = UINT64_MAX;
+    else position += dec->start_delay;
+    if (0 == position)
+    {
+seek_zero:
+        dec->offset = dec->start_offset;
+        dec->to_skip = 0;
+        goto do_exit;
+    }
+    if (!dec->indexes_built)
+    {   /* opened through a VBR tag or MP3D_DO_NOT_SCAN: build the index now */
+        dec->indexes_built = 1;
+        dec->samples = 0;
+        dec->buffer_samples = 0;
+        int ret = mp3dec_iterate_buf(dec->file.buffer + dec->start_offset, dec->file.size - dec->start_offset, load_index<S>, dec);
+        if (ret && MP3D_E_USER != ret) return ret;
+        for (i = 0; i < dec->index.num_frames; i++) dec->index.frames[i].offset += dec->start_offset;
+        dec->samples = dec->detected_samples;
+    }
+    if (!dec->index.frames) goto seek_zero;
+    i = idx_search(&dec->index, position);
+    if (i)
+    {
+        int to_fill_bytes = 511;
+        i -= std::min(i, (size_t)MINIMP3_PREDECODE_FRAMES);
+        if (3 == dec->info.layer)
+        {
+            while (i && to_fill_bytes)
+            {   /* walk back until the bit reservoir can be full when decoding starts */
+                const uint8_t *hdr = dec->file.buffer + dec->index.frames[i - 1].offset;
+                int frame_size = hdr_frame_bytes(hdr, dec->free_format_bytes) + hdr_padding(hdr);
+                BitReader bs;
+                GranuleSide side[4];
+                bs.init(hdr + 4, frame_size - 4);
+                if (hdr_is_crc(hdr)) bs.get(16);
+                i--;
+                if (read_side_info(&bs, side, hdr) < 0) break;
+                int frame_bytes = (bs.limit - bs.pos)/8;
+                to_fill_bytes -= std::min(to_fill_bytes, frame_bytes);
+            }
+        }
+    }
+    dec->offset = dec->index.frames[i].offset;
+    if (position > dec->index.frames[i].sample)
+    {
+        uint64_t skip64 = position - dec->index.frames[i].sample;
+        dec->to_skip = (skip64 > (uint64_t)INT_MAX) ? INT_MAX : (int)skip64;
+    } else
+        dec->to_skip = 0;
+    while ((i + 1) < dec->index.num_frames && !dec->index.frames[i].sample && !dec->index.frames[i + 1].sample)
+    {   /* leading frames that produced nothing */
+        const uint8_t *hdr = dec->file.buffer + dec->index.frames[i].offset;
+        int frame_samples = (int)hdr_frame_samples(hdr)*dec->info.channels;
+        if (dec->to_skip > (INT_MAX - frame_samples)) dec->to_skip = INT_MAX;
+        else dec->to_skip += frame_samples;
+        i++;
+    }
+do_exit:
+    dec->buffer_samples = 0;
+    dec->buffer_consumed = 0;
+    dec->input_consumed = 0;
+    dec->input_filled = 0;
+    dec->last_error = 0;
+    mp3dec_init(&dec->mp3d);
+    return 0;
+}
+
+template <class S>
+size_t ex_read_frame(ExT<S> *dec, S **buf, mp3dec_frame_info_t *frame_info, size_t max_samples)
+{
+    if (!dec || !buf || !frame_info)
+    {
+        if (dec) dec->last_error = MP3D_E_PARAM;
+        return 0;
+    }
+    if (dec->detected_samples && dec->cur_sample >= dec->detected_samples) return 0;
+    if (dec->last_error) return 0;
+    *buf = NULL;
+    uint64_t end_offset = dec->end_offset ? dec->end_offset : dec->file.size;
+    while (dec->buffer_consumed == dec->buffer_samples)
+    {
+        const uint8_t *dec_buf = dec->file.buffer + dec->offset;
+        uint64_t buf_size = end_offset - dec->offset;
+        if (!buf_size) return 0;
+        dec->buffer_samples = decode_frame(&dec->mp3d, dec_buf, (int)std::min<uint64_t>(buf_size, (uint64_t)INT_MAX), dec->buffer, frame_info);
+        dec->buffer_consumed = 0;
+        if (dec->info.hz != frame_info->hz || dec->info.layer != frame_info->layer)
+        {
+            dec->last_error = MP3D_E_DECODE;
+            return 0;
+        }
+        if (dec->buffer_samples)
+        {
+            dec->buffer_samples *= frame_info->channels;
+            if (dec->to_skip > 0)
+            {
+                int skip = std::min(dec->buffer_samples, dec->to_skip);
+                dec->buffer_consumed += skip;
+                dec->to_skip -= skip;
+            }
+            if (!(dec->flags & MP3D_ALLOW_MONO_STEREO_TRANSITION) && dec->buffer_consumed != dec->buffer_samples &&
+                dec->info.channels != frame_info->channels)
+            {
+                dec->last_error = MP3D_E_DECODE;
+                return 0;
+            }
+        } else if (dec->to_skip > 0)
+        {
+            int frame_samples = (int)hdr_frame_samples(dec_buf)*frame_info->channels;
+            dec->to_skip -= std::min(frame_samples, dec->to_skip);
+        }
+        dec->offset += frame_info->frame_bytes;
+    }
+    size_t out = std::min((size_t)(dec->buffer_samples - dec->buffer_consumed), max_samples);
+    if (dec->detected_samples && dec->cur_sample + out >= dec->detected_samples)
+        out = (size_t)(dec->detected_samples - dec->cur_sample);
+    dec->cur_sample += out;
+    *buf = dec->buffer + dec->buffer_consumed;
+    dec->buffer_consumed += (int)out;
+    return out;
+}
+
+template <class S>
+size_t ex_read(ExT<S> *dec, S *buf, size_t samples)
+{
+    if (!dec || !buf)
+    {
+        if (dec) dec->last_error = MP3D_E_PARAM;
+        return 0;
+    }
+    mp3dec_frame_info_t fi;
+    memset(&fi, 0, sizeof(fi));
+    size_t want = samples;
+    while (samples)
+    {
+        S *frame = NULL;
+        size_t got = ex_read_frame(dec, &frame, &fi, samples);
+        if (!got) break;
+        memcpy(buf, frame, got*sizeof(S));
+        buf += got;
+        samples -= got;
+    }
+    return want - samples;
+}
+
+template <class S>
+void ex_close(ExT<S> *dec)
+{
+    if (!dec) return;
+    if (dec->is_file && dec->file.buffer) free((void *)dec->file.buffer);
+    if (dec->index.frames) free(dec->index.frames);
+    memset(dec, 0, sizeof(*dec));
+}
+
+/* whole stream through the caller's I/O callbacks (seek to 0, read until short) */
+int slurp_io(mp3dec_io_t *io, uint8_t **out, size_t *out_size)
+{
+    if (io->seek(0, io->seek_data)) return MP3D_E_IOERROR;
+    size_t cap = 1 << 20, n = 0;
+    uint8_t *p = (uint8_t *)malloc(cap);
+    if (!p) return MP3D_E_MEMORY;
+    for (;;)
+    {
+        if (n == cap)
+        {
+            uint8_t *g = (uint8_t *)realloc(p, cap*2);
+            if (!g) { free(p); return MP3D_E_MEMORY; }
+            p = g; cap *= 2;
+        }
+        const size_t want = cap - n;
+        size_t r = io->read(p + n, want, io->read_data);
+        if (r > want) { free(p); return MP3D_E_IOERROR; }
+        n += r;
+        if (r != want) break;     /* short read: end of stream */
+    }
+    *out = p; *out_size = n;
+    return 0;
+}
+
+int slurp_file(const char *name, uint8_t **out, size_t *out_size)
+{
+    if (!name) return MP3D_E_PARAM;
+    FILE *f = fopen(name, "rb");
+    if (!f) return MP3D_E_IOERROR;
+    int res = MP3D_E_IOERROR;
+    uint8_t *p = NULL;
+    long size = -1;
+    if (!fseek(f, 0, SEEK_END) && (size = ftell(f)) >= 0 && !fseek(f, 0, SEEK_SET))
+    {
+        p = (uint8_t *)malloc(size ? (size_t)size : 1);
+        if (!p) res = MP3D_E_MEMORY;
+        else if (fread(p, 1, (size_t)size, f) == (size_t)size) res = 0;
+    }
+    fclose(f);
+    if (res) { free(p); return res; }
+    *out = p; *out_size = (size_t)size;
+    return 0;
+}
+
+template <class S>
+int ex_open_owned(ExT<S> *dec, uint8_t *p, size_t n, int flags)
+{
+    int ret = ex_open_buf(dec, p, n, flags);
+    if (ret) { free(p); return ret; }
+    dec->is_file = 1;
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mp3dec_iterate_buf(const uint8_t *buf, size_t buf_size, MP3D_ITERATE_CB callback, void *user_data)
+{
+    const uint8_t *orig = buf;
+    if (!buf || (size_t)-1 == buf_size || !callback) return MP3D_E_PARAM;
+    skip_id3(&buf, &buf_size);
+    if (!buf_size) return 0;
+    mp3dec_frame_info_t fi;
+    memset(&fi, 0, sizeof(fi));
+    for (;;)
+    {
+        int free_format_bytes = 0, frame_size = 0;
+        int i = find_frame(buf, (int)std::min(buf_size, (size_t)INT_MAX), &free_format_bytes, &frame_size);
+        buf += i;
+        buf_size -= i;
+        if (i && !frame_size) continue;
+        if (!frame_size) break;
+        fill_info(&fi, buf, frame_size);
+        int ret = callback(user_data, buf, frame_size, free_format_bytes, buf_size, (uint64_t)(buf - orig), &fi);
+        if (ret) return ret;
+        buf += frame_size;
+        buf_size -= frame_size;
+    }
+    return 0;
+}
+
+int mp3dec_iterate_cb(mp3dec_io_t *io, uint8_t *buf, size_t buf_size, MP3D_ITERATE_CB callback, void *user_data)
+{
+    if (!io || !buf || (size_t)-1 == buf_size || buf_size < MINIMP3_BUF_SIZE || !callback) return MP3D_E_PARAM;
+    uint8_t *p; size_t n;
+    int r = slurp_io(io, &p, &n);
+    if (r) return r;
+    r = mp3dec_iterate_buf(p, n, callback, user_data);
+    free(p);
+    return r;
+}
+
+int mp3dec_detect_cb(mp3dec_io_t *io, uint8_t *buf, size_t buf_size)
+{
+    if (!buf || (size_t)-1 == buf_size || (io && buf_size < MINIMP3_BUF_SIZE)) return MP3D_E_PARAM;
+    if (!io) return mp3dec_detect_buf(buf, buf_size);
+    uint8_t *p; size_t n;
+    int r = slurp_io(io, &p, &n);
+    if (r) return r;
+    r = mp3dec_detect_buf(p, n);
+    free(p);
+    return r;
+}
+
+#define LOAD_CB_IMPL(NAME, LOADBUF)                                                                                  \
+    int NAME(mp3dec_t *dec, mp3dec_io_t *io, uint8_t *buf, size_t buf_size, mp3dec_file_info_t *info,                \
+             MP3D_PROGRESS_CB progress_cb, void *user_data)                                                          \
+    {                                                                                                                \
+        if (!dec || !buf || !info || (size_t)-1 == buf_size || (io && buf_size < MINIMP3_BUF_SIZE)) return MP3D_E_PARAM; \
+        if (!io) return LOADBUF(dec, buf, buf_size, info, progress_cb, user_data);                                   \
+        uint8_t *p; size_t n;                                                                                        \
+        int r = slurp_io(io, &p, &n);                                                                                \
+        if (r) return r;                                                                                             \
+        r = LOADBUF(dec, p, n, info, progress_cb, user_data);                                                        \
+        free(p);                                                                                                     \
+        return r;                                                                                                    \
+    }
+int mp3dec_load_buf_f32(mp3dec_t *, const uint8_t *, size_t, mp3dec_file_info_t *, MP3D_PROGRESS_CB, void *);
+LOAD_CB_IMPL(mp3dec_load_cb, mp3dec_load_buf)
+LOAD_CB_IMPL(mp3dec_load_cb_f32, mp3dec_load_buf_f32)
+
+#define EX_API(SUFFIX, S)                                                                                            \
+    int mp3dec_ex_open_buf##SUFFIX(mp3dec_ex_t *dec, const uint8_t *buf, size_t buf_size, int flags)                 \
+    { return ex_open_buf((ExT<S> *)dec, buf, buf_size, flags); }                                                     \
+    int mp3dec_ex_open_cb##SUFFIX(mp3dec_ex_t *dec, mp3dec_io_t *io, int flags)                                      \
+    {                                                                                                                \
+        if (!dec || !io || (flags & (~MP3D_FLAGS_MASK))) return MP3D_E_PARAM;                                        \
+        uint8_t *p; size_t n;                                                                                        \
+        int r = slurp_io(io, &p, &n);                                                                                \
+        if (r) return r;                                                                                             \
+        return ex_open_owned((ExT<S> *)dec, p, n, flags);                                                            \
+    }                                                                                                                \
+    int mp3dec_ex_open##SUFFIX(mp3dec_ex_t *dec, const char *file_name, int flags)                                   \
+    {                                                                                                                \
+        if (!dec) return MP3D_E_PARAM;                                                                               \
+        uint8_t *p; size_t n;                                                                                        \
+        int r = slurp_file(file_name, &p, &n);                                                                       \
+        if (r) return r;                                                                                             \
+        return ex_open_owned((ExT<S> *)dec, p, n, flags);                                                            \
+    }                                                                                                                \
+    void mp3dec_ex_close##SUFFIX(mp3dec_ex_t *dec) { ex_close((ExT<S> *)dec); }                                      \
+    int mp3dec_ex_seek##SUFFIX(mp3dec_ex_t *dec, uint64_t position) { return ex_seek((ExT<S> *)dec, position); }     \
+    size_t mp3dec_ex_read_frame##SUFFIX(mp3dec_ex_t *dec, S **buf, mp3dec_frame_info_t *fi, size_t max_samples)      \
+    { return ex_read_frame((ExT<S> *)dec, buf, fi, max_samples); }                                                   \
+    size_t mp3dec_ex_read##SUFFIX(mp3dec_ex_t *dec, S *buf, size_t samples) { return ex_read((ExT<S> *)dec, buf, samples); }
+
+EX_API(, int16_t)
+EX_API(_f32, float)
+
+int mp3dec_detect(const char *file_name)
+{
+    uint8_t *p; size_t n;
+    int r = slurp_file(file_name, &p, &n);
+    if (r) return r;
+    r = mp3dec_detect_buf(p, n);
+    free(p);
+    return r;
+}
+
+int mp3dec_iterate(const char *file_name, MP3D_ITERATE_CB callback, void *user_data)
+{
+    uint8_t *p; size_t n;
+    int r = slurp_file(file_name, &p, &n);
+    if (r) return r;
+    r = mp3dec_iterate_buf(p, n, callback, user_data);
+    free(p);
+    return r;
+}
+
+#define LOAD_FILE_IMPL(NAME, LOADBUF)                                                                                \
+    int NAME(mp3dec_t *dec, const char *file_name, mp3dec_file_info_t *info, MP3D_PROGRESS_CB progress_cb, void *user_data) \
+    {                                                                                                                \
+        uint8_t *p; size_t n;                                                                                        \
+        int r = slurp_file(file_name, &p, &n);                                                                       \
+        if (r) return r;                                                                                             \
+        r = LOADBUF(dec, p, n, info, progress_cb, user_data);                                                        \
+        free(p);                                                                                                     \
+        return r;                                                                                                    \
+    }
+LOAD_FILE_IMPL(mp3dec_load, mp3dec_load_buf)
+LOAD_FILE_IMPL(mp3dec_load_f32, mp3dec_load_buf_f32)
+
+}  // extern "C"

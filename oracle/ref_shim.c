@@ -463,3 +463,50 @@ long ref_bench_decode(const uint8_t *const *bufs, const long *sizes, int n, int 
     free(th); free(jobs);
     return total;
 }
+
+/* ------------------------------------------------------------ streaming / seek API (minimp3_ex.h:700-1013) */
+
+/* open_buf + optional seek + read in portions, like minimp3_test.c modes 6-8.  Returns samples read. */
+long ref_ex_decode(const uint8_t *buf, size_t size, int flags, uint64_t seek_pos, size_t portion, mp3d_sample_t *out,
+                   long cap, uint64_t *total_samples, int *open_ret, int *last_error, int *channels, int *hz)
+{
+    static mp3dec_ex_t dec;
+    long got = 0;
+    *open_ret = mp3dec_ex_open_buf(&dec, buf, size, flags);
+    *total_samples = 0;
+    *last_error = 0;
+    if (*open_ret) return 0;
+    *total_samples = dec.samples;
+    *channels = dec.info.channels;
+    *hz = dec.info.hz;
+    if (seek_pos && mp3dec_ex_seek(&dec, seek_pos)) { *last_error = -100; mp3dec_ex_close(&dec); return 0; }
+    if (!portion) portion = 1152;
+    while (got + (long)portion <= cap)
+    {
+        size_t n = mp3dec_ex_read(&dec, out + got, portion);
+        got += (long)n;
+        if (n != portion) break;
+    }
+    *last_error = dec.last_error;
+    mp3dec_ex_close(&dec);
+    return got;
+}
+
+typedef struct { int n; uint64_t offsets[4096]; int frame_sizes[4096]; } ref_iter_log;
+static int ref_iter_cb(void *user, const uint8_t *frame, int frame_size, int free_format_bytes, size_t buf_size, uint64_t offset, mp3dec_frame_info_t *info)
+{
+    ref_iter_log *l = (ref_iter_log *)user;
+    (void)frame; (void)free_format_bytes; (void)buf_size; (void)info;
+    if (l->n < 4096) { l->offsets[l->n] = offset; l->frame_sizes[l->n] = frame_size; }
+    l->n++;
+    return 0;
+}
+int ref_iterate(const uint8_t *buf, size_t size, uint64_t *offsets, int *frame_sizes, int cap)
+{
+    static ref_iter_log l;
+    int i;
+    l.n = 0;
+    mp3dec_iterate_buf(buf, size, ref_iter_cb, &l);
+    for (i = 0; i < l.n && i < cap && i < 4096; i++) { offsets[i] = l.offsets[i]; frame_sizes[i] = l.frame_sizes[i]; }
+    return l.n;
+}

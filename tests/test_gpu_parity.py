@@ -240,6 +240,39 @@ def test_layer12_conformance_psnr(name, m, manifest):
     assert ps >= 96.0 and ps >= manifest[name]["ref_psnr"] - 1.0
 
 
+def test_corrupted_streams_decode_without_faults(m, ref):
+    """byte damage + truncation: same sample counts as the reference, no CUDA error, and -- away from the damage --
+    mostly the same PCM (the reference itself reads stale stack bytes on some malformed granules, so exact
+    equality is only required of the undamaged streams in the same batch)"""
+    import zlib
+    names = ["l3-compl", "l3-he_mode", "l3-si_block", "M2L3_bitrate_22_all", "l2-fl10", "l3-sin1k0db"]
+    datas, clean = [], []
+    for n in names:
+        base = load_vector(n)
+        rng = np.random.default_rng(zlib.crc32(n.encode()))
+        for trial in range(4):
+            d = bytearray(base)
+            for _ in range(10):
+                d[int(rng.integers(0, len(d)))] = int(rng.integers(0, 256))
+            if trial % 2:
+                d = d[:int(rng.integers(len(d)//2, len(d)))]
+            datas.append(bytes(d))
+            clean.append(False)
+        datas.append(base)
+        clean.append(True)
+    rets, outs = m.mp3dec_decode_batch_cuda(datas, raw_frames=True)
+    close = 0
+    for d, c, r, o in zip(datas, clean, rets, outs):
+        want, _ = ref.decode_frames(d)
+        assert r == 0 and len(o["pcm"]) == len(want)
+        if len(want):
+            diff = np.abs(o["pcm"].astype(np.int32) - want.astype(np.int32))
+            if c:
+                assert diff.max() <= 1
+            close += int((diff <= 1).mean() > 0.9)
+    assert close >= len(datas)*0.8
+
+
 def test_layer12_float_output(m, ref_f32):
     data = load_vector("l2-fl12")
     want, _ = ref_f32.decode_frames(data)

@@ -124,3 +124,27 @@ def test_layer12_streams_are_planned():
     w = harness.walk(load_vector("l2-fl10"), raw=True)
     assert w["info"]["ret"] == 0 and w["info"]["layer"] == 2 and w["info"]["n_gc"] == 0
     assert w["info"]["samples_decoded"] == 112896
+
+
+@pytest.mark.parametrize("name", ["l3-compl", "l3-he_mode", "l3-sin1k0db", "M2L3_bitrate_16_all", "l3-he_free", "l2-fl10", "l1-fl1",
+                                  "l2-nonstandard-free_format"])
+def test_corrupted_streams_walk_like_the_reference(name, ref):
+    """robustness: random byte damage (resyncs, bad side info, reservoir underruns, overrunning Layer II frames) must
+    give the same frame boundaries and sample counts as the reference's own parser"""
+    data = bytearray(load_vector(name))
+    import zlib
+    rng = np.random.default_rng(zlib.crc32(name.encode()))
+    for trial in range(24):
+        d = bytearray(data)
+        for _ in range(12):
+            p = int(rng.integers(0, len(d)))
+            d[p] = int(rng.integers(0, 256))
+        if trial % 2:
+            cut = int(rng.integers(len(d)//2, len(d)))
+            d = d[:cut]
+        d = bytes(d)
+        pcm, frames = ref.decode_frames(d)
+        w = harness.walk(d, raw=True)
+        assert w["info"]["frames"] == len(frames), trial
+        assert w["info"]["frames_decoded"] == sum(1 for f in frames if f.samples), trial
+        assert w["info"]["samples_decoded"] == len(pcm), trial
