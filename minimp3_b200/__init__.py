@@ -235,7 +235,8 @@ class BatchPlan:
     def read_tap(self, which):
         n = int(self.stats["n_granule_channels"])
         shapes = {0: ((n, 576), np.int16), 1: ((n, 40), np.float32), 2: ((n, 576), np.float32), 3: ((n, 576), np.float32),
-                  4: ((n, 32), np.uint8), 5: ((n, 40), np.uint8), 6: ((n,), np.uint16)}
+                  4: ((n, 32), np.uint8), 5: ((n, 40), np.uint8), 6: ((n,), np.uint16),
+                  7: ((int(self.stats["n_tiles"]), 16), np.int64)}
         shape, dt = shapes[which]
         a = np.zeros(shape, dt)
         r = self.L.mp3dec_batch_plan_read_tap(self.handle, which, a.ctypes.data, a.nbytes)

@@ -172,13 +172,13 @@ struct BufferSet
 {
     PinBuf h_md, h_gcs, h_tiles, h_ist, h_order, h_pcm, h_l12, h_tiles12;
     DevBuf d_md, d_gcs, d_tiles, d_istlist, d_order, d_xr, d_nzl, d_istpos, d_pcm, d_l12, d_tiles12, d_sub12;
-    DevBuf d_tap_q, d_tap_scf, d_tap_sub;
+    DevBuf d_tap_q, d_tap_scf, d_tap_sub, d_phase_clk;
     void release()
     {
         h_md.release(); h_gcs.release(); h_tiles.release(); h_ist.release(); h_order.release(); h_pcm.release(); h_l12.release(); h_tiles12.release();
         d_l12.release(); d_tiles12.release(); d_sub12.release();
         d_md.release(); d_gcs.release(); d_tiles.release(); d_istlist.release(); d_order.release(); d_xr.release(); d_nzl.release();
-        d_istpos.release(); d_pcm.release(); d_tap_q.release(); d_tap_scf.release(); d_tap_sub.release();
+        d_istpos.release(); d_pcm.release(); d_tap_q.release(); d_tap_scf.release(); d_tap_sub.release(); d_phase_clk.release();
     }
 };
 
@@ -486,7 +486,9 @@ int mp3dec_batch_plan_enable_taps(mp3dec_batch_plan_t *P)
     cudaSetDevice(P->ctx->device);
     BufferSet &B = *P->bufs;
     const size_t n = (size_t)P->n_gc;
-    if (!B.d_tap_q.ensure(n*576*2 + 64) || !B.d_tap_scf.ensure(n*40*4 + 64) || !B.d_tap_sub.ensure(n*576*4 + 64)) return MP3D_E_MEMORY;
+    if (!B.d_tap_q.ensure(n*576*2 + 64) || !B.d_tap_scf.ensure(n*40*4 + 64) || !B.d_tap_sub.ensure(n*576*4 + 64) ||
+        !B.d_phase_clk.ensure((size_t)P->n_tiles*128 + 64)) return MP3D_E_MEMORY;
+    cudaMemset(B.d_phase_clk.p, 0, (size_t)P->n_tiles*128);
     P->taps = true;
     return 0;
 }
@@ -552,6 +554,7 @@ static int plan_run_stages(mp3dec_batch_plan_t *P, int stage_mask)
         ta.pcm = B.d_pcm.p;
         ta.float_output = P->opts.float_output;
         ta.tap_sub = P->taps ? (float *)B.d_tap_sub.p : nullptr;
+        ta.phase_clk = P->taps ? (long long *)B.d_phase_clk.p : nullptr;
         e = launch_transform(P->ctx->tables, ta, P->stream);
     }
     if (e == cudaSuccess && P->n_l12 && (stage_mask & 8))
@@ -610,9 +613,10 @@ int mp3dec_batch_plan_read_tap(mp3dec_batch_plan_t *P, int which, void *dst, siz
     case 4: src = B.d_gcs.p; bytes = n*sizeof(GcDesc); break;
     case 5: src = B.d_istpos.p; bytes = n*40; break;
     case 6: src = B.d_nzl.p; bytes = n*2; break;
+    case 7: src = B.d_phase_clk.p; bytes = (size_t)P->n_tiles*128; break;
     default: return MP3D_E_PARAM;
     }
-    if ((which == 0 || which == 1 || which == 3) && !P->taps) return MP3D_E_PARAM;
+    if ((which == 0 || which == 1 || which == 3 || which == 7) && !P->taps) return MP3D_E_PARAM;
     if (dst_bytes < bytes) return MP3D_E_PARAM;
     if (cudaStreamSynchronize(P->stream) != cudaSuccess) return MP3D_E_CUDA;
     if (bytes && cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost) != cudaSuccess) return MP3D_E_CUDA;

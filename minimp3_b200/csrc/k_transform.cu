@@ -23,6 +23,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 
+#include <cstdlib>
 #include "kernels.h"
 #include "l3_math.cuh"
 #define MP3T_QUAL static const
@@ -36,11 +37,11 @@ namespace {
 constexpr int GT = MP3B_TILE_GRANULES;
 constexpr int kThreads = 256;
 constexpr int kSlots = (GT + 2)*2;          /* granule-channel slots incl. two halo granules per channel */
-constexpr int kXPitch = 19;                 /* 18 lines + 1 pad: conflict-free per-subband access */
-constexpr int kXSlot = 32*kXPitch;          /* 608 floats */
+constexpr int kXPitch = 18;                 /* rows sit in shared memory exactly as in HBM (bulk copies) */
+constexpr int kXSlot = 576;
 constexpr int kRows = 15 + 18*GT;           /* time slots per channel: 15 history + tile */
 constexpr int kYPitch = 33;
-constexpr int kXFloats = kSlots*kXSlot;     /* 12160 */
+constexpr int kXFloats = kSlots*kXSlot;     /* 11520 */
 constexpr int kYFloats = 2*kRows*kYPitch;   /* 10494, aliases XS */
 constexpr int kTFloats = kSlots*288;
 static_assert(kYFloats <= kXFloats, "Y must fit in the X region");
@@ -64,12 +65,39 @@ struct SlotMeta
 
 struct Smem
 {
-    float x[kXFloats];      /* spectra, later time/subband matrix Y */
+    alignas(128) float x[kXFloats];      /* spectra, later time/subband matrix Y */
     float t[kTFloats];      /* tails [slot][i][sb] */
     SlotMeta meta[kSlots];
     int job_start[kSlots + 1];   /* compacted (slot, subband) job list: prefix sums of the per-slot job counts */
     int njob[kSlots];
+    unsigned long long mbar[kThreads/32];   /* one transaction barrier per warp: its rows' bulk copies */
 };
+
+
+/* ---- TMA bulk copy + transaction barrier (PTX ISA: cp.async.bulk, mbarrier) ---- */
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t done;
+    do
+    {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
 
 /* saturating round-to-nearest-even float -> int16 in one instruction: what the reference's
  * min/max + cvtps2dq + packssdw sequence computes (minimp3.h:1541-1542) */
@@ -184,7 +212,7 @@ __device__ __forceinline__ void special_round_pass(const float *special, void *p
 
 template <bool FLOAT_OUT>
 __global__ void __launch_bounds__(kThreads, 3)
-k_l3_transform(TransformArgs a, const uint16_t *__restrict__ reorder_map, const float *__restrict__ fir_coef)
+k_l3_transform(TransformArgs a, const uint16_t *__restrict__ reorder_inv, const float *__restrict__ fir_coef)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Smem &S = *reinterpret_cast<Smem *>(smem_raw);
@@ -193,119 +221,144 @@ k_l3_transform(TransformArgs a, const uint16_t *__restrict__ reorder_map, const 
     const int nch = tile.nch, n_gr = tile.n_gr;
     const int n_slots = (n_gr + 2)*nch;
     const bool stateful = a.state_in != nullptr;
+    int clk_i = 0;
+#define MP3B_STAMP() do { if (a.phase_clk && tid == 0 && clk_i < 16) a.phase_clk[(size_t)blockIdx.x*16 + clk_i++] = clock64(); } while (0)
+    MP3B_STAMP();
 
-    /* ---- phase 0: slot table; clear the tail region (only active subbands get written) ---- */
+    /* ---- phase 0 (warp 0, lane = slot): slot table from the descriptors, one TMA bulk copy per row for its
+     * decoded extent (lines at or beyond nzl were never written by the entropy kernel and are zero by
+     * definition), IMDCT job list.  Rows keep the HBM line order; short blocks are de-interleaved when the
+     * IMDCT jobs read them.  Everybody else clears the tail region meanwhile. ---- */
+    const int n_units = n_slots/nch;           /* granules incl. halo; unit u belongs to warp u % 8 */
+    if (warp == 0)
     {
-        float4 *z = reinterpret_cast<float4 *>(S.t);
-        for (int k = tid; k < kTFloats/4; k += kThreads) z[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    if (tid < kSlots)
-    {
+        if (lane < kThreads/32)
+        {
+            const int owned = lane < n_units ? (n_units - lane + kThreads/32 - 1)/(kThreads/32) : 0;
+            mbar_init(smem_addr(&S.mbar[lane]), (uint32_t)max(1, owned*nch));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
         SlotMeta m;
         m.gc = -1; m.nzl = 0; m.block_type = 0; m.n_long = 0; m.map = -1; m.ms = 0; m.nzl_other = 0; m.act = stateful ? 32 : 0;
-        if (tid < n_slots)
+        if (lane < n_slots)
         {
-            const int i = tid/nch - 2, ch = tid%nch;
-            int gc = i >= 0 ? (int)tile.gc_first + i*nch + ch : (stateful ? -1 : tile.halo[ch][-1 - i]);
+            const int i = lane/nch - 2, ch = lane%nch;
+            const int gc = i >= 0 ? (int)tile.gc_first + i*nch + ch : (stateful ? -1 : tile.halo[ch][-1 - i]);
             if (gc >= 0)
             {
                 const GcDesc d = a.gcs[gc];
+                const int nz = a.nzl[gc], nz_other = a.nzl[gc ^ 1];     /* stereo pairs sit on indices (2k, 2k+1) */
                 m.gc = gc;
-                m.nzl = a.nzl[gc];
+                m.nzl = nz;
                 m.block_type = d.flags0 & GCF_BLOCK_TYPE_MASK;
                 const bool mixed = d.flags0 & GCF_MIXED;
                 m.n_long = mixed ? (d.sr_idx == 1 ? 4 : 2) : 0;   /* 8 kHz MPEG-2.5 keeps 4 long subbands */
                 if (m.block_type == 2) m.map = d.sr_idx*2 + (mixed ? 1 : 0);
                 if (d.flags1 & GCF1_MS_PLAIN)
                 {
-                    /* L3_midside_stereo (minimp3.h:879-909): stereo pairs sit on descriptor indices (2k, 2k+1) */
+                    /* L3_midside_stereo (minimp3.h:879-909) */
                     m.ms = (d.flags1 & GCF1_CH) ? 2 : 1;
-                    m.nzl_other = a.nzl[gc ^ 1];
+                    m.nzl_other = nz_other;
                 }
                 /* lines at or above the decoded extent are zero; antialias leaks 8 lines into the next subband */
                 const int ext = m.ms ? max(m.nzl, m.nzl_other) : m.nzl;
                 m.act = (stateful || m.block_type == 2) ? 32 : (ext ? min(32, (ext + 17)/18 + 1) : 0);
             }
+            const uint32_t bar = smem_addr(&S.mbar[(lane/nch) & (kThreads/32 - 1)]);
+            const uint32_t bytes = (uint32_t)((m.nzl + 3) & ~3)*4u;
+            if (m.gc >= 0 && bytes)
+            {
+                mbar_arrive_expect_tx(bar, bytes);
+                bulk_g2s(smem_addr(S.x + lane*kXSlot), a.xr + (size_t)m.gc*576, bytes, bar);
+            } else
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
         }
-        S.meta[tid] = m;
+        if (lane < kSlots) S.meta[lane] = m;
+        /* job list of the IMDCT phases: only subbands that are active in the granule itself or in the one before
+         * it (whose tail overlaps into this one) need work, everything else is exactly zero */
+        const int act = lane < n_slots ? m.act : 0;
+        int prev_act = __shfl_up_sync(0xffffffffu, act, nch);
+        if (lane < nch) prev_act = 0;
+        const int nj = max(act, prev_act);
+        int incl = nj;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1)
+        {
+            const int v = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += v;
+        }
+        if (lane < n_slots)
+        {
+            S.njob[lane] = nj;
+            S.job_start[lane] = incl - nj;
+            if (lane == n_slots - 1) S.job_start[n_slots] = incl;
+        }
+    }
+    {
+        float4 *z = reinterpret_cast<float4 *>(S.t);
+        for (int k = tid; k < kTFloats/4; k += kThreads) z[k] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     __syncthreads();
+    MP3B_STAMP();
 
-    /* job list of the IMDCT phases: only subbands that are active in the granule itself or in the one before it
-     * (whose tail overlaps into this one) need work, everything else is exactly zero */
-    if (tid < n_slots)
+    /* ---- phase 1: each warp finishes the rows of its granules: clears what the IMDCT jobs can touch beyond
+     * the copied extent, waits for its copies and applies plain MS stereo in place: (L, R) <- (L + R, L - R) ---- */
     {
-        int jobs_before = 0;
-        for (int sl = 0; sl < tid; sl++) jobs_before += max(S.meta[sl].act, sl >= nch ? S.meta[sl - nch].act : 0);
-        const int nj = max(S.meta[tid].act, tid >= nch ? S.meta[tid - nch].act : 0);
-        S.njob[tid] = nj;
-        S.job_start[tid] = jobs_before;
-        if (tid == n_slots - 1) S.job_start[n_slots] = jobs_before + nj;
-    }
-
-    /* ---- phase 1: spectra -> shared (short blocks: [window][freq] -> [freq][window] on the fly; plain MS
-     * stereo as L+R / L-R of the two rows).  Lines at or beyond nzl were never written by the entropy kernel
-     * and are zero by definition. ---- */
-    for (int slot = warp; slot < n_slots; slot += kThreads/32)
-    {
-        const SlotMeta m = S.meta[slot];
-        float *dst = S.x + slot*kXSlot;
-        /* clear the slot with 128-bit stores, then write only the 32-line chunks that hold data */
-        {
-            float4 *z = reinterpret_cast<float4 *>(dst);
-#pragma unroll
-            for (int k = 0; k < 5; k++)
-                if (lane + 32*k < kXSlot/4) z[lane + 32*k] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        __syncwarp();
-        if (m.map < 0)
-        {
-            const float *src = a.xr + (size_t)(m.gc >= 0 ? m.gc : 0)*576 + lane;
-            const float *oth = a.xr + (size_t)((m.gc >= 0 ? m.gc : 0) ^ 1)*576 + lane;
-            const int n_own = (m.nzl + 31) >> 5, n_oth = m.ms ? (m.nzl_other + 31) >> 5 : 0;
-            const int n_live = max(n_own, n_oth);
-            for (int k0 = 0; k0 < n_live; k0 += 6)
+        const uint32_t bar = smem_addr(&S.mbar[warp]);
+        for (int u = warp; u < n_units; u += kThreads/32)
+            for (int ch = 0; ch < nch; ch++)
             {
-                float v[6];
-#pragma unroll
-                for (int k = 0; k < 6; k++) v[k] = k0 + k < n_own ? __ldg(src + 32*(k0 + k)) : 0.f;
-                if (m.ms)
+                const int slot = u*nch + ch;
+                const SlotMeta m = S.meta[slot];
+                const int from = m.gc >= 0 ? ((m.nzl + 3) >> 2) : 0;
+                const int to = (min(576, (m.act + 1)*18) + 3) >> 2;
+                float4 *z = reinterpret_cast<float4 *>(S.x + slot*kXSlot);
+                for (int k = from + lane; k < to; k += 32) z[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        __syncwarp();
+        MP3B_STAMP();
+        if (warp < n_units) mbar_wait(bar, 0);
+        MP3B_STAMP();
+        if (nch == 2)
+        {
+            for (int u = warp; u < n_units; u += kThreads/32)
+            {
+                const SlotMeta m0 = S.meta[u*2], m1 = S.meta[u*2 + 1];
+                if (m0.ms && m1.gc == (m0.gc ^ 1))
                 {
-#pragma unroll
-                    for (int k = 0; k < 6; k++)
+                    const int lim4 = (max(m0.nzl, m1.nzl) + 3) >> 2;
+                    float4 *l = reinterpret_cast<float4 *>(S.x + u*2*kXSlot), *r = l + kXSlot/4;
+                    for (int k = lane; k < lim4; k += 32)
                     {
-                        const float o = k0 + k < n_oth ? __ldg(oth + 32*(k0 + k)) : 0.f;
-                        v[k] = m.ms == 1 ? v[k] + o : o - v[k];
+                        const float4 vl = l[k], vr = r[k];
+                        l[k] = make_float4(vl.x + vr.x, vl.y + vr.y, vl.z + vr.z, vl.w + vr.w);
+                        r[k] = make_float4(vl.x - vr.x, vl.y - vr.y, vl.z - vr.z, vl.w - vr.w);
+                    }
+                } else
+                {
+                    /* the other channel of the granule is not part of the tile (halo across a channel-mode
+                     * change): fetch it from HBM */
+                    for (int ch = 0; ch < 2; ch++)
+                    {
+                        const SlotMeta m = ch ? m1 : m0;
+                        if (!m.ms) continue;
+                        float *x = S.x + (u*2 + ch)*kXSlot;
+                        const float *oth = a.xr + (size_t)(m.gc ^ 1)*576;
+                        const int lim = max(m.nzl, m.nzl_other);
+                        for (int e = lane; e < lim; e += 32)
+                        {
+                            const float o = e < m.nzl_other ? __ldg(oth + e) : 0.f;
+                            x[e] = m.ms == 1 ? x[e] + o : o - x[e];
+                        }
                     }
                 }
-#pragma unroll
-                for (int k = 0; k < 6; k++)
-                {
-                    const int e = lane + 32*(k0 + k);
-                    if (k0 + k < n_live) dst[e + ((e*3641) >> 16)] = v[k];     /* e + e/18: row pitch 19 */
-                }
-            }
-        } else
-        {
-            const float *src = a.xr + (size_t)m.gc*576;
-            const float *oth = a.xr + (size_t)(m.gc ^ 1)*576;
-            const uint16_t *map = reorder_map + m.map*576;
-#pragma unroll 6
-            for (int k = 0; k < 18; k++)
-            {
-                const int e = lane + 32*k;
-                float v = e < m.nzl ? __ldg(src + e) : 0.f;
-                if (m.ms)
-                {
-                    const float o = e < m.nzl_other ? __ldg(oth + e) : 0.f;
-                    v = m.ms == 1 ? v + o : o - v;
-                }
-                const int dl = (int)__ldg(map + e);
-                dst[dl + ((dl*3641) >> 16)] = v;
             }
         }
+        MP3B_STAMP();
     }
     __syncthreads();
+    MP3B_STAMP();
 
     /* ---- phases 2+3a: per active (slot, subband): antialias butterflies against both neighbours
      * (minimp3.h:1012-1045, recomputed on the fly instead of a separate in-place pass), then IMDCT tail and
@@ -341,8 +394,19 @@ k_l3_transform(TransformArgs a, const uint16_t *__restrict__ reorder_map, const 
             {
                 float x[18], tail[9];
                 const float *src = S.x + slot*kXSlot + sb*kXPitch;
+                const bool is_short = m.block_type == 2 && sb >= m.n_long;
+                if (is_short)
+                {
+                    /* [window][frequency] -> [frequency][window] (L3_reorder, minimp3.h:1000-1010) */
+                    const uint16_t *inv = reorder_inv + m.map*576 + sb*18;
+                    const float *row = S.x + slot*kXSlot;
 #pragma unroll
-                for (int k = 0; k < 18; k++) x[k] = src[k];
+                    for (int k = 0; k < 18; k++) x[k] = row[__ldg(inv + k)];
+                } else
+                {
+#pragma unroll
+                    for (int k = 0; k < 18; k++) x[k] = src[k];
+                }
                 const int aa_bands = m.block_type == 2 ? m.n_long - 1 : 31;
                 if (sb >= 1 && sb - 1 < aa_bands)
                 {
@@ -356,7 +420,7 @@ k_l3_transform(TransformArgs a, const uint16_t *__restrict__ reorder_map, const 
 #pragma unroll
                     for (int i = 0; i < 8; i++) x[17 - i] = src[kXPitch + i]*c_k.aa_ca[i] + x[17 - i]*c_k.aa_cs[i];
                 }
-                if (m.block_type == 2 && sb >= m.n_long) imdct_short_core(x, own[r], tail, c_k.twid3);
+                if (is_short) imdct_short_core(x, own[r], tail, c_k.twid3);
                 else imdct36_core(x, own[r], tail, c_k.twid9);
 #pragma unroll
                 for (int i = 0; i < 9; i++) t[i*32] = tail[i];
@@ -364,6 +428,7 @@ k_l3_transform(TransformArgs a, const uint16_t *__restrict__ reorder_map, const 
         }
     }
     __syncthreads();
+    MP3B_STAMP();
 
     /* the spectra are consumed: clear the time/subband matrix that takes their place (inactive subbands stay 0) */
     {
@@ -371,6 +436,7 @@ k_l3_transform(TransformArgs a, const uint16_t *__restrict__ reorder_map, const 
         for (int k = tid; k < (kYFloats + 3)/4; k += kThreads) z[k] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     __syncthreads();
+    MP3B_STAMP();
 
     /* ---- phase 3b: overlap with the previous granule's tail, frequency inversion, write Y[time][subband] ---- */
 #pragma unroll
@@ -411,6 +477,7 @@ k_l3_transform(TransformArgs a, const uint16_t *__restrict__ reorder_map, const 
         }
     }
     __syncthreads();
+    MP3B_STAMP();
 
     /* ---- phase 4: 32-point DCT-II over subbands for every time slot (minimp3.h:1274-1427) ---- */
     {
@@ -435,6 +502,7 @@ k_l3_transform(TransformArgs a, const uint16_t *__restrict__ reorder_map, const 
         }
     }
     __syncthreads();
+    MP3B_STAMP();
 
     /* ---- phase 5: window FIR + PCM conversion ---- */
     float *special = S.x + kYFloats;     /* slack behind Y: n_gr*2*18*nch floats */
@@ -443,10 +511,12 @@ k_l3_transform(TransformArgs a, const uint16_t *__restrict__ reorder_map, const 
     if (!FLOAT_OUT)
     {
         __syncthreads();
+    MP3B_STAMP();
         if (nch == 2) special_round_pass<2, 18>(special, a.pcm, tile.pcm_off, n_gr, tid);
         else special_round_pass<1, 18>(special, a.pcm, tile.pcm_off, n_gr, tid);
     }
 
+    MP3B_STAMP();
     /* ---- carried state out (single-frame API): tails of the last granule + last 15 transformed slots ---- */
     if (a.state_out)
     {
@@ -544,7 +614,13 @@ int tables_upload(DeviceTables *t)
     if (cudaMemcpyToSymbol(c_k, &k, sizeof(k)) != cudaSuccess) return -1;
     static uint16_t map[16*576];
     static float fir[32*16];
-    build_reorder_map(map);
+    {
+        /* the kernel gathers: it wants the source line of every destination line */
+        static uint16_t fwd[16*576];
+        build_reorder_map(fwd);
+        for (int r = 0; r < 16; r++)
+            for (int e = 0; e < 576; e++) map[r*576 + fwd[r*576 + e]] = (uint16_t)e;
+    }
     build_fir(fir);
     if (cudaMalloc(&t->reorder_map, sizeof(map)) != cudaSuccess) return -1;
     if (cudaMalloc(&t->fir_coef, sizeof(fir)) != cudaSuccess) return -1;
@@ -564,7 +640,8 @@ void tables_free(DeviceTables *t)
 cudaError_t launch_transform(const DeviceTables &t, const TransformArgs &a, cudaStream_t s)
 {
     if (!a.n_tiles) return cudaSuccess;
-    const size_t smem = sizeof(Smem);
+    size_t smem = sizeof(Smem);
+    if (const char *pad = getenv("MP3B_DEBUG_SMEM_PAD")) smem += (size_t)atoi(pad);   /* occupancy experiments */
     cudaError_t e;
     if (a.float_output)
     {

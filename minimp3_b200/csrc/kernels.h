@@ -13,7 +13,7 @@ namespace mp3b {
 /* Device-resident constant tables (uploaded once per device by tables_upload). */
 struct DeviceTables
 {
-    uint16_t *reorder_map;   /* [16][576]: (sr_idx*2 + mixed) -> destination line of source line e */
+    uint16_t *reorder_map;   /* [16][576]: (sr_idx*2 + mixed) -> source line of short-block destination line e */
     float *fir_coef;         /* [32][16]: per output phase j the 16 signed window taps */
 };
 
@@ -57,6 +57,8 @@ struct TransformArgs
     float *state_out;
     /* optional tap (tests): subband samples after IMDCT + sign, [n_gc][576] */
     float *tap_sub;
+    /* optional profiling aid: clock64() of thread 0 at every phase boundary, [n_tiles][16] */
+    long long *phase_clk;
 };
 
 struct Layer12Args
