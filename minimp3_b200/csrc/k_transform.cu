@@ -225,11 +225,14 @@ k_l3_transform(TransformArgs a, const uint16_t *__restrict__ reorder_inv, const 
 #define MP3B_STAMP() do { if (a.phase_clk && tid == 0 && clk_i < 16) a.phase_clk[(size_t)blockIdx.x*16 + clk_i++] = clock64(); } while (0)
     MP3B_STAMP();
 
-    /* ---- phase 0 (warp 0, lane = slot): slot table from the descriptors, one TMA bulk copy per row for its
-     * decoded extent (lines at or beyond nzl were never written by the entropy kernel and are zero by
-     * definition), IMDCT job list.  Rows keep the HBM line order; short blocks are de-interleaved when the
-     * IMDCT jobs read them.  Everybody else clears the tail region meanwhile. ---- */
+    /* ---- phase 0: warp 0 (lane = slot) fetches the descriptors, everybody clears the spectra and tail regions
+     * meanwhile (lines at or beyond nzl were never written by the entropy kernel and are zero by definition;
+     * only active subbands write tails); then warp 0 builds the slot table, issues one TMA bulk copy per row for
+     * its decoded extent and lays out the IMDCT job list.  Rows keep the HBM line order; short blocks are
+     * de-interleaved when the IMDCT jobs read them. ---- */
     const int n_units = n_slots/nch;           /* granules incl. halo; unit u belongs to warp u % 8 */
+    GcDesc d;
+    int gc = -1, nz = 0, nz_other = 0;
     if (warp == 0)
     {
         if (lane < kThreads/32)
@@ -238,17 +241,33 @@ k_l3_transform(TransformArgs a, const uint16_t *__restrict__ reorder_inv, const 
             mbar_init(smem_addr(&S.mbar[lane]), (uint32_t)max(1, owned*nch));
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
-        __syncwarp();
+        if (lane < n_slots)
+        {
+            const int i = lane/nch - 2, ch = lane%nch;
+            gc = i >= 0 ? (int)tile.gc_first + i*nch + ch : (stateful ? -1 : tile.halo[ch][-1 - i]);
+            if (gc >= 0)
+            {
+                d = a.gcs[gc];
+                nz = a.nzl[gc];
+                nz_other = a.nzl[gc ^ 1];     /* stereo pairs sit on indices (2k, 2k+1) */
+            }
+        }
+    }
+    {
+        float4 *z = reinterpret_cast<float4 *>(S.x);
+        for (int k = tid; k < (kXFloats + kTFloats)/4; k += kThreads) z[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    /* the bulk copies (async proxy) land on top of the cleared rows */
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (warp == 0)
+    {
+        asm volatile("bar.sync 1, %0;" :: "n"(kThreads) : "memory");
         SlotMeta m;
         m.gc = -1; m.nzl = 0; m.block_type = 0; m.n_long = 0; m.map = -1; m.ms = 0; m.nzl_other = 0; m.act = stateful ? 32 : 0;
         if (lane < n_slots)
         {
-            const int i = lane/nch - 2, ch = lane%nch;
-            const int gc = i >= 0 ? (int)tile.gc_first + i*nch + ch : (stateful ? -1 : tile.halo[ch][-1 - i]);
             if (gc >= 0)
             {
-                const GcDesc d = a.gcs[gc];
-                const int nz = a.nzl[gc], nz_other = a.nzl[gc ^ 1];     /* stereo pairs sit on indices (2k, 2k+1) */
                 m.gc = gc;
                 m.nzl = nz;
                 m.block_type = d.flags0 & GCF_BLOCK_TYPE_MASK;
@@ -283,10 +302,10 @@ k_l3_transform(TransformArgs a, const uint16_t *__restrict__ reorder_inv, const 
         const int nj = max(act, prev_act);
         int incl = nj;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1)
+        for (int dd = 1; dd < 32; dd <<= 1)
         {
-            const int v = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += v;
+            const int v = __shfl_up_sync(0xffffffffu, incl, dd);
+            if (lane >= dd) incl += v;
         }
         if (lane < n_slots)
         {
@@ -294,54 +313,68 @@ k_l3_transform(TransformArgs a, const uint16_t *__restrict__ reorder_inv, const 
             S.job_start[lane] = incl - nj;
             if (lane == n_slots - 1) S.job_start[n_slots] = incl;
         }
-    }
-    {
-        float4 *z = reinterpret_cast<float4 *>(S.t);
-        for (int k = tid; k < kTFloats/4; k += kThreads) z[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
+    } else
+        asm volatile("bar.arrive 1, %0;" :: "n"(kThreads) : "memory");
     __syncthreads();
     MP3B_STAMP();
 
-    /* ---- phase 1: each warp finishes the rows of its granules: clears what the IMDCT jobs can touch beyond
-     * the copied extent, waits for its copies and applies plain MS stereo in place: (L, R) <- (L + R, L - R) ---- */
+    /* ---- phase 1: each warp waits for the rows of its granules and applies plain MS stereo in place:
+     * (L, R) <- (L + R, L - R) ---- */
     {
-        const uint32_t bar = smem_addr(&S.mbar[warp]);
-        for (int u = warp; u < n_units; u += kThreads/32)
-            for (int ch = 0; ch < nch; ch++)
-            {
-                const int slot = u*nch + ch;
-                const SlotMeta m = S.meta[slot];
-                const int from = m.gc >= 0 ? ((m.nzl + 3) >> 2) : 0;
-                const int to = (min(576, (m.act + 1)*18) + 3) >> 2;
-                float4 *z = reinterpret_cast<float4 *>(S.x + slot*kXSlot);
-                for (int k = from + lane; k < to; k += 32) z[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-        __syncwarp();
-        MP3B_STAMP();
-        if (warp < n_units) mbar_wait(bar, 0);
+        if (warp < n_units) mbar_wait(smem_addr(&S.mbar[warp]), 0);
         MP3B_STAMP();
         if (nch == 2)
         {
-            for (int u = warp; u < n_units; u += kThreads/32)
+            /* at most two granules per warp: fetch both before storing anything */
+            constexpr int kU = (GT + 2 + kThreads/32 - 1)/(kThreads/32);
+            int lim4[kU];
+            bool far[kU];
+#pragma unroll
+            for (int j = 0; j < kU; j++)
             {
-                const SlotMeta m0 = S.meta[u*2], m1 = S.meta[u*2 + 1];
-                if (m0.ms && m1.gc == (m0.gc ^ 1))
+                const int u = warp + j*(kThreads/32);
+                lim4[j] = 0;
+                far[j] = false;
+                if (u < n_units)
                 {
-                    const int lim4 = (max(m0.nzl, m1.nzl) + 3) >> 2;
-                    float4 *l = reinterpret_cast<float4 *>(S.x + u*2*kXSlot), *r = l + kXSlot/4;
-                    for (int k = lane; k < lim4; k += 32)
+                    const SlotMeta m0 = S.meta[u*2], m1 = S.meta[u*2 + 1];
+                    if (m0.ms && m1.gc == (m0.gc ^ 1)) lim4[j] = (max(m0.nzl, m1.nzl) + 3) >> 2;
+                    else far[j] = m0.ms || m1.ms;
+                }
+            }
+            int lim_max = 0;
+#pragma unroll
+            for (int j = 0; j < kU; j++) lim_max = max(lim_max, lim4[j]);
+            for (int k = lane; k < lim_max; k += 32)
+            {
+                float4 vl[kU], vr[kU];
+#pragma unroll
+                for (int j = 0; j < kU; j++)
+                    if (k < lim4[j])
                     {
-                        const float4 vl = l[k], vr = r[k];
-                        l[k] = make_float4(vl.x + vr.x, vl.y + vr.y, vl.z + vr.z, vl.w + vr.w);
-                        r[k] = make_float4(vl.x - vr.x, vl.y - vr.y, vl.z - vr.z, vl.w - vr.w);
+                        const float4 *l = reinterpret_cast<const float4 *>(S.x + (warp + j*(kThreads/32))*2*kXSlot);
+                        vl[j] = l[k];
+                        vr[j] = l[k + kXSlot/4];
                     }
-                } else
+#pragma unroll
+                for (int j = 0; j < kU; j++)
+                    if (k < lim4[j])
+                    {
+                        float4 *l = reinterpret_cast<float4 *>(S.x + (warp + j*(kThreads/32))*2*kXSlot);
+                        l[k] = make_float4(vl[j].x + vr[j].x, vl[j].y + vr[j].y, vl[j].z + vr[j].z, vl[j].w + vr[j].w);
+                        l[k + kXSlot/4] = make_float4(vl[j].x - vr[j].x, vl[j].y - vr[j].y, vl[j].z - vr[j].z, vl[j].w - vr[j].w);
+                    }
+            }
+#pragma unroll
+            for (int j = 0; j < kU; j++)
+                if (far[j])
                 {
                     /* the other channel of the granule is not part of the tile (halo across a channel-mode
                      * change): fetch it from HBM */
+                    const int u = warp + j*(kThreads/32);
                     for (int ch = 0; ch < 2; ch++)
                     {
-                        const SlotMeta m = ch ? m1 : m0;
+                        const SlotMeta m = S.meta[u*2 + ch];
                         if (!m.ms) continue;
                         float *x = S.x + (u*2 + ch)*kXSlot;
                         const float *oth = a.xr + (size_t)(m.gc ^ 1)*576;
@@ -353,7 +386,6 @@ k_l3_transform(TransformArgs a, const uint16_t *__restrict__ reorder_inv, const 
                         }
                     }
                 }
-            }
         }
         MP3B_STAMP();
     }
