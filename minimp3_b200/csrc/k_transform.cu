@@ -68,8 +68,6 @@ struct Smem
     alignas(128) float x[kXFloats];      /* spectra, later time/subband matrix Y */
     float t[kTFloats];      /* tails [slot][i][sb] */
     SlotMeta meta[kSlots];
-    int job_start[kSlots + 1];   /* compacted (slot, subband) job list: prefix sums of the per-slot job counts */
-    int njob[kSlots];
     unsigned long long mbar[kThreads/32];   /* one transaction barrier per warp: its rows' bulk copies */
 };
 
@@ -225,170 +223,142 @@ k_l3_transform(TransformArgs a, const uint16_t *__restrict__ reorder_inv, const 
 #define MP3B_STAMP() do { if (a.phase_clk && tid == 0 && clk_i < 16) a.phase_clk[(size_t)blockIdx.x*16 + clk_i++] = clock64(); } while (0)
     MP3B_STAMP();
 
-    /* ---- phase 0: warp 0 (lane = slot) fetches the descriptors, everybody clears the spectra and tail regions
-     * meanwhile (lines at or beyond nzl were never written by the entropy kernel and are zero by definition;
-     * only active subbands write tails); then warp 0 builds the slot table, issues one TMA bulk copy per row for
-     * its decoded extent and lays out the IMDCT job list.  Rows keep the HBM line order; short blocks are
-     * de-interleaved when the IMDCT jobs read them. ---- */
-    const int n_units = n_slots/nch;           /* granules incl. halo; unit u belongs to warp u % 8 */
+    /* ---- phases 0+1, every warp on its own for the granules it owns (unit u = granule incl. halo belongs to
+     * warp u % 8; lane = (unit, channel)): fetch the descriptors, clear the rows and tails of the unit meanwhile
+     * (lines at or beyond nzl were never written by the entropy kernel and are zero by definition; only active
+     * subbands write tails), one TMA bulk copy per row for its decoded extent on the warp's transaction barrier,
+     * wait, plain MS stereo in place.  Rows keep the HBM line order; short blocks are de-interleaved when the
+     * IMDCT jobs read them.  No block-wide barrier until the rows are complete. ---- */
+    constexpr int kW = kThreads/32;
+    constexpr int kU = (GT + 2 + kW - 1)/kW;   /* granules per warp */
+    const int n_units = n_slots/nch;
+    if (tid == 0 && blockIdx.x + 1024 < a.n_tiles)
+        asm volatile("prefetch.global.L2 [%0];" :: "l"(a.tiles + blockIdx.x + 1024));   /* a later wave's descriptor */
+    const int uj = nch == 2 ? lane >> 1 : lane, uch = nch == 2 ? lane & 1 : 0;
+    const int my_unit = warp + kW*uj;
+    const int my_slot = my_unit*nch + uch;
+    const bool has = uj < kU && my_unit < n_units;
     GcDesc d;
     int gc = -1, nz = 0, nz_other = 0;
-    if (warp == 0)
+    if (has)
     {
-        if (lane < kThreads/32)
+        const int i = my_unit - 2;
+        gc = i >= 0 ? (int)tile.gc_first + i*nch + uch : (stateful ? -1 : tile.halo[uch][-1 - i]);
+        if (gc >= 0)
         {
-            const int owned = lane < n_units ? (n_units - lane + kThreads/32 - 1)/(kThreads/32) : 0;
-            mbar_init(smem_addr(&S.mbar[lane]), (uint32_t)max(1, owned*nch));
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        }
-        if (lane < n_slots)
-        {
-            const int i = lane/nch - 2, ch = lane%nch;
-            gc = i >= 0 ? (int)tile.gc_first + i*nch + ch : (stateful ? -1 : tile.halo[ch][-1 - i]);
-            if (gc >= 0)
-            {
-                d = a.gcs[gc];
-                nz = a.nzl[gc];
-                nz_other = a.nzl[gc ^ 1];     /* stereo pairs sit on indices (2k, 2k+1) */
-            }
+            d = a.gcs[gc];
+            nz = a.nzl[gc];
+            nz_other = a.nzl[gc ^ 1];     /* stereo pairs sit on indices (2k, 2k+1) */
         }
     }
+    const uint32_t bar = smem_addr(&S.mbar[warp]);
+    const unsigned has_mask = __ballot_sync(0xffffffffu, has);
+    if (lane == 0 && has_mask)
     {
-        float4 *z = reinterpret_cast<float4 *>(S.x);
-        for (int k = tid; k < (kXFloats + kTFloats)/4; k += kThreads) z[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        mbar_init(bar, (uint32_t)__popc(has_mask));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+#pragma unroll
+    for (int j = 0; j < kU; j++)
+    {
+        const int u = warp + kW*j;
+        if (u < n_units)
+        {
+            float4 *zx = reinterpret_cast<float4 *>(S.x + u*nch*kXSlot);
+            for (int k = lane; k < nch*(kXSlot/4); k += 32) zx[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 *zt = reinterpret_cast<float4 *>(S.t + u*nch*288);
+            for (int k = lane; k < nch*72; k += 32) zt[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
     }
     /* the bulk copies (async proxy) land on top of the cleared rows */
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    if (warp == 0)
+    __syncwarp();
+    SlotMeta m;
+    m.gc = -1; m.nzl = 0; m.block_type = 0; m.n_long = 0; m.map = -1; m.ms = 0; m.nzl_other = 0; m.act = stateful ? 32 : 0;
+    if (has)
     {
-        asm volatile("bar.sync 1, %0;" :: "n"(kThreads) : "memory");
-        SlotMeta m;
-        m.gc = -1; m.nzl = 0; m.block_type = 0; m.n_long = 0; m.map = -1; m.ms = 0; m.nzl_other = 0; m.act = stateful ? 32 : 0;
-        if (lane < n_slots)
+        if (gc >= 0)
         {
-            if (gc >= 0)
+            m.gc = gc;
+            m.nzl = nz;
+            m.block_type = d.flags0 & GCF_BLOCK_TYPE_MASK;
+            const bool mixed = d.flags0 & GCF_MIXED;
+            m.n_long = mixed ? (d.sr_idx == 1 ? 4 : 2) : 0;   /* 8 kHz MPEG-2.5 keeps 4 long subbands */
+            if (m.block_type == 2) m.map = d.sr_idx*2 + (mixed ? 1 : 0);
+            if (d.flags1 & GCF1_MS_PLAIN)
             {
-                m.gc = gc;
-                m.nzl = nz;
-                m.block_type = d.flags0 & GCF_BLOCK_TYPE_MASK;
-                const bool mixed = d.flags0 & GCF_MIXED;
-                m.n_long = mixed ? (d.sr_idx == 1 ? 4 : 2) : 0;   /* 8 kHz MPEG-2.5 keeps 4 long subbands */
-                if (m.block_type == 2) m.map = d.sr_idx*2 + (mixed ? 1 : 0);
-                if (d.flags1 & GCF1_MS_PLAIN)
-                {
-                    /* L3_midside_stereo (minimp3.h:879-909) */
-                    m.ms = (d.flags1 & GCF1_CH) ? 2 : 1;
-                    m.nzl_other = nz_other;
-                }
-                /* lines at or above the decoded extent are zero; antialias leaks 8 lines into the next subband */
-                const int ext = m.ms ? max(m.nzl, m.nzl_other) : m.nzl;
-                m.act = (stateful || m.block_type == 2) ? 32 : (ext ? min(32, (ext + 17)/18 + 1) : 0);
+                /* L3_midside_stereo (minimp3.h:879-909) */
+                m.ms = (d.flags1 & GCF1_CH) ? 2 : 1;
+                m.nzl_other = nz_other;
             }
-            const uint32_t bar = smem_addr(&S.mbar[(lane/nch) & (kThreads/32 - 1)]);
-            const uint32_t bytes = (uint32_t)((m.nzl + 3) & ~3)*4u;
-            if (m.gc >= 0 && bytes)
-            {
-                mbar_arrive_expect_tx(bar, bytes);
-                bulk_g2s(smem_addr(S.x + lane*kXSlot), a.xr + (size_t)m.gc*576, bytes, bar);
-            } else
-                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
+            /* lines at or above the decoded extent are zero; antialias leaks 8 lines into the next subband */
+            const int ext = m.ms ? max(m.nzl, m.nzl_other) : m.nzl;
+            m.act = (stateful || m.block_type == 2) ? 32 : (ext ? min(32, (ext + 17)/18 + 1) : 0);
         }
-        if (lane < kSlots) S.meta[lane] = m;
-        /* job list of the IMDCT phases: only subbands that are active in the granule itself or in the one before
-         * it (whose tail overlaps into this one) need work, everything else is exactly zero */
-        const int act = lane < n_slots ? m.act : 0;
-        int prev_act = __shfl_up_sync(0xffffffffu, act, nch);
-        if (lane < nch) prev_act = 0;
-        const int nj = max(act, prev_act);
-        int incl = nj;
-#pragma unroll
-        for (int dd = 1; dd < 32; dd <<= 1)
+        S.meta[my_slot] = m;
+        const uint32_t bytes = (uint32_t)((m.nzl + 3) & ~3)*4u;
+        if (m.gc >= 0 && bytes)
         {
-            const int v = __shfl_up_sync(0xffffffffu, incl, dd);
-            if (lane >= dd) incl += v;
-        }
-        if (lane < n_slots)
-        {
-            S.njob[lane] = nj;
-            S.job_start[lane] = incl - nj;
-            if (lane == n_slots - 1) S.job_start[n_slots] = incl;
-        }
-    } else
-        asm volatile("bar.arrive 1, %0;" :: "n"(kThreads) : "memory");
-    __syncthreads();
-    MP3B_STAMP();
-
-    /* ---- phase 1: each warp waits for the rows of its granules and applies plain MS stereo in place:
-     * (L, R) <- (L + R, L - R) ---- */
-    {
-        if (warp < n_units) mbar_wait(smem_addr(&S.mbar[warp]), 0);
-        MP3B_STAMP();
-        if (nch == 2)
-        {
-            /* at most two granules per warp: fetch both before storing anything */
-            constexpr int kU = (GT + 2 + kThreads/32 - 1)/(kThreads/32);
-            int lim4[kU];
-            bool far[kU];
-#pragma unroll
-            for (int j = 0; j < kU; j++)
-            {
-                const int u = warp + j*(kThreads/32);
-                lim4[j] = 0;
-                far[j] = false;
-                if (u < n_units)
-                {
-                    const SlotMeta m0 = S.meta[u*2], m1 = S.meta[u*2 + 1];
-                    if (m0.ms && m1.gc == (m0.gc ^ 1)) lim4[j] = (max(m0.nzl, m1.nzl) + 3) >> 2;
-                    else far[j] = m0.ms || m1.ms;
-                }
-            }
-            int lim_max = 0;
-#pragma unroll
-            for (int j = 0; j < kU; j++) lim_max = max(lim_max, lim4[j]);
-            for (int k = lane; k < lim_max; k += 32)
-            {
-                float4 vl[kU], vr[kU];
-#pragma unroll
-                for (int j = 0; j < kU; j++)
-                    if (k < lim4[j])
-                    {
-                        const float4 *l = reinterpret_cast<const float4 *>(S.x + (warp + j*(kThreads/32))*2*kXSlot);
-                        vl[j] = l[k];
-                        vr[j] = l[k + kXSlot/4];
-                    }
-#pragma unroll
-                for (int j = 0; j < kU; j++)
-                    if (k < lim4[j])
-                    {
-                        float4 *l = reinterpret_cast<float4 *>(S.x + (warp + j*(kThreads/32))*2*kXSlot);
-                        l[k] = make_float4(vl[j].x + vr[j].x, vl[j].y + vr[j].y, vl[j].z + vr[j].z, vl[j].w + vr[j].w);
-                        l[k + kXSlot/4] = make_float4(vl[j].x - vr[j].x, vl[j].y - vr[j].y, vl[j].z - vr[j].z, vl[j].w - vr[j].w);
-                    }
-            }
-#pragma unroll
-            for (int j = 0; j < kU; j++)
-                if (far[j])
-                {
-                    /* the other channel of the granule is not part of the tile (halo across a channel-mode
-                     * change): fetch it from HBM */
-                    const int u = warp + j*(kThreads/32);
-                    for (int ch = 0; ch < 2; ch++)
-                    {
-                        const SlotMeta m = S.meta[u*2 + ch];
-                        if (!m.ms) continue;
-                        float *x = S.x + (u*2 + ch)*kXSlot;
-                        const float *oth = a.xr + (size_t)(m.gc ^ 1)*576;
-                        const int lim = max(m.nzl, m.nzl_other);
-                        for (int e = lane; e < lim; e += 32)
-                        {
-                            const float o = e < m.nzl_other ? __ldg(oth + e) : 0.f;
-                            x[e] = m.ms == 1 ? x[e] + o : o - x[e];
-                        }
-                    }
-                }
-        }
-        MP3B_STAMP();
+            mbar_arrive_expect_tx(bar, bytes);
+            bulk_g2s(smem_addr(S.x + my_slot*kXSlot), a.xr + (size_t)m.gc*576, bytes, bar);
+        } else
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
     }
+    MP3B_STAMP();
+    if (has_mask) mbar_wait(bar, 0);
+    MP3B_STAMP();
+    if (nch == 2)
+    {
+        const int p_gc = __shfl_xor_sync(0xffffffffu, m.gc, 1), p_nzl = __shfl_xor_sync(0xffffffffu, m.nzl, 1);
+        const bool pair_ok = has && m.ms && m.gc >= 0 && p_gc == (m.gc ^ 1);
+        const int my_lim4 = pair_ok ? (max(m.nzl, p_nzl) + 3) >> 2 : 0;
+        int lim4[kU], lim_max = 0;
+#pragma unroll
+        for (int j = 0; j < kU; j++)
+        {
+            lim4[j] = __shfl_sync(0xffffffffu, my_lim4, j*2);
+            lim_max = max(lim_max, lim4[j]);
+        }
+        /* both granules of the warp in flight before anything is stored */
+        for (int k = lane; k < lim_max; k += 32)
+        {
+            float4 vl[kU], vr[kU];
+#pragma unroll
+            for (int j = 0; j < kU; j++)
+                if (k < lim4[j])
+                {
+                    const float4 *l = reinterpret_cast<const float4 *>(S.x + (warp + j*kW)*2*kXSlot);
+                    vl[j] = l[k];
+                    vr[j] = l[k + kXSlot/4];
+                }
+#pragma unroll
+            for (int j = 0; j < kU; j++)
+                if (k < lim4[j])
+                {
+                    float4 *l = reinterpret_cast<float4 *>(S.x + (warp + j*kW)*2*kXSlot);
+                    l[k] = make_float4(vl[j].x + vr[j].x, vl[j].y + vr[j].y, vl[j].z + vr[j].z, vl[j].w + vr[j].w);
+                    l[k + kXSlot/4] = make_float4(vl[j].x - vr[j].x, vl[j].y - vr[j].y, vl[j].z - vr[j].z, vl[j].w - vr[j].w);
+                }
+        }
+        unsigned far_mask = __ballot_sync(0xffffffffu, has && m.ms && !pair_ok);
+        while (far_mask)
+        {
+            /* the other channel of the granule is not part of the tile (halo across a channel-mode change):
+             * fetch it from HBM */
+            const int src_lane = __ffs(far_mask) - 1;
+            far_mask &= far_mask - 1;
+            const int f_gc = __shfl_sync(0xffffffffu, m.gc, src_lane), f_ms = __shfl_sync(0xffffffffu, m.ms, src_lane);
+            const int f_nzl = __shfl_sync(0xffffffffu, m.nzl, src_lane), f_other = __shfl_sync(0xffffffffu, m.nzl_other, src_lane);
+            float *x = S.x + __shfl_sync(0xffffffffu, my_slot, src_lane)*kXSlot;
+            const float *oth = a.xr + (size_t)(f_gc ^ 1)*576;
+            for (int e = lane; e < max(f_nzl, f_other); e += 32)
+            {
+                const float o = e < f_other ? __ldg(oth + e) : 0.f;
+                x[e] = f_ms == 1 ? x[e] + o : o - x[e];
+            }
+        }
+    }
+    MP3B_STAMP();
     __syncthreads();
     MP3B_STAMP();
 
@@ -397,18 +367,54 @@ k_l3_transform(TransformArgs a, const uint16_t *__restrict__ reorder_inv, const 
      * own half ---- */
     constexpr int kJobs3 = (kSlots*32 + kThreads - 1)/kThreads;   /* 3 */
     float own[kJobs3][9];
-    const int n_jobs3 = S.job_start[n_slots];
+    /* job list: only subbands that are active in the granule itself or in the one before it (whose tail overlaps
+     * into this one) need work, everything else is exactly zero.  Every warp scans the per-slot job counts in
+     * registers (lane = slot) and looks its jobs up with shuffles. */
+    int job_incl, job_excl;
+    {
+        const int act = lane < n_slots ? S.meta[lane].act : 0;
+        int prev_act = __shfl_up_sync(0xffffffffu, act, nch);
+        if (lane < nch) prev_act = 0;
+        const int nj = lane < n_slots ? max(act, prev_act) : 0;
+        job_incl = nj;
+#pragma unroll
+        for (int dd = 1; dd < 32; dd <<= 1)
+        {
+            const int v = __shfl_up_sync(0xffffffffu, job_incl, dd);
+            if (lane >= dd) job_incl += v;
+        }
+        job_excl = job_incl - nj;
+    }
+    const int n_jobs3 = __shfl_sync(0xffffffffu, job_incl, 31);
     int job_slot[kJobs3], job_sb[kJobs3];
+    {
+        int lo[kJobs3];
+#pragma unroll
+        for (int r = 0; r < kJobs3; r++) lo[r] = 0;
+#pragma unroll
+        for (int step = 16; step >= 1; step >>= 1)
+        {
+            /* first slot whose inclusive count exceeds the job index */
+#pragma unroll
+            for (int r = 0; r < kJobs3; r++)
+            {
+                const int v = __shfl_sync(0xffffffffu, job_incl, lo[r] + step - 1);
+                if (v <= tid + r*kThreads) lo[r] += step;
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < kJobs3; r++)
+        {
+            const int e = __shfl_sync(0xffffffffu, job_excl, lo[r] & 31);
+            job_sb[r] = tid + r*kThreads - e;
+            job_slot[r] = tid + r*kThreads < n_jobs3 ? lo[r] : -1;
+        }
+    }
 #pragma unroll
     for (int r = 0; r < kJobs3; r++)
     {
         const int job = tid + r*kThreads;
-        int slot = 0;
-        if (job < n_jobs3)
-            while (job >= S.job_start[slot + 1]) slot++;
-        const int sb = job - S.job_start[slot];
-        job_slot[r] = job < n_jobs3 ? slot : -1;
-        job_sb[r] = sb;
+        const int slot = max(job_slot[r], 0), sb = job_sb[r];
 #pragma unroll
         for (int k = 0; k < 9; k++) own[r][k] = 0.f;
         if (job < n_jobs3)
