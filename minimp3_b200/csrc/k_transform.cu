@@ -44,6 +44,7 @@ constexpr int kYPitch = 33;
 constexpr int kXFloats = kSlots*kXSlot;     /* 11520 */
 constexpr int kYFloats = 2*kRows*kYPitch;   /* 10494, aliases XS */
 constexpr int kTFloats = kSlots*288;
+static_assert(sizeof(TileRec) == 256 && MP3B_TILE_SLOTS == kSlots, "tile record layout");
 static_assert(kYFloats <= kXFloats, "Y must fit in the X region");
 static_assert(GT*32 <= kThreads, "one FIR job per thread");
 static_assert(kXFloats - kYFloats >= GT*2*18*2, "slack behind Y holds the specially rounded outputs");
@@ -59,7 +60,6 @@ struct SlotMeta
                         set -- for ANY block type, as in minimp3.h:1260 (0, 2, 4) */
     int map;         /* reorder map row or -1 */
     int ms;          /* plain MS stereo applied on load: 0 none, 1 this row = L + R, 2 this row = L - R */
-    int nzl_other;   /* extent of the partner channel's row (ms != 0) */
     int act;         /* subbands that can hold non-zero lines after antialias (0..32) */
 };
 
@@ -208,6 +208,71 @@ __device__ __forceinline__ void special_round_pass(const float *special, void *p
     }
 }
 
+/* ---- tile records: one warp per tile (lane = slot) turns the tile descriptor, the granule descriptors and the
+ * extents left by the entropy / intensity-stereo kernels into the TileRec the transform CTA starts from ---- */
+__global__ void __launch_bounds__(256)
+k_l3_tile_meta(TransformArgs a)
+{
+    const int lane = threadIdx.x & 31;
+    const uint32_t t = blockIdx.x*(blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (t >= a.n_tiles) return;
+    const TileDesc tile = a.tiles[t];
+    const bool stateful = a.state_in != nullptr;
+    const int nch = tile.nch, n_slots = (tile.n_gr + 2)*nch;
+    int gc = -1, nzl = 0, act = stateful ? 32 : 0, bt = 0, ms = 0, n_long = 0, map = -1;
+    if (lane < n_slots)
+    {
+        const int i = lane/nch - 2, ch = lane%nch;
+        gc = i >= 0 ? (int)tile.gc_first + i*nch + ch : (stateful ? -1 : tile.halo[ch][-1 - i]);
+        if (gc >= 0)
+        {
+            const GcDesc d = a.gcs[gc];
+            nzl = a.nzl[gc];
+            bt = d.flags0 & GCF_BLOCK_TYPE_MASK;
+            const bool mixed = d.flags0 & GCF_MIXED;
+            n_long = mixed ? (d.sr_idx == 1 ? 4 : 2) : 0;   /* 8 kHz MPEG-2.5 keeps 4 long subbands (minimp3.h:1260) */
+            if (bt == 2) map = d.sr_idx*2 + (mixed ? 1 : 0);
+            int ext = nzl;
+            if (d.flags1 & GCF1_MS_PLAIN)
+            {
+                /* L3_midside_stereo (minimp3.h:879-909): stereo pairs sit on descriptor indices (2k, 2k+1) */
+                ms = (d.flags1 & GCF1_CH) ? 2 : 1;
+                ext = max(ext, (int)a.nzl[gc ^ 1]);
+            }
+            /* lines at or above the decoded extent are zero; antialias leaks 8 lines into the next subband */
+            act = (stateful || bt == 2) ? 32 : (ext ? min(32, (ext + 17)/18 + 1) : 0);
+        }
+    }
+    /* IMDCT job list: only subbands that are active in the granule itself or in the one before it (whose tail
+     * overlaps into this one) need work, everything else is exactly zero */
+    const int act_l = lane < n_slots ? act : 0;
+    int prev_act = __shfl_up_sync(0xffffffffu, act_l, nch);
+    if (lane < nch) prev_act = 0;
+    int incl = lane < n_slots ? max(act_l, prev_act) : 0;
+#pragma unroll
+    for (int dd = 1; dd < 32; dd <<= 1)
+    {
+        const int v = __shfl_up_sync(0xffffffffu, incl, dd);
+        if (lane >= dd) incl += v;
+    }
+    TileRec *rec = a.tile_recs + t;
+    if (lane < MP3B_TILE_SLOTS)
+    {
+        TileSlot ts;
+        ts.gc = gc;
+        ts.info = (uint32_t)nzl | (uint32_t)act << TSI_ACT_SHIFT | (uint32_t)bt << TSI_BT_SHIFT | (uint32_t)ms << TSI_MS_SHIFT |
+                  (uint32_t)n_long << TSI_NLONG_SHIFT | (uint32_t)(map + 1) << TSI_MAP_SHIFT;
+        rec->slot[lane] = ts;
+        rec->job_incl[lane] = (uint16_t)incl;
+    }
+    if (lane == 0)
+    {
+        rec->n_gr = tile.n_gr;
+        rec->nch = tile.nch;
+        rec->pcm_off = tile.pcm_off;
+    }
+}
+
 template <bool FLOAT_OUT>
 __global__ void __launch_bounds__(kThreads, 3)
 k_l3_transform(TransformArgs a, const uint16_t *__restrict__ reorder_inv, const float *__restrict__ fir_coef)
@@ -215,7 +280,15 @@ k_l3_transform(TransformArgs a, const uint16_t *__restrict__ reorder_inv, const 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Smem &S = *reinterpret_cast<Smem *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const TileDesc tile = a.tiles[blockIdx.x];
+    const TileRec *rec = a.tile_recs + blockIdx.x;
+    struct { uint8_t n_gr, nch, pad[6]; uint64_t pcm_off; } tile;
+    {
+        const uint4 h = __ldg(reinterpret_cast<const uint4 *>(&rec->n_gr));
+        tile.n_gr = (uint8_t)(h.x & 0xff);
+        tile.nch = (uint8_t)((h.x >> 8) & 0xff);
+        tile.pcm_off = (uint64_t)h.z | (uint64_t)h.w << 32;
+    }
+    int job_incl = (int)__ldg(&rec->job_incl[min(lane, MP3B_TILE_SLOTS - 1)]);   /* lanes past the table hold the total */
     const int nch = tile.nch, n_gr = tile.n_gr;
     const int n_slots = (n_gr + 2)*nch;
     const bool stateful = a.state_in != nullptr;
@@ -224,33 +297,38 @@ k_l3_transform(TransformArgs a, const uint16_t *__restrict__ reorder_inv, const 
     MP3B_STAMP();
 
     /* ---- phases 0+1, every warp on its own for the granules it owns (unit u = granule incl. halo belongs to
-     * warp u % 8; lane = (unit, channel)): fetch the descriptors, clear the rows and tails of the unit meanwhile
-     * (lines at or beyond nzl were never written by the entropy kernel and are zero by definition; only active
-     * subbands write tails), one TMA bulk copy per row for its decoded extent on the warp's transaction barrier,
-     * wait, plain MS stereo in place.  Rows keep the HBM line order; short blocks are de-interleaved when the
-     * IMDCT jobs read them.  No block-wide barrier until the rows are complete. ---- */
+     * warp u % 8; lane = (unit, channel)): fetch the slot records (one round trip: k_l3_tile_meta did the
+     * dependent work), clear the rows and tails of the unit meanwhile (lines at or beyond nzl were never written
+     * by the entropy kernel and are zero by definition; only active subbands write tails), one TMA bulk copy per
+     * row for its decoded extent on the warp's transaction barrier, wait, plain MS stereo in place.  Rows keep
+     * the HBM line order; short blocks are de-interleaved when the IMDCT jobs read them.  No block-wide barrier
+     * until the rows are complete. ---- */
     constexpr int kW = kThreads/32;
     constexpr int kU = (GT + 2 + kW - 1)/kW;   /* granules per warp */
-    const int n_units = n_slots/nch;
     if (tid == 0 && blockIdx.x + 1024 < a.n_tiles)
-        asm volatile("prefetch.global.L2 [%0];" :: "l"(a.tiles + blockIdx.x + 1024));   /* a later wave's descriptor */
-    const int uj = nch == 2 ? lane >> 1 : lane, uch = nch == 2 ? lane & 1 : 0;
-    const int my_unit = warp + kW*uj;
-    const int my_slot = my_unit*nch + uch;
-    const bool has = uj < kU && my_unit < n_units;
-    GcDesc d;
-    int gc = -1, nz = 0, nz_other = 0;
-    if (has)
+        asm volatile("prefetch.global.L2 [%0];" :: "l"(a.tile_recs + blockIdx.x + 1024));   /* a later wave's record */
+    if (tid == 32 && blockIdx.x + 1024 < a.n_tiles)
+        asm volatile("prefetch.global.L2 [%0];" :: "l"(reinterpret_cast<const char *>(a.tile_recs + blockIdx.x + 1024) + 128));
+    /* the slot records do not depend on the header: ask for all kU*2 a warp can own, keep those that exist */
+    const int uj = lane >> 1, uch = lane & 1;          /* as if stereo; remapped below for mono */
+    TileSlot ts_st, ts_mono;
+    ts_st.gc = -1; ts_st.info = 0; ts_mono = ts_st;
+    if (lane < kU*2 && (warp + kW*uj)*2 + uch < MP3B_TILE_SLOTS)
     {
-        const int i = my_unit - 2;
-        gc = i >= 0 ? (int)tile.gc_first + i*nch + uch : (stateful ? -1 : tile.halo[uch][-1 - i]);
-        if (gc >= 0)
-        {
-            d = a.gcs[gc];
-            nz = a.nzl[gc];
-            nz_other = a.nzl[gc ^ 1];     /* stereo pairs sit on indices (2k, 2k+1) */
-        }
+        const uint2 v = __ldg(reinterpret_cast<const uint2 *>(&rec->slot[(warp + kW*uj)*2 + uch]));
+        ts_st.gc = (int)v.x; ts_st.info = v.y;
     }
+    if (lane < kU)
+    {
+        const uint2 v = __ldg(reinterpret_cast<const uint2 *>(&rec->slot[warp + kW*lane]));
+        ts_mono.gc = (int)v.x; ts_mono.info = v.y;
+    }
+    const int n_units = n_slots/nch;
+    const int my_unit = nch == 2 ? warp + kW*uj : warp + kW*lane;
+    const int my_ch = nch == 2 ? uch : 0;
+    const int my_slot = my_unit*nch + my_ch;
+    const bool has = (nch == 2 ? lane < kU*2 : lane < kU) && my_unit < n_units;
+    const TileSlot ts = nch == 2 ? ts_st : ts_mono;
     const uint32_t bar = smem_addr(&S.mbar[warp]);
     const unsigned has_mask = __ballot_sync(0xffffffffu, has);
     if (lane == 0 && has_mask)
@@ -274,27 +352,16 @@ k_l3_transform(TransformArgs a, const uint16_t *__restrict__ reorder_inv, const 
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncwarp();
     SlotMeta m;
-    m.gc = -1; m.nzl = 0; m.block_type = 0; m.n_long = 0; m.map = -1; m.ms = 0; m.nzl_other = 0; m.act = stateful ? 32 : 0;
+    m.gc = -1; m.nzl = 0; m.block_type = 0; m.n_long = 0; m.map = -1; m.ms = 0; m.act = 0;
     if (has)
     {
-        if (gc >= 0)
-        {
-            m.gc = gc;
-            m.nzl = nz;
-            m.block_type = d.flags0 & GCF_BLOCK_TYPE_MASK;
-            const bool mixed = d.flags0 & GCF_MIXED;
-            m.n_long = mixed ? (d.sr_idx == 1 ? 4 : 2) : 0;   /* 8 kHz MPEG-2.5 keeps 4 long subbands */
-            if (m.block_type == 2) m.map = d.sr_idx*2 + (mixed ? 1 : 0);
-            if (d.flags1 & GCF1_MS_PLAIN)
-            {
-                /* L3_midside_stereo (minimp3.h:879-909) */
-                m.ms = (d.flags1 & GCF1_CH) ? 2 : 1;
-                m.nzl_other = nz_other;
-            }
-            /* lines at or above the decoded extent are zero; antialias leaks 8 lines into the next subband */
-            const int ext = m.ms ? max(m.nzl, m.nzl_other) : m.nzl;
-            m.act = (stateful || m.block_type == 2) ? 32 : (ext ? min(32, (ext + 17)/18 + 1) : 0);
-        }
+        m.gc = ts.gc;
+        m.nzl = (int)(ts.info & TSI_NZL_MASK);
+        m.act = (int)(ts.info >> TSI_ACT_SHIFT) & 63;
+        m.block_type = (int)(ts.info >> TSI_BT_SHIFT) & 3;
+        m.ms = (int)(ts.info >> TSI_MS_SHIFT) & 3;
+        m.n_long = (int)(ts.info >> TSI_NLONG_SHIFT) & 7;
+        m.map = ((int)(ts.info >> TSI_MAP_SHIFT) & 31) - 1;
         S.meta[my_slot] = m;
         const uint32_t bytes = (uint32_t)((m.nzl + 3) & ~3)*4u;
         if (m.gc >= 0 && bytes)
@@ -348,7 +415,7 @@ k_l3_transform(TransformArgs a, const uint16_t *__restrict__ reorder_inv, const 
             const int src_lane = __ffs(far_mask) - 1;
             far_mask &= far_mask - 1;
             const int f_gc = __shfl_sync(0xffffffffu, m.gc, src_lane), f_ms = __shfl_sync(0xffffffffu, m.ms, src_lane);
-            const int f_nzl = __shfl_sync(0xffffffffu, m.nzl, src_lane), f_other = __shfl_sync(0xffffffffu, m.nzl_other, src_lane);
+            const int f_nzl = __shfl_sync(0xffffffffu, m.nzl, src_lane), f_other = (int)__ldg(a.nzl + (f_gc ^ 1));
             float *x = S.x + __shfl_sync(0xffffffffu, my_slot, src_lane)*kXSlot;
             const float *oth = a.xr + (size_t)(f_gc ^ 1)*576;
             for (int e = lane; e < max(f_nzl, f_other); e += 32)
@@ -368,24 +435,14 @@ k_l3_transform(TransformArgs a, const uint16_t *__restrict__ reorder_inv, const 
     constexpr int kJobs3 = (kSlots*32 + kThreads - 1)/kThreads;   /* 3 */
     float own[kJobs3][9];
     /* job list: only subbands that are active in the granule itself or in the one before it (whose tail overlaps
-     * into this one) need work, everything else is exactly zero.  Every warp scans the per-slot job counts in
-     * registers (lane = slot) and looks its jobs up with shuffles. */
-    int job_incl, job_excl;
+     * into this one) need work, everything else is exactly zero.  Every warp holds the prefix sums of the
+     * per-slot job counts in registers (lane = slot) and looks its jobs up with shuffles. */
+    int job_excl;
     {
-        const int act = lane < n_slots ? S.meta[lane].act : 0;
-        int prev_act = __shfl_up_sync(0xffffffffu, act, nch);
-        if (lane < nch) prev_act = 0;
-        const int nj = lane < n_slots ? max(act, prev_act) : 0;
-        job_incl = nj;
-#pragma unroll
-        for (int dd = 1; dd < 32; dd <<= 1)
-        {
-            const int v = __shfl_up_sync(0xffffffffu, job_incl, dd);
-            if (lane >= dd) job_incl += v;
-        }
-        job_excl = job_incl - nj;
+        const int up = __shfl_up_sync(0xffffffffu, job_incl, 1);
+        job_excl = lane ? up : 0;
     }
-    const int n_jobs3 = __shfl_sync(0xffffffffu, job_incl, 31);
+    const int n_jobs3 = __shfl_sync(0xffffffffu, job_incl, MP3B_TILE_SLOTS - 1);
     int job_slot[kJobs3], job_sb[kJobs3];
     {
         int lo[kJobs3];
@@ -681,6 +738,7 @@ cudaError_t launch_transform(const DeviceTables &t, const TransformArgs &a, cuda
     size_t smem = sizeof(Smem);
     if (const char *pad = getenv("MP3B_DEBUG_SMEM_PAD")) smem += (size_t)atoi(pad);   /* occupancy experiments */
     cudaError_t e;
+    k_l3_tile_meta<<<(a.n_tiles + 7)/8, 256, 0, s>>>(a);
     if (a.float_output)
     {
         e = cudaFuncSetAttribute(k_l3_transform<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -63,6 +63,31 @@ typedef struct
     int32_t  halo[2][2];
 } TileDesc;
 
+/* What one transform CTA needs to know about its tile, laid out by k_l3_tile_meta once the extents (nzl) are
+ * known so that the CTA gets everything in one round trip: per slot (granule incl. two halo granules x channel)
+ * the row to copy and how to treat it, the prefix sums of the IMDCT job list, and the tile header. */
+#define MP3B_TILE_SLOTS ((MP3B_TILE_GRANULES + 2)*2)
+/* TileSlot.info */
+#define TSI_NZL_MASK     0x3ffu          /* bits 0..9: decoded extent in lines (multiple of 32) */
+#define TSI_ACT_SHIFT    10              /* bits 10..15: subbands that can hold non-zero lines after antialias */
+#define TSI_BT_SHIFT     16              /* bits 16..17: block type */
+#define TSI_MS_SHIFT     18              /* bits 18..19: 0 none, 1 row = L + R, 2 row = L - R */
+#define TSI_NLONG_SHIFT  20              /* bits 20..22: leading long subbands of a mixed block (0, 2, 4) */
+#define TSI_MAP_SHIFT    23              /* bits 23..27: reorder map row + 1, 0 = none */
+typedef struct
+{
+    int32_t  gc;                 /* granule-channel row or -1 (zero state) */
+    uint32_t info;
+} TileSlot;
+typedef struct
+{
+    uint8_t  n_gr, nch, pad[6];           /* header: one 16-byte load */
+    uint64_t pcm_off;
+    TileSlot slot[MP3B_TILE_SLOTS];
+    uint16_t job_incl[MP3B_TILE_SLOTS];   /* inclusive prefix sums of the per-slot (slot, subband) job counts */
+    uint8_t  pad2[256 - MP3B_TILE_SLOTS*10 - 16];
+} TileRec;
+
 
 /* One Layer I / II frame (minimp3.h:1783-1802): payload position + header; its output is n_blocks blocks of
  * 12 time slots x 32 subbands per channel in the subband buffer sub12[block-channel][12][32]. */
