@@ -72,6 +72,24 @@ struct Smem
 };
 
 
+/* ---- packed FP32 pairs (PTX f32x2, sm_100: FFMA2 / FADD2 / FMUL2) ---- */
+__device__ __forceinline__ unsigned long long pack_f32x2(float lo, float hi)
+{
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack_f32x2(unsigned long long v, float &lo, float &hi)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long fma_f32x2(unsigned long long a, unsigned long long b, unsigned long long c)
+{
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+
 /* ---- TMA bulk copy + transaction barrier (PTX ISA: cp.async.bulk, mbarrier) ---- */
 __device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
@@ -117,12 +135,15 @@ __device__ __forceinline__ void fir_phase(const float *ybase, const float *__res
 {
     const int i = tid >> 5, j = tid & 31;
     if (i >= n_gr) return;
-    float c[16];
+    /* taps as (c[2m], c[2m+1]) pairs, history as (A[h], B[h-1]) pairs: one packed FMA (Blackwell FFMA2) advances
+     * the A-sum and the B-sum of the reference formula together; lanes of the pair never mix, so every partial
+     * sum is the one two scalar FMA chains would produce */
+    unsigned long long c2[8];
 #pragma unroll
-    for (int k = 0; k < 16; k += 4)
+    for (int k = 0; k < 8; k += 2)
     {
-        const float4 q = __ldg(reinterpret_cast<const float4 *>(fir_coef + j*16 + k));
-        c[k] = q.x; c[k + 1] = q.y; c[k + 2] = q.z; c[k + 3] = q.w;
+        const ulonglong2 q = __ldg(reinterpret_cast<const ulonglong2 *>(fir_coef + j*16 + 2*k));
+        c2[k] = q.x; c2[k + 1] = q.y;
     }
     const int ia = j < 16 ? 16 + j : (j == 16 ? 0 : 48 - j);
     const int ib = j <= 16 ? 16 - j : j - 16;
@@ -133,27 +154,20 @@ __device__ __forceinline__ void fir_phase(const float *ybase, const float *__res
     {
         const float *ya = ybase + (ch*ROWS + i*SLOTS)*kYPitch + ia;
         const float *yb = ybase + (ch*ROWS + i*SLOTS)*kYPitch + ib;
-        float A[16], B[16];
+        unsigned long long P[16];
 #pragma unroll
-        for (int h = 0; h < 15; h++)
-        {
-            A[h] = ya[h*kYPitch];
-            B[h] = yb[h*kYPitch];
-        }
+        for (int h = 1; h < 15; h++) P[h] = pack_f32x2(ya[h*kYPitch], yb[(h - 1)*kYPitch]);
 #pragma unroll
         for (int tt = 0; tt < SLOTS; tt++)
         {
-            const int cur = (15 + tt) & 15;
-            A[cur] = ya[(15 + tt)*kYPitch];
-            B[cur] = yb[(15 + tt)*kYPitch];
-            float acc0 = 0.f, acc1 = 0.f;
+            const int row = 15 + tt;
+            P[row & 15] = pack_f32x2(ya[row*kYPitch], yb[(row - 1)*kYPitch]);
+            unsigned long long acc = 0ull;
 #pragma unroll
-            for (int m = 0; m < 8; m++)
-            {
-                acc0 = fmaf(c[2*m], A[(15 + tt - 2*m) & 15], acc0);
-                acc1 = fmaf(c[2*m + 1], B[(15 + tt - 2*m - 1) & 15], acc1);
-            }
-            res[ch][tt] = acc0 + acc1;
+            for (int m = 0; m < 8; m++) acc = fma_f32x2(c2[m], P[(row - 2*m) & 15], acc);
+            float lo, hi;
+            unpack_f32x2(acc, lo, hi);
+            res[ch][tt] = lo + hi;
         }
     }
     if (FLOAT_OUT)
