@@ -50,6 +50,7 @@ static_assert(GT*32 <= kThreads, "one FIR job per thread");
 static_assert(kXFloats - kYFloats >= GT*2*18*2, "slack behind Y holds the specially rounded outputs");
 
 __constant__ ImdctConsts c_k;
+__constant__ unsigned long long c_sec2[16];   /* (s, s) pairs of dct_sec[16..30]: levels 16, 8, 4, 2 of the Lee recursion */
 
 struct SlotMeta
 {
@@ -88,6 +89,76 @@ __device__ __forceinline__ unsigned long long fma_f32x2(unsigned long long a, un
     unsigned long long r;
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
     return r;
+}
+
+__device__ __forceinline__ unsigned long long add_f32x2(unsigned long long a, unsigned long long b)
+{
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ unsigned long long sub_f32x2(unsigned long long a, unsigned long long b)
+{
+    unsigned long long r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ unsigned long long mul_f32x2(unsigned long long a, unsigned long long b)
+{
+    unsigned long long r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+
+/* Lee recursion on pairs: the two half-size transforms every level of dct2_32 (l3_math.cuh) spawns do the same
+ * operations with the same constants, so they ride in the two lanes of packed FP32 instructions.  Lane-wise
+ * identical to the scalar recursion. */
+template <int N>
+struct Dct2Pair
+{
+    static __device__ __forceinline__ void run(unsigned long long *x, const unsigned long long *sec)
+    {
+        unsigned long long a[N/2], b[N/2];
+#pragma unroll
+        for (int i = 0; i < N/2; i++)
+        {
+            a[i] = add_f32x2(x[i], x[N - 1 - i]);
+            b[i] = mul_f32x2(sub_f32x2(x[i], x[N - 1 - i]), sec[i]);
+        }
+        Dct2Pair<N/2>::run(a, sec + N/2);
+        Dct2Pair<N/2>::run(b, sec + N/2);
+#pragma unroll
+        for (int k = 0; k < N/2; k++)
+        {
+            x[2*k] = a[k];
+            x[2*k + 1] = (k + 1 < N/2) ? add_f32x2(b[k], b[k + 1]) : b[k];
+        }
+    }
+};
+template <>
+struct Dct2Pair<1>
+{
+    static __device__ __forceinline__ void run(unsigned long long *, const unsigned long long *) {}
+};
+
+/* 32-point DCT-II of dct2_32(): first butterfly level in scalars, the two 16-point halves as one packed
+ * transform, scalar recombination */
+__device__ __forceinline__ void dct2_32_paired(float *x)
+{
+    unsigned long long p[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++)
+        p[i] = pack_f32x2(x[i] + x[31 - i], (x[i] - x[31 - i])*c_k.dct_sec[i]);
+    Dct2Pair<16>::run(p, c_sec2);
+    float a[16], b[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) unpack_f32x2(p[k], a[k], b[k]);
+#pragma unroll
+    for (int k = 0; k < 16; k++)
+    {
+        x[2*k] = a[k];
+        x[2*k + 1] = k + 1 < 16 ? b[k] + b[k + 1] : b[k];
+    }
 }
 
 /* ---- TMA bulk copy + transaction barrier (PTX ISA: cp.async.bulk, mbarrier) ---- */
@@ -605,7 +676,7 @@ k_l3_transform(TransformArgs a, const uint16_t *__restrict__ reorder_inv, const 
             float v[32];
 #pragma unroll
             for (int k = 0; k < 32; k++) v[k] = y[k];
-            dct2_32(v, c_k.dct_sec);
+            dct2_32_paired(v);
 #pragma unroll
             for (int k = 0; k < 32; k++) y[k] = v[k];
         }
@@ -692,7 +763,7 @@ k_l12_synth(Synth12Args a, const float *__restrict__ fir_coef)
         float v[32];
 #pragma unroll
         for (int k = 0; k < 32; k++) v[k] = row[k];
-        dct2_32(v, c_k.dct_sec);
+        dct2_32_paired(v);
 #pragma unroll
         for (int k = 0; k < 32; k++) row[k] = v[k];
     }
@@ -721,6 +792,12 @@ int tables_upload(DeviceTables *t)
     ImdctConsts k;
     build_consts(&k);
     if (cudaMemcpyToSymbol(c_k, &k, sizeof(k)) != cudaSuccess) return -1;
+    {
+        float sec2[32];
+        for (int i = 0; i < 15; i++) sec2[2*i] = sec2[2*i + 1] = k.dct_sec[16 + i];
+        sec2[30] = sec2[31] = 0.f;
+        if (cudaMemcpyToSymbol(c_sec2, sec2, sizeof(sec2)) != cudaSuccess) return -1;
+    }
     static uint16_t map[16*576];
     static float fir[32*16];
     {
