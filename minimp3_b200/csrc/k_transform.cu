@@ -340,6 +340,7 @@ k_l3_tile_meta(TransformArgs a)
         const int v = __shfl_up_sync(0xffffffffu, incl, dd);
         if (lane >= dd) incl += v;
     }
+    const int nj = lane < n_slots ? max(act_l, prev_act) : 0;
     TileRec *rec = a.tile_recs + t;
     if (lane < MP3B_TILE_SLOTS)
     {
@@ -348,13 +349,20 @@ k_l3_tile_meta(TransformArgs a)
         ts.info = (uint32_t)nzl | (uint32_t)act << TSI_ACT_SHIFT | (uint32_t)bt << TSI_BT_SHIFT | (uint32_t)ms << TSI_MS_SHIFT |
                   (uint32_t)n_long << TSI_NLONG_SHIFT | (uint32_t)(map + 1) << TSI_MAP_SHIFT;
         rec->slot[lane] = ts;
-        rec->job_incl[lane] = (uint16_t)incl;
     }
     if (lane == 0)
     {
         rec->n_gr = tile.n_gr;
         rec->nch = tile.nch;
         rec->pcm_off = tile.pcm_off;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    if (lane == 0) rec->n_jobs = (uint16_t)total;
+    uint16_t *jobs = a.tile_jobs + (size_t)t*MP3B_TILE_JOBS;
+    for (int sl = 0; sl < n_slots; sl++)
+    {
+        const int start = __shfl_sync(0xffffffffu, incl - nj, sl), n = __shfl_sync(0xffffffffu, nj, sl);
+        if (lane < n) jobs[start + lane] = (uint16_t)(sl << 8 | lane);
     }
 }
 
@@ -366,14 +374,20 @@ k_l3_transform(TransformArgs a, const uint16_t *__restrict__ reorder_inv, const 
     Smem &S = *reinterpret_cast<Smem *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const TileRec *rec = a.tile_recs + blockIdx.x;
-    struct { uint8_t n_gr, nch, pad[6]; uint64_t pcm_off; } tile;
+    struct { uint8_t n_gr, nch; uint16_t n_jobs; uint64_t pcm_off; } tile;
     {
         const uint4 h = __ldg(reinterpret_cast<const uint4 *>(&rec->n_gr));
         tile.n_gr = (uint8_t)(h.x & 0xff);
         tile.nch = (uint8_t)((h.x >> 8) & 0xff);
+        tile.n_jobs = (uint16_t)(h.x >> 16);
         tile.pcm_off = (uint64_t)h.z | (uint64_t)h.w << 32;
     }
-    int job_incl = (int)__ldg(&rec->job_incl[min(lane, MP3B_TILE_SLOTS - 1)]);   /* lanes past the table hold the total */
+    /* this thread's IMDCT jobs (slot << 8 | subband): fetched now, needed after the rows are in */
+    constexpr int kJobs3 = (kSlots*32 + kThreads - 1)/kThreads;   /* 3 */
+    uint16_t job_code[kJobs3];
+#pragma unroll
+    for (int r = 0; r < kJobs3; r++)
+        job_code[r] = tid + r*kThreads < MP3B_TILE_JOBS ? __ldg(a.tile_jobs + (size_t)blockIdx.x*MP3B_TILE_JOBS + tid + r*kThreads) : (uint16_t)0;
     const int nch = tile.nch, n_gr = tile.n_gr;
     const int n_slots = (n_gr + 2)*nch;
     const bool stateful = a.state_in != nullptr;
@@ -517,40 +531,14 @@ k_l3_transform(TransformArgs a, const uint16_t *__restrict__ reorder_inv, const 
     /* ---- phases 2+3a: per active (slot, subband): antialias butterflies against both neighbours
      * (minimp3.h:1012-1045, recomputed on the fly instead of a separate in-place pass), then IMDCT tail and
      * own half ---- */
-    constexpr int kJobs3 = (kSlots*32 + kThreads - 1)/kThreads;   /* 3 */
     float own[kJobs3][9];
-    /* job list: only subbands that are active in the granule itself or in the one before it (whose tail overlaps
-     * into this one) need work, everything else is exactly zero.  Every warp holds the prefix sums of the
-     * per-slot job counts in registers (lane = slot) and looks its jobs up with shuffles. */
-    int job_excl;
-    {
-        const int up = __shfl_up_sync(0xffffffffu, job_incl, 1);
-        job_excl = lane ? up : 0;
-    }
-    const int n_jobs3 = __shfl_sync(0xffffffffu, job_incl, MP3B_TILE_SLOTS - 1);
+    const int n_jobs3 = tile.n_jobs;
     int job_slot[kJobs3], job_sb[kJobs3];
+#pragma unroll
+    for (int r = 0; r < kJobs3; r++)
     {
-        int lo[kJobs3];
-#pragma unroll
-        for (int r = 0; r < kJobs3; r++) lo[r] = 0;
-#pragma unroll
-        for (int step = 16; step >= 1; step >>= 1)
-        {
-            /* first slot whose inclusive count exceeds the job index */
-#pragma unroll
-            for (int r = 0; r < kJobs3; r++)
-            {
-                const int v = __shfl_sync(0xffffffffu, job_incl, lo[r] + step - 1);
-                if (v <= tid + r*kThreads) lo[r] += step;
-            }
-        }
-#pragma unroll
-        for (int r = 0; r < kJobs3; r++)
-        {
-            const int e = __shfl_sync(0xffffffffu, job_excl, lo[r] & 31);
-            job_sb[r] = tid + r*kThreads - e;
-            job_slot[r] = tid + r*kThreads < n_jobs3 ? lo[r] : -1;
-        }
+        job_slot[r] = tid + r*kThreads < n_jobs3 ? job_code[r] >> 8 : -1;
+        job_sb[r] = job_code[r] & 31;
     }
 #pragma unroll
     for (int r = 0; r < kJobs3; r++)

@@ -51,6 +51,7 @@ struct TransformArgs
     const float *xr;
     const uint16_t *nzl;
     TileRec *tile_recs;           /* scratch [n_tiles], written by k_l3_tile_meta, read by k_l3_transform */
+    uint16_t *tile_jobs;          /* scratch [n_tiles][MP3B_TILE_JOBS], likewise */
     void *pcm;                    /* int16 or float, interleaved */
     int float_output;
     /* optional carried state for the single-frame API (null in batch mode): mp3dec_t.mdct_overlap / qmf_state */

@@ -74,6 +74,10 @@ typedef struct
 #define TSI_MS_SHIFT     18              /* bits 18..19: 0 none, 1 row = L + R, 2 row = L - R */
 #define TSI_NLONG_SHIFT  20              /* bits 20..22: leading long subbands of a mixed block (0, 2, 4) */
 #define TSI_MAP_SHIFT    23              /* bits 23..27: reorder map row + 1, 0 = none */
+/* IMDCT job list of a tile: [MP3B_TILE_JOBS] entries (slot << 8 | subband), the first TileRec.n_jobs valid:
+ * only subbands that are active in the granule itself or in the one before it (whose tail overlaps into it)
+ * need work, everything else is exactly zero. */
+#define MP3B_TILE_JOBS (MP3B_TILE_SLOTS*32)
 typedef struct
 {
     int32_t  gc;                 /* granule-channel row or -1 (zero state) */
@@ -81,11 +85,12 @@ typedef struct
 } TileSlot;
 typedef struct
 {
-    uint8_t  n_gr, nch, pad[6];           /* header: one 16-byte load */
+    uint8_t  n_gr, nch;                   /* header: one 16-byte load */
+    uint16_t n_jobs;                      /* entries of the tile's IMDCT job list */
+    uint8_t  pad[4];
     uint64_t pcm_off;
     TileSlot slot[MP3B_TILE_SLOTS];
-    uint16_t job_incl[MP3B_TILE_SLOTS];   /* inclusive prefix sums of the per-slot (slot, subband) job counts */
-    uint8_t  pad2[256 - MP3B_TILE_SLOTS*10 - 16];
+    uint8_t  pad2[256 - MP3B_TILE_SLOTS*8 - 16];
 } TileRec;
 
 
