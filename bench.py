@@ -30,7 +30,8 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-VECTOR = os.path.join(ROOT, "tests", "golden", "vectors", "l3-sin1k0db.bit")
+VECTOR_DIR = os.path.join(ROOT, "tests", "golden", "vectors")
+DEFAULT_VECTOR = "l3-sin1k0db.bit"     # BASELINE.json configs[1]: 44.1 kHz stereo Layer III
 METRIC = "decoded PCM samples/sec (whole box), 44.1k stereo L3 batch"
 UNIT = "samples/s"
 # algorithmic bytes per output sample: transform kernel 4 B spectra in + 2 B PCM out;
@@ -119,7 +120,8 @@ def run_reference(args, rank, world):
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built and /root/reference absent"}))
         return
     ref = refshim.Ref()
-    data = open(VECTOR, "rb").read()
+    data = open(os.path.join(VECTOR_DIR, args.vector), "rb").read()
+    vname = os.path.splitext(args.vector)[0]
     cores = os.cpu_count() or 1
     # bounded sample: enough streams for ~1 s of wall time per step, never more than the GPU batch
     n_streams = max(cores, min(args.streams, cores*32))
@@ -135,10 +137,10 @@ def run_reference(args, rank, world):
     value = total/secs
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 2),
             "ms_per_step": 1e3*secs/steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic: l3-sin1k0db.bit (44.1 kHz stereo Layer III conformance stream) tiled",
+            "dtype": "f32", "data": "synthetic: %s (Layer III conformance stream) tiled" % args.vector,
             "impl": "reference",
-            "config": {"workload": "%d-stream batch tiled from l3-sin1k0db (44.1 kHz stereo L3), CPU sample of the %d-stream GPU batch"
-                       % (n_streams, args.streams), "streams": n_streams},
+            "config": {"workload": "%d-stream batch tiled from %s (44.1 kHz stereo L3), CPU sample of the %d-stream GPU batch"
+                       % (n_streams, vname, args.streams), "streams": n_streams},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference",
                              "sample": "%d streams x %d steps, minimp3 SSE2 path (gcc -O2), one mp3dec_t per stream, pthreads"
                              % (n_streams, steps)},
@@ -153,6 +155,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--streams", type=int, default=1024, help="streams per GPU")
+    ap.add_argument("--vector", default=DEFAULT_VECTOR, help="stream in tests/golden/vectors the batch is tiled from (other than the default: exploration only)")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -177,7 +180,8 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    data = open(VECTOR, "rb").read()
+    data = open(os.path.join(VECTOR_DIR, args.vector), "rb").read()
+    vname = os.path.splitext(args.vector)[0]
     streams = [data]*args.streams          # independent streams; shards need no collective
     stream = torch.cuda.Stream()
     plan = m.BatchPlan(streams, device=local_rank, raw_frames=False, output=m.OUT_PINNED, cuda_stream=stream.cuda_stream)
@@ -268,8 +272,8 @@ def main():
                 traffic = None
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_max/args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f32", "data": "synthetic: l3-sin1k0db.bit (44.1 kHz stereo Layer III conformance stream) tiled",
-                "config": {"workload": "%d-stream batch tiled from l3-sin1k0db (44.1 kHz stereo L3) per GPU" % args.streams,
+                "dtype": "f32", "data": "synthetic: %s (Layer III conformance stream) tiled" % args.vector,
+                "config": {"workload": "%d-stream batch tiled from %s (44.1 kHz stereo L3) per GPU" % (args.streams, vname),
                            "streams_per_gpu": args.streams, "frames_per_gpu": int(st["n_frames"]),
                            "granule_channels_per_gpu": int(st["n_granule_channels"]), "samples_per_step_per_gpu": samples_per_step,
                            "parallelism": "streams sharded over %d GPU(s), no collective" % world,

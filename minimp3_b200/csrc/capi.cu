@@ -528,8 +528,10 @@ static int plan_run_stages(mp3dec_batch_plan_t *P, int stage_mask)
     ea.xr = (float *)B.d_xr.p;
     ea.nzl = (uint16_t *)B.d_nzl.p;
     ea.ist_pos = (uint8_t *)B.d_istpos.p;
-    ea.tap_q = P->taps ? (int16_t *)B.d_tap_q.p : nullptr;
-    ea.tap_scf = P->taps ? (float *)B.d_tap_scf.p : nullptr;
+    static const bool clk_only = getenv("MP3B_DEBUG_CLK_ONLY") != nullptr;   /* tools/phase_times.py: phase clocks without the stage taps */
+    const bool stage_taps = P->taps && !clk_only;
+    ea.tap_q = stage_taps ? (int16_t *)B.d_tap_q.p : nullptr;
+    ea.tap_scf = stage_taps ? (float *)B.d_tap_scf.p : nullptr;
     cudaError_t e = cudaSuccess;
     if (stage_mask & 1) e = launch_entropy(P->ctx->tables, ea, P->stream);
     if (e == cudaSuccess && P->n_ist && (stage_mask & 2))
@@ -556,7 +558,7 @@ static int plan_run_stages(mp3dec_batch_plan_t *P, int stage_mask)
         ta.tile_jobs = (uint16_t *)B.d_tile_jobs.p;
         ta.pcm = B.d_pcm.p;
         ta.float_output = P->opts.float_output;
-        ta.tap_sub = P->taps ? (float *)B.d_tap_sub.p : nullptr;
+        ta.tap_sub = stage_taps ? (float *)B.d_tap_sub.p : nullptr;
         ta.phase_clk = P->taps ? (long long *)B.d_phase_clk.p : nullptr;
         e = launch_transform(P->ctx->tables, ta, P->stream);
     }

@@ -9,9 +9,10 @@
  * sorts them, see build_order in host_parse.cpp) so that its lanes finish together.  Huffman decode
  * is serial inside a granule, so the parallelism is across granules; to keep the memory side coalesced
  * the warp runs a SIMT-uniform loop over line pairs (iteration k produces lines 2k, 2k+1 of all 32
- * granule-channels; a count1 quad takes two iterations), stages 32 lines x 32 rows in shared memory and
- * flushes them as full 128-byte row segments.  Code books, |q|^(4/3) and band widths sit in shared memory.
- * Rows are only written up to the last decoded line (rounded up to 32); nzl[] tells the consumer.
+ * granule-channels; a count1 quad takes two iterations) and every lane stores its pair straight into its row:
+ * the two 16-byte stores that make up a 32-byte sector arrive within a few microseconds and merge in L2, so
+ * HBM sees whole sectors and no shared-memory transpose is needed.  Code books, |q|^(4/3) and band widths sit in
+ * shared memory.  Rows are only written up to the last decoded line (rounded up to 32); nzl[] tells the consumer.
  */
 #include <cuda_runtime.h>
 
@@ -25,9 +26,7 @@ namespace mp3b {
 namespace {
 
 constexpr int kWarpsPerBlock = 16;
-constexpr int kStageLines = 32;
 constexpr int kC1Base = MP3T_HUFF_LUT_SIZE;          /* count1 table A (64 entries) then B (16) */
-constexpr int kStagePitch = 33;
 
 struct SharedTables
 {
@@ -41,7 +40,7 @@ struct SharedTables
 
 struct WarpScratch
 {
-    float stage[kStageLines*kStagePitch];   /* also holds the previous granule's scalefactors during set-up */
+    uint8_t prev[40*32];    /* the previous granule's scalefactors during set-up (scfsi) */
     uint8_t iscf[40*32];
 };
 
@@ -105,7 +104,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock*32, 2) k_l3_entropy(EntropyArgs
             GcDesc d0;
             const bool use_d0 = valid && (d.flags1 & GCF1_GR1) && d.scfsi;
             if (use_d0) d0 = load_desc(a.gcs + (gc - ((d.flags1 & GCF1_STEREO) ? 2 : 1)));
-            dec.init(d, use_d0 ? &d0 : nullptr, a.md_words, a.md_n_words, T, W.iscf + lane, reinterpret_cast<uint8_t *>(W.stage) + lane, 32,
+            dec.init(d, use_d0 ? &d0 : nullptr, a.md_words, a.md_n_words, T, W.iscf + lane, W.prev + lane, 32,
                      want_ist ? ist_local : nullptr, &n_ist);
             if (want_ist)
             {
@@ -121,43 +120,26 @@ __global__ void __launch_bounds__(kWarpsPerBlock*32, 2) k_l3_entropy(EntropyArgs
         }
         int16_t *tq = (a.tap_q && valid) ? a.tap_q + (size_t)gc*576 : nullptr;
 
+        float *row = a.xr + (size_t)gc*576;
         int iter = 0;
-        int flushed = 0;   /* lines already flushed */
         for (;;)
         {
-            float v0, v1;
-            int q0, q1;
-            dec.step(T, v0, v1, q0, q1);
-            if (tq && (q0 | q1)) { tq[2*iter] = (int16_t)q0; tq[2*iter + 1] = (int16_t)q1; }
+            /* two steps = four lines = one 16-byte store */
+            float4 v;
+            int q0, q1, q2, q3;
+            dec.step(T, v.x, v.y, q0, q1);
+            dec.step(T, v.z, v.w, q2, q3);
+            if (tq && (q0 | q1 | q2 | q3))
             {
-                const int col = (2*iter) & (kStageLines - 1);
-                W.stage[col*kStagePitch + lane] = v0;
-                W.stage[(col + 1)*kStagePitch + lane] = v1;
+                tq[2*iter] = (int16_t)q0; tq[2*iter + 1] = (int16_t)q1;
+                tq[2*iter + 2] = (int16_t)q2; tq[2*iter + 3] = (int16_t)q3;
             }
-            iter++;
+            /* a finished lane keeps writing zeros up to the 32-line boundary behind its last decoded line */
+            const int my_end = dec.mode == EMODE_DONE ? ((dec.extent + 31) & ~31) : 576;
+            if (valid && 2*iter < my_end) *reinterpret_cast<float4 *>(row + 2*iter) = v;
+            iter += 2;
             bool finished = iter == 288;
             if ((iter & 15) == 0 && !finished) finished = __ballot_sync(0xffffffffu, dec.mode != EMODE_DONE) == 0;
-            if (finished || (iter & 15) == 0)
-            {
-                /* ---- flush lines [flushed, 2*iter) of all 32 rows ---- */
-                __syncwarp();
-                const int my_ext = !valid ? 0 : (dec.mode == EMODE_DONE) ? ((dec.extent + 31) & ~31) : 576;
-                const int n_lines = 2*iter - flushed;   /* 32 */
-                for (int r = 0; r < 32; r++)
-                {
-                    const int e = __shfl_sync(0xffffffffu, my_ext, r);
-                    const uint32_t g = __shfl_sync(0xffffffffu, gc, r);
-                    if (flushed >= e) continue;
-                    float *row = a.xr + (size_t)g*576;
-                    for (int c = lane; c < n_lines; c += 32)
-                    {
-                        const int line = flushed + c;
-                        if (line < e) row[line] = W.stage[(line & (kStageLines - 1))*kStagePitch + r];
-                    }
-                }
-                flushed = 2*iter;
-                __syncwarp();
-            }
             if (finished) break;
         }
         /* ---- per-row extent for the consumer ---- */

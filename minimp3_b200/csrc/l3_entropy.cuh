@@ -34,17 +34,26 @@ struct BitRd
     const uint32_t *w;
     uint64_t n_words, widx;
     uint32_t hi, lo;        /* window, MSB-aligned: `avail` valid bits from bit 31 of hi downwards */
-    uint32_t next, next2;   /* two words of lookahead */
+    uint32_t next, next2;   /* two words of lookahead; next2 still in memory byte order */
     int avail;
     int pos;                /* bits consumed since init */
 
-    MP3_HD uint32_t word(uint64_t i) const
+    /* word i as stored (big-endian bit order not applied yet).  The device buffer carries 64 bytes of slack
+     * behind the last payload byte (capi.cu), the host harness is bounds-checked. */
+    MP3_HD uint32_t raw(uint64_t i) const
     {
-        if (i >= n_words) return 0u;
 #if defined(__CUDA_ARCH__)
-        return __byte_perm(__ldg(w + i), 0, 0x0123);
+        return __ldg(w + i);
 #else
-        return __builtin_bswap32(w[i]);
+        return i >= n_words ? 0u : w[i];
+#endif
+    }
+    static MP3_HD uint32_t be(uint32_t v)
+    {
+#if defined(__CUDA_ARCH__)
+        return __byte_perm(v, 0, 0x0123);
+#else
+        return __builtin_bswap32(v);
 #endif
     }
     /* upper 32 bits of (h:l) << n, 0 <= n < 32 */
@@ -61,12 +70,12 @@ struct BitRd
         w = words; n_words = nw;
         widx = bit_off >> 5;
         const int sh = (int)(bit_off & 31);
-        const uint32_t w0 = word(widx), w1 = word(widx + 1);
+        const uint32_t w0 = be(raw(widx)), w1 = be(raw(widx + 1));
         hi = shl_hi(w0, w1, sh);
         lo = w1 << sh;
         avail = 64 - sh;
-        next = word(widx + 2);
-        next2 = word(widx + 3);
+        next = be(raw(widx + 2));
+        next2 = raw(widx + 3);
         widx += 4;
         pos = 0;
     }
@@ -79,8 +88,8 @@ struct BitRd
             hi |= shl_hi(0u, next, sh);
             lo = next << sh;
             avail += 32;
-            next = next2;
-            next2 = word(widx++);
+            next = be(next2);          /* the byte swap waits here, one refill after the load was issued */
+            next2 = raw(widx++);
         }
     }
     MP3_HD uint32_t peek(int n) const { return n ? hi >> (32 - n) : 0u; }
@@ -338,16 +347,16 @@ struct GranuleDecoder
             x = (pending >> 1) & 1;
             y = pending & 1;
         }
+        /* at least 32 bits in the window: both escapes and signs take 2*(13 + 1) at most */
         br.refill();
-        if (x == 15 && linbits) { x += (int)br.peek(linbits); br.skip(linbits); br.refill(); }
+        if (x == 15 && linbits) { x += (int)br.peek(linbits); br.skip(linbits); }
         if (x)
         {
             const int neg = (int)br.peek(1); br.skip(1);
             const float m = MP3_FMUL(one, l3_pow43(x, T.pow43));
             v0 = neg ? -m : m; q0 = neg ? -x : x;
         }
-        br.refill();
-        if (y == 15 && linbits) { y += (int)br.peek(linbits); br.skip(linbits); br.refill(); }
+        if (y == 15 && linbits) { y += (int)br.peek(linbits); br.skip(linbits); }
         if (y)
         {
             const int neg = (int)br.peek(1); br.skip(1);

@@ -7,6 +7,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+os.environ.setdefault("MP3B_DEBUG_CLK_ONLY", "1")
 import minimp3_b200 as m  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 256
