@@ -10,8 +10,8 @@
  * is serial inside a granule, so the parallelism is across granules; to keep the memory side coalesced
  * the warp runs a SIMT-uniform loop over line pairs (iteration k produces lines 2k, 2k+1 of all 32
  * granule-channels; a count1 quad takes two iterations) and every lane stores its pair straight into its row:
- * the two 16-byte stores that make up a 32-byte sector arrive within a few microseconds and merge in L2, so
- * HBM sees whole sectors and no shared-memory transpose is needed.  Code books, |q|^(4/3) and band widths sit in
+ * eight lines = one 32-byte sector are collected in registers and leave as two 16-byte stores, so
+ * L2 and HBM see whole sectors and no shared-memory transpose is needed.  Code books, |q|^(4/3) and band widths sit in
  * shared memory.  Rows are only written up to the last decoded line (rounded up to 32); nzl[] tells the consumer.
  */
 #include <cuda_runtime.h>
@@ -122,9 +122,10 @@ __global__ void __launch_bounds__(kWarpsPerBlock*32, 2) k_l3_entropy(EntropyArgs
 
         float *row = a.xr + (size_t)gc*576;
         int iter = 0;
+        float4 held = make_float4(0.f, 0.f, 0.f, 0.f);
         for (;;)
         {
-            /* two steps = four lines = one 16-byte store */
+            /* two steps = four lines = half a 32-byte sector */
             float4 v;
             int q0, q1, q2, q3;
             dec.step(T, v.x, v.y, q0, q1);
@@ -136,7 +137,16 @@ __global__ void __launch_bounds__(kWarpsPerBlock*32, 2) k_l3_entropy(EntropyArgs
             }
             /* a finished lane keeps writing zeros up to the 32-line boundary behind its last decoded line */
             const int my_end = dec.mode == EMODE_DONE ? ((dec.extent + 31) & ~31) : 576;
-            if (valid && 2*iter < my_end) *reinterpret_cast<float4 *>(row + 2*iter) = v;
+            if (iter & 2)
+            {
+                /* every other round: the 32-byte sector leaves as a whole */
+                if (valid && 2*iter < my_end)
+                {
+                    *reinterpret_cast<float4 *>(row + 2*iter - 4) = held;
+                    *reinterpret_cast<float4 *>(row + 2*iter) = v;
+                }
+            } else
+                held = v;
             iter += 2;
             bool finished = iter == 288;
             if ((iter & 15) == 0 && !finished) finished = __ballot_sync(0xffffffffu, dec.mode != EMODE_DONE) == 0;
