@@ -29,6 +29,19 @@ struct EntropyTables
 /* MSB-first bit reader over big-endian bytes, fed by aligned 32-bit loads.  The 64-bit window is kept as two
  * 32-bit halves (funnel shifts instead of 64-bit shifts) and two more words are fetched ahead of need so the
  * global-load latency overlaps with the decoding of the bits already in the window. */
+/* m with its sign bit toggled when neg is 1 */
+MP3_HD float flip_sign(float m, uint32_t neg)
+{
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(__float_as_uint(m) ^ (neg << 31));
+#else
+    union { float f; uint32_t u; } c;
+    c.f = m;
+    c.u ^= neg << 31;
+    return c.f;
+#endif
+}
+
 struct BitRd
 {
     const uint32_t *w;
@@ -347,21 +360,26 @@ struct GranuleDecoder
             x = (pending >> 1) & 1;
             y = pending & 1;
         }
-        /* at least 32 bits in the window: both escapes and signs take 2*(13 + 1) at most */
+        /* escapes and signs of both values (minimp3.h:807-826) from one snapshot of the window, without
+         * branches: at least 32 bits are in, the four fields take 2*(13 + 1) at most */
         br.refill();
-        if (x == 15 && linbits) { x += (int)br.peek(linbits); br.skip(linbits); }
-        if (x)
         {
-            const int neg = (int)br.peek(1); br.skip(1);
-            const float m = MP3_FMUL(one, l3_pow43(x, T.pow43));
-            v0 = neg ? -m : m; q0 = neg ? -x : x;
-        }
-        if (y == 15 && linbits) { y += (int)br.peek(linbits); br.skip(linbits); }
-        if (y)
-        {
-            const int neg = (int)br.peek(1); br.skip(1);
-            const float m = MP3_FMUL(one, l3_pow43(y, T.pow43));
-            v1 = neg ? -m : m; q1 = neg ? -y : y;
+            const uint32_t t = br.hi;
+            const int n1 = x == 15 ? linbits : 0, s1 = x != 0;
+            const int n2 = y == 15 ? linbits : 0, s2 = y != 0;
+            x += (int)((t >> 1) >> (31 - n1));
+            const uint32_t t1 = t << n1;
+            const uint32_t neg_x = (t1 >> 31) & (uint32_t)s1;
+            const uint32_t t2 = t1 << s1;
+            y += (int)((t2 >> 1) >> (31 - n2));
+            const uint32_t t3 = t2 << n2;
+            const uint32_t neg_y = (t3 >> 31) & (uint32_t)s2;
+            br.skip(n1 + s1 + n2 + s2);
+            /* a zero value gives one * 0 = +0 and reads no sign */
+            v0 = flip_sign(MP3_FMUL(one, l3_pow43(x, T.pow43)), neg_x);
+            v1 = flip_sign(MP3_FMUL(one, l3_pow43(y, T.pow43)), neg_y);
+            q0 = neg_x ? -x : x;
+            q1 = neg_y ? -y : y;
         }
         if (mode == EMODE_BIG) { if (--big_left == 0) mode = EMODE_C1A; }
         else mode = (mode == EMODE_C1A) ? EMODE_C1B : EMODE_C1A;
