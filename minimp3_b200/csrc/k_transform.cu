@@ -70,6 +70,7 @@ struct Smem
     float t[kTFloats];      /* tails [slot][i][sb] */
     SlotMeta meta[kSlots];
     unsigned long long mbar[kThreads/32];   /* one transaction barrier per warp: its rows' bulk copies */
+    alignas(16) float fir_taps[512];
 };
 
 
@@ -195,13 +196,21 @@ __device__ __forceinline__ uint32_t f2s16_rn_sat(float x)
     return (uint32_t)(uint16_t)r;
 }
 
+/* the 32 x 16 window taps, staged once per CTA in shared memory as [4 chunks][32 phases][4 taps] so that the
+ * FIR threads of a warp (one per phase) fetch them with conflict-free 16-byte loads */
+__device__ __forceinline__ void stage_fir_taps(float *fir_taps, const float *__restrict__ fir_coef, int tid)
+{
+    if (tid < 128)
+        reinterpret_cast<float4 *>(fir_taps)[tid] = __ldg(reinterpret_cast<const float4 *>(fir_coef) + (tid & 31)*4 + (tid >> 5));
+}
+
 /* ---- phase 5: 512-tap window as a 16-tap FIR per output phase (ISO 11172-3 fig. A.2 restated) ----
  * pcm[32 t + j] = sum_m  D[64m + j] V_{t-2m}[j] + D[64m + 32 + j] V_{t-2m-1}[32 + j];  V_t[j] = +-y_t[ia],
  * V_t[32 + j] = -y_t[ib] (signs folded into the taps).  One thread = one output phase j of one granule, both
  * channels; the 16-slot history lives in registers.  The two phases the reference rounds with its scalar
  * helper (j = 0, 16) are parked in shared memory and finished by a separate pass. */
 template <bool FLOAT_OUT, int NCH, int SLOTS, int ROWS>
-__device__ __forceinline__ void fir_phase(const float *ybase, const float *__restrict__ fir_coef, float *special,
+__device__ __forceinline__ void fir_phase(const float *ybase, const float *fir_taps, float *special,
                                           void *pcm, uint64_t pcm_off, int n_gr, int tid)
 {
     const int i = tid >> 5, j = tid & 31;
@@ -213,7 +222,7 @@ __device__ __forceinline__ void fir_phase(const float *ybase, const float *__res
 #pragma unroll
     for (int k = 0; k < 8; k += 2)
     {
-        const ulonglong2 q = __ldg(reinterpret_cast<const ulonglong2 *>(fir_coef + j*16 + 2*k));
+        const ulonglong2 q = reinterpret_cast<const ulonglong2 *>(fir_taps)[(k >> 1)*32 + j];   /* [chunk][phase]: no bank conflicts */
         c2[k] = q.x; c2[k + 1] = q.y;
     }
     const int ia = j < 16 ? 16 + j : (j == 16 ? 0 : 48 - j);
@@ -374,6 +383,7 @@ k_l3_transform(TransformArgs a, const uint16_t *__restrict__ reorder_inv, const 
     Smem &S = *reinterpret_cast<Smem *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const TileRec *rec = a.tile_recs + blockIdx.x;
+    stage_fir_taps(S.fir_taps, fir_coef, tid);     /* visible to everybody long before phase 5 (several barriers) */
     struct { uint8_t n_gr, nch; uint16_t n_jobs; uint64_t pcm_off; } tile;
     {
         const uint4 h = __ldg(reinterpret_cast<const uint4 *>(&rec->n_gr));
@@ -674,8 +684,8 @@ k_l3_transform(TransformArgs a, const uint16_t *__restrict__ reorder_inv, const 
 
     /* ---- phase 5: window FIR + PCM conversion ---- */
     float *special = S.x + kYFloats;     /* slack behind Y: n_gr*2*18*nch floats */
-    if (nch == 2) fir_phase<FLOAT_OUT, 2, 18, kRows>(S.x, fir_coef, special, a.pcm, tile.pcm_off, n_gr, tid);
-    else fir_phase<FLOAT_OUT, 1, 18, kRows>(S.x, fir_coef, special, a.pcm, tile.pcm_off, n_gr, tid);
+    if (nch == 2) fir_phase<FLOAT_OUT, 2, 18, kRows>(S.x, S.fir_taps, special, a.pcm, tile.pcm_off, n_gr, tid);
+    else fir_phase<FLOAT_OUT, 1, 18, kRows>(S.x, S.fir_taps, special, a.pcm, tile.pcm_off, n_gr, tid);
     if (!FLOAT_OUT)
     {
         __syncthreads();
@@ -712,7 +722,9 @@ __global__ void __launch_bounds__(kThreads, 3)
 k_l12_synth(Synth12Args a, const float *__restrict__ fir_coef)
 {
     __shared__ float y[kY12Floats + GT*2*12*2];
+    __shared__ __align__(16) float fir_taps[512];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    stage_fir_taps(fir_taps, fir_coef, tid);
     const TileDesc tile = a.tiles[blockIdx.x];
     const int nch = tile.nch, n_gr = tile.n_gr;
     const bool stateful = a.state_in != nullptr;
@@ -757,8 +769,8 @@ k_l12_synth(Synth12Args a, const float *__restrict__ fir_coef)
     }
     __syncthreads();
     float *special = y + kY12Floats;
-    if (nch == 2) fir_phase<FLOAT_OUT, 2, 12, kRows12>(y, fir_coef, special, a.pcm, tile.pcm_off, n_gr, tid);
-    else fir_phase<FLOAT_OUT, 1, 12, kRows12>(y, fir_coef, special, a.pcm, tile.pcm_off, n_gr, tid);
+    if (nch == 2) fir_phase<FLOAT_OUT, 2, 12, kRows12>(y, fir_taps, special, a.pcm, tile.pcm_off, n_gr, tid);
+    else fir_phase<FLOAT_OUT, 1, 12, kRows12>(y, fir_taps, special, a.pcm, tile.pcm_off, n_gr, tid);
     if (!FLOAT_OUT)
     {
         __syncthreads();
