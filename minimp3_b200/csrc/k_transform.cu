@@ -47,6 +47,7 @@ constexpr int kTFloats = kSlots*288;
 static_assert(sizeof(TileRec) == 256 && MP3B_TILE_SLOTS == kSlots, "tile record layout");
 static_assert(kYFloats <= kXFloats, "Y must fit in the X region");
 static_assert(GT*32 <= kThreads, "one FIR job per thread");
+static_assert(((GT + 2 + kThreads/32 - 1)/(kThreads/32))*2 <= 4, "a warp clears at most four rows, a quarter-warp each");
 static_assert(kXFloats - kYFloats >= GT*2*18*2, "slack behind Y holds the specially rounded outputs");
 
 __constant__ ImdctConsts c_k;
@@ -407,9 +408,9 @@ k_l3_transform(TransformArgs a, const uint16_t *__restrict__ reorder_inv, const 
 
     /* ---- phases 0+1, every warp on its own for the granules it owns (unit u = granule incl. halo belongs to
      * warp u % 8; lane = (unit, channel)): fetch the slot records (one round trip: k_l3_tile_meta did the
-     * dependent work), clear the rows and tails of the unit meanwhile (lines at or beyond nzl were never written
-     * by the entropy kernel and are zero by definition; only active subbands write tails), one TMA bulk copy per
-     * row for its decoded extent on the warp's transaction barrier, wait, plain MS stereo in place.  Rows keep
+     * dependent work), one TMA bulk copy per row for its decoded extent on the warp's transaction barrier (lines
+     * at or beyond nzl were never written by the entropy kernel and are zero by definition), clear the rest of
+     * the rows and the tails meanwhile, wait, plain MS stereo in place.  Rows keep
      * the HBM line order; short blocks are de-interleaved when the IMDCT jobs read them.  No block-wide barrier
      * until the rows are complete. ---- */
     constexpr int kW = kThreads/32;
@@ -445,20 +446,6 @@ k_l3_transform(TransformArgs a, const uint16_t *__restrict__ reorder_inv, const 
         mbar_init(bar, (uint32_t)__popc(has_mask));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-#pragma unroll
-    for (int j = 0; j < kU; j++)
-    {
-        const int u = warp + kW*j;
-        if (u < n_units)
-        {
-            float4 *zx = reinterpret_cast<float4 *>(S.x + u*nch*kXSlot);
-            for (int k = lane; k < nch*(kXSlot/4); k += 32) zx[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-            float4 *zt = reinterpret_cast<float4 *>(S.t + u*nch*288);
-            for (int k = lane; k < nch*72; k += 32) zt[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-    }
-    /* the bulk copies (async proxy) land on top of the cleared rows */
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncwarp();
     SlotMeta m;
     m.gc = -1; m.nzl = 0; m.block_type = 0; m.n_long = 0; m.map = -1; m.ms = 0; m.act = 0;
@@ -479,6 +466,25 @@ k_l3_transform(TransformArgs a, const uint16_t *__restrict__ reorder_inv, const 
             bulk_g2s(smem_addr(S.x + my_slot*kXSlot), a.xr + (size_t)m.gc*576, bytes, bar);
         } else
             asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
+    }
+    /* while the copies are in flight: clear what the IMDCT jobs can read beyond the copied extent (own lines and
+     * the eight the antialias butterflies take from the next subband) and the tails of the warp's rows */
+    {
+        const int my_from = has && m.gc >= 0 ? (m.nzl + 3) >> 2 : 0;
+        const int my_to = has ? (min(576, (m.act + 1)*18) + 3) >> 2 : 0;
+        /* four groups of eight lanes, group g on the row of lane g (a quarter-warp per 16-byte store phase) */
+        const int g = lane >> 3, gl = lane & 7;
+        const int from = __shfl_sync(0xffffffffu, my_from, g), to = __shfl_sync(0xffffffffu, my_to, g);
+        const int slot = __shfl_sync(0xffffffffu, my_slot, g);
+        if ((has_mask >> g) & 1)
+        {
+            float4 *zx = reinterpret_cast<float4 *>(S.x + slot*kXSlot);
+            for (int k = from + gl; k < to; k += 8) zx[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 *zt = reinterpret_cast<float4 *>(S.t + slot*288);
+#pragma unroll
+            for (int k = 0; k < 9; k++) zt[gl + 8*k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        __syncwarp();
     }
     MP3B_STAMP();
     if (has_mask) mbar_wait(bar, 0);
