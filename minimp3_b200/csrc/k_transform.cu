@@ -12,13 +12,18 @@
  *     tail(g)       depends on spectrum(g)                                 (9 values per subband)
  *     subband(g)    depends on spectrum(g) and tail(g-1)
  *     pcm(g)        depends on subband(g) and the last 15 time slots of subband(g-1)
- * Phases (256 threads, all data in shared memory):
- *   1 load spectra (coalesced; short-block reorder folded into the store index)   [XS]
- *   2 antialias butterflies
- *   3 IMDCT: one thread per (granule-channel, subband): a) tail + own half, b) overlap with tail(g-1)  [TS, YS]
- *   4 32-point DCT-II: one thread per (channel, time slot), in place                [YS]
- *   5 window FIR: one thread per (granule, output phase j), 16 taps from registers, packed PCM store
- * Bounded by the FP32 pipe (about 60 flop per output sample) long before HBM (4 B in + 2 B out per sample).
+ * k_l3_tile_meta (one warp per tile) first turns descriptors + decoded extents into a 256-byte tile record and the
+ * list of IMDCT jobs that are not identically zero, so the transform CTA starts from one round trip.
+ * Phases of k_l3_transform (256 threads, all data in shared memory):
+ *   0+1 per warp, no block barrier: slot records -> one TMA bulk copy per row (decoded extent only) on the
+ *       warp's mbarrier; rows cleared beyond the extent while the copies fly; plain MS stereo in place   [XS]
+ *   2+3a antialias + IMDCT per listed (slot, subband) job: tail to shared memory, own half in registers  [TS]
+ *   3b  overlap with tail(g-1), frequency inversion, write Y[time][subband]                              [YS]
+ *   4   32-point DCT-II: one thread per (channel, time slot), in place; half-size transforms of the Lee
+ *       recursion paired in packed FP32 (FFMA2)                                                          [YS]
+ *   5   window FIR: one thread per (granule, output phase j), taps and history as FP32 pairs (FFMA2),
+ *       packed PCM store
+ * Bounded by the issue / FP32 pipes long before HBM (4 B in + 2 B out per sample).
  */
 #include <cuda_runtime.h>
 #include <math.h>
