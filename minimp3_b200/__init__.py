@@ -106,7 +106,7 @@ def load():
     L.mp3dec_f32_to_s16.restype = None
     L.mp3dec_detect_buf.argtypes = [vp, C.c_size_t]
     for fn in (L.mp3dec_load_buf, L.mp3dec_load_buf_f32):
-        fn.argtypes = [C.POINTER(Mp3Dec), vp, C.c_size_t, C.POINTER(FileInfo), vp, vp]
+        fn.argtypes = [C.POINTER(Mp3Dec), vp, C.c_size_t, C.POINTER(FileInfo), vp, vp]   # progress_cb: PROGRESS_CB or None
         fn.restype = C.c_int
     L.mp3dec_decode_batch_cuda.argtypes = [C.POINTER(BatchStream), C.c_int, C.POINTER(FileInfo), C.POINTER(C.c_int),
                                            C.POINTER(BatchOpts)]
@@ -305,14 +305,21 @@ def mp3dec_decode_batch_cuda(streams, **kw):
     return b.results(copy=True)
 
 
-def mp3dec_load_buf(data, float_output=False):
-    """mp3dec_load_buf through the C entry point; returns (ret, pcm, info dict)."""
+PROGRESS_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_size_t, C.c_uint64, C.POINTER(FrameInfo))
+
+
+def mp3dec_load_buf(data, float_output=False, progress=None):
+    """mp3dec_load_buf through the C entry point; returns (ret, pcm, info dict).
+
+    ``progress(file_size, offset, frame_info) -> int`` mirrors MP3D_PROGRESS_CB (minimp3_ex.h:52): called once per
+    decoded frame, a non-zero return stops the decode and becomes ``ret``."""
     L = load()
     dec = Mp3Dec()
     fi = FileInfo()
     buf = _as_u8(data)
     fn = L.mp3dec_load_buf_f32 if float_output else L.mp3dec_load_buf
-    ret = fn(C.byref(dec), buf.ctypes.data, len(data), C.byref(fi), None, None)
+    cb = PROGRESS_CB(lambda ud, size, off, info: int(progress(size, off, info.contents))) if progress else None
+    ret = fn(C.byref(dec), buf.ctypes.data, len(data), C.byref(fi), cb, None)
     ct = C.c_float if float_output else C.c_int16
     if fi.buffer and fi.samples:
         pcm = np.ctypeslib.as_array(C.cast(fi.buffer, C.POINTER(ct)), shape=(fi.samples,)).copy()

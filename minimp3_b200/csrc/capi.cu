@@ -784,11 +784,15 @@ void mp3dec_init(mp3dec_t *dec) { dec->header[0] = 0; }   /* minimp3.h:1708-1711
 
 int mp3dec_detect_buf(const uint8_t *buf, size_t buf_size) { return detect_buf(buf, buf_size); }
 
+extern "C" __attribute__((visibility("hidden"))) int mp3dec_load_buf_progress(mp3dec_t *dec, const uint8_t *buf, size_t buf_size, mp3dec_file_info_t *info,
+                                        MP3D_PROGRESS_CB progress_cb, void *user_data, int float_output);
+
 static int load_buf_impl(mp3dec_t *dec, const uint8_t *buf, size_t buf_size, mp3dec_file_info_t *info,
                          MP3D_PROGRESS_CB progress_cb, void *user_data, int float_output)
 {
     if (!dec || !buf || !info || (size_t)-1 == buf_size) return MP3D_E_PARAM;
-    (void)progress_cb; (void)user_data;
+    /* a progress callback wants the frames one by one and may cancel: frame-by-frame flavour (csrc/ex_api.cpp) */
+    if (progress_cb) return mp3dec_load_buf_progress(dec, buf, buf_size, info, progress_cb, user_data, float_output);
     memset(info, 0, sizeof(*info));
     mp3dec_init(dec);
     mp3dec_batch_stream_t s = { buf, buf_size };

@@ -372,6 +372,109 @@ int ex_open_owned(ExT<S> *dec, uint8_t *p, size_t n, int flags)
     return 0;
 }
 
+/* mp3dec_load_buf with a progress callback (minimp3_ex.h:313-522 restated): the callback sees every decoded
+ * frame in order and may cancel, so this flavour walks the stream through the single-frame GPU path instead of the
+ * one-shot batch. */
+template <class S>
+int load_buf_frames(mp3dec_t *dec, const uint8_t *buf, size_t buf_size, mp3dec_file_info_t *info,
+                    MP3D_PROGRESS_CB progress_cb, void *user_data)
+{
+    const size_t orig_size = buf_size;
+    memset(info, 0, sizeof(*info));
+    skip_id3(&buf, &buf_size);
+    if (!buf_size) return 0;
+    mp3dec_init(dec);
+    mp3dec_frame_info_t fi;
+    memset(&fi, 0, sizeof(fi));
+    uint64_t detected_samples = 0;
+    size_t to_skip = 0;
+    int frame_samples = 0;
+    for (;;)
+    {   /* first frame: stream parameters and the optional Xing/Info tag */
+        int free_format_bytes = 0, frame_size = 0;
+        const int i = find_frame(buf, (int)std::min(buf_size, (size_t)INT_MAX), &free_format_bytes, &frame_size);
+        buf += i;
+        buf_size -= i;
+        if (i && !frame_size) continue;
+        if (!frame_size) return 0;
+        fill_info(&fi, buf, frame_size);
+        frame_samples = (int)hdr_frame_samples(buf)*fi.channels;
+        if (3 == fi.layer)
+        {
+            uint32_t frames;
+            int delay, padding;
+            const int ret = check_vbrtag(buf, frame_size, &frames, &delay, &padding);
+            if (ret > 0)
+            {
+                padding *= fi.channels;
+                to_skip = (size_t)delay*fi.channels;
+                detected_samples = (uint64_t)frame_samples*frames;
+                if (detected_samples >= to_skip) detected_samples -= to_skip;
+                if (padding > 0 && detected_samples >= (uint64_t)padding) detected_samples -= padding;
+                if (!detected_samples) return 0;
+            }
+            if (ret)
+            {
+                buf += frame_size;
+                buf_size -= frame_size;
+            }
+        }
+        break;
+    }
+    size_t allocated = MINIMP3_MAX_SAMPLES_PER_FRAME*sizeof(S);
+    if (detected_samples) allocated += (size_t)detected_samples*sizeof(S);
+    else allocated += (buf_size/fi.frame_bytes)*(size_t)frame_samples*sizeof(S);
+    S *out = (S *)malloc(allocated);
+    if (!out) return MP3D_E_MEMORY;
+    info->channels = fi.channels;
+    info->hz = fi.hz;
+    info->layer = fi.layer;
+    size_t n_samples = 0, avg_kbps = 0, frames = 0;
+    int ret = 0;
+    do
+    {
+        if (allocated - n_samples*sizeof(S) < MINIMP3_MAX_SAMPLES_PER_FRAME*sizeof(S))
+        {
+            allocated *= 2;
+            S *grown = (S *)realloc(out, allocated);
+            if (!grown) { free(out); return MP3D_E_MEMORY; }
+            out = grown;
+        }
+        size_t samples = (size_t)decode_frame(dec, buf, (int)std::min(buf_size, (size_t)INT_MAX), out + n_samples, &fi);
+        buf += fi.frame_bytes;
+        buf_size -= fi.frame_bytes;
+        if (samples)
+        {
+            if (info->hz != fi.hz || info->layer != fi.layer) { ret = MP3D_E_DECODE; break; }
+            if (info->channels && info->channels != fi.channels) { ret = MP3D_E_DECODE; break; }
+            samples *= fi.channels;
+            if (to_skip)
+            {
+                const size_t skip = std::min(samples, to_skip);
+                to_skip -= skip;
+                samples -= skip;
+                memmove(out, out + skip, samples*sizeof(S));
+            }
+            n_samples += samples;
+            avg_kbps += fi.bitrate_kbps;
+            frames++;
+            ret = progress_cb(user_data, orig_size, orig_size - buf_size, &fi);
+            if (ret) break;
+        }
+    } while (fi.frame_bytes);
+    if (detected_samples && n_samples > detected_samples) n_samples = (size_t)detected_samples;
+    if (allocated != n_samples*sizeof(S))
+    {
+        S *fit = (S *)realloc(out, n_samples*sizeof(S));
+        if (!fit && n_samples) { free(out); return MP3D_E_MEMORY; }
+        out = fit;
+    }
+    info->buffer = (mp3d_sample_t *)out;
+    info->samples = n_samples;
+    if (frames) info->avg_bitrate_kbps = (int)(avg_kbps/frames);
+    return ret;
+}
+
 }  // namespace
 
 extern "C" {
@@ -422,6 +525,13 @@ int mp3dec_detect_cb(mp3dec_io_t *io, uint8_t *buf, size_t buf_size)
     r = mp3dec_detect_buf(p, n);
     free(p);
     return r;
+}
+
+__attribute__((visibility("hidden"))) int mp3dec_load_buf_progress(mp3dec_t *dec, const uint8_t *buf, size_t buf_size, mp3dec_file_info_t *info,
+                                        MP3D_PROGRESS_CB progress_cb, void *user_data, int float_output)
+{
+    return float_output ? load_buf_frames<float>(dec, buf, buf_size, info, progress_cb, user_data)
+                        : load_buf_frames<int16_t>(dec, buf, buf_size, info, progress_cb, user_data);
 }
 
 #define LOAD_CB_IMPL(NAME, LOADBUF)                                                                                  \

@@ -109,3 +109,26 @@ def test_stdio_flavours(m, ref):
     assert ex.samples == len(want)
     L.mp3dec_ex_close(C.byref(ex))
     assert L.mp3dec_ex_open(C.byref(ex), b"/nonexistent/file.mp3", SEEK_TO_SAMPLE) == m.MP3D_E_IOERROR
+
+
+@pytest.mark.parametrize("name", ["l3-compl", "l3-nonstandard-sin1k0db_lame_vbrtag", "l3-nonstandard-id3v2", "l1-fl1",
+                                  "l2-fl10"])
+def test_load_buf_progress_callback(name, m, ref):
+    """MP3D_PROGRESS_CB (minimp3_ex.h:52, 504-509): one call per decoded frame with a growing offset; the result is
+    the one of the callback-free call; a non-zero return cancels and is handed back."""
+    data = load_vector(name)
+    rret, rpcm, rinfo = ref.load_buf(data)
+    calls = []
+    ret, pcm, info = m.mp3dec_load_buf(data, progress=lambda size, off, fi: calls.append((size, off, fi.frame_bytes, fi.hz)) or 0)
+    assert ret == rret and info == rinfo and len(pcm) == len(rpcm)
+    assert np.abs(pcm.astype(np.int32) - rpcm.astype(np.int32)).max() <= 1
+    assert calls and all(c[0] == len(data) for c in calls) and calls[-1][1] <= len(data)
+    assert all(b[1] > a[1] for a, b in zip(calls, calls[1:])) and all(c[3] == rinfo["hz"] for c in calls)
+    ret0, pcm0, _ = m.mp3dec_load_buf(data)                     # the one-shot batch flavour gives the same stream
+    assert ret0 == ret and len(pcm0) == len(pcm) and np.abs(pcm0.astype(np.int32) - pcm.astype(np.int32)).max() <= 1
+    if len(calls) <= 3:
+        return                                                  # one-frame vectors: nothing left to cancel
+    seen = []
+    ret, part, _ = m.mp3dec_load_buf(data, progress=lambda size, off, fi: seen.append(off) or (5 if len(seen) == 3 else 0))
+    assert ret == 5 and len(seen) == 3 and 0 < len(part) < len(pcm)
+    assert np.array_equal(part, pcm[:len(part)])
