@@ -259,6 +259,22 @@ def main():
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = n_out*world/(float(te.item())*1e-3)
 
+    # ---- same call, PCM left in HBM (SURVEY 8d timing scope ii: host parse + H2D + kernels, no D2H) ------
+    dev_ms = []
+    batch_dev = m._Batch(streams, device=local_rank, raw_frames=False, output=m.OUT_DEVICE, host_threads=host_threads)
+    for i in range(args.e2e_steps + 2):
+        barrier()
+        t0 = time.perf_counter()
+        n_dev = batch_dev.call()
+        t1 = time.perf_counter()
+        if i >= 2:
+            dev_ms.append((t1 - t0)*1e3)
+    assert n_dev == samples_per_step
+    td = torch.tensor([statistics.median(dev_ms)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(td, op=dist.ReduceOp.MAX)
+    dev_value = n_dev*world/(float(td.item())*1e-3)
+
     if rank == 0:
         peak, peak_kind = measured_peaks()
         dom = max(("entropy", "transform"), key=lambda k: kern.get(k, 0.0))
@@ -282,7 +298,9 @@ def main():
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 2*n_out,
                         "ms_per_step": float(te.item()), "host_parse_ms": parse_ms, "h2d_ms": h2d_ms,
                         "host_threads_per_rank": host_threads,
-                        "api": "mp3dec_decode_batch_cuda(host buffers) -> pinned host PCM, chunk-pipelined inside the call"},
+                        "api": "mp3dec_decode_batch_cuda(host buffers) -> pinned host PCM, chunk-pipelined inside the call",
+                        "pcm_left_on_device": {"value": dev_value, "unit": UNIT, "ms_per_step": float(td.item()),
+                                               "note": "same call with MP3D_BATCH_OUT_DEVICE: host parse + H2D + kernels, no D2H"}},
                 "gpu_launches": int(st["kernels_per_run"])*args.steps,
                 "kernels_ms": kern,
                 "roofline": {"bound": "hbm", "kernel": "k_l3_" + dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
