@@ -1,6 +1,6 @@
 /*
  * oracle/mp3_oracle.c -- TEST INFRASTRUCTURE ONLY: a plain-C, single-threaded CPU restatement of the
- * Layer III decode path of lieff/minimp3, used as the checker for the CUDA kernels.  Never linked into,
+ * decode path of lieff/minimp3 (Layer III, and Layer I/II from the ISO allocation tables), used as the checker for the CUDA kernels.  Never linked into,
  * imported by or executed from the product (minimp3_b200/).
  *
  * Pin status: PINNED.  tests/test_oracle.py checks this file against (a) the golden manifest produced by the
@@ -544,7 +544,182 @@ static int16_t orc_round_simd(float s)
     return (int16_t)lrintf(s);
 }
 
-/* ------------------------------------------------------------------ frame loop (minimp3.h:1713-1806, L3 only) */
+
+/* ------------------------------------------------------------------ Layer I / II (minimp3.h:316-482, 1783-1802)
+ * Restated from the ISO tables: per subband a bit-allocation field width and the list of quantiser classes it
+ * selects (11172-3 tables B.2a-d, 13818-3 table B.1); a class is a number of levels: 2^k - 1 (k-bit codes, one
+ * per sample) or 3 / 5 / 9 (three samples packed into one 5 / 7 / 10-bit code). */
+typedef struct { int levels, bits, grouped; } orc_qclass;
+
+static orc_qclass orc_l12_class(int levels)
+{
+    orc_qclass c;
+    c.levels = levels; c.grouped = 0; c.bits = 0;
+    if (levels == 3) { c.bits = 5; c.grouped = 1; }
+    else if (levels == 5) { c.bits = 7; c.grouped = 1; }
+    else if (levels == 9) { c.bits = 10; c.grouped = 1; }
+    else if (levels) { int k = 0; while ((1 << k) - 1 < levels) k++; c.bits = k; }
+    return c;
+}
+
+/* levels per allocation code; 0 = nothing transmitted */
+static const int ORC_L2_A0[16] = { 0, 3, 7, 15, 31, 63, 127, 255, 511, 1023, 2047, 4095, 8191, 16383, 32767, 65535 };   /* B.2a sb 0-2  */
+static const int ORC_L2_A1[16] = { 0, 3, 5, 7, 9, 15, 31, 63, 127, 255, 511, 1023, 2047, 4095, 8191, 65535 };            /* B.2a sb 3-10 */
+static const int ORC_L2_A2[8]  = { 0, 3, 5, 7, 9, 15, 31, 65535 };                                                       /* B.2a sb 11-22 */
+static const int ORC_L2_A3[4]  = { 0, 3, 5, 65535 };                                                                     /* B.2a sb 23-  */
+static const int ORC_L2_C0[16] = { 0, 3, 5, 9, 15, 31, 63, 127, 255, 511, 1023, 2047, 4095, 8191, 16383, 32767 };        /* B.2c sb 0-1, its first 8 / 4 entries for the 3- / 2-bit fields */
+static const int ORC_L2_M0[16] = { 0, 3, 5, 7, 9, 15, 31, 63, 127, 255, 511, 1023, 2047, 4095, 8191, 16383 };            /* 13818-3 B.1 sb 0-3 */
+static const int ORC_L1[16]    = { 0, 3, 7, 15, 31, 63, 127, 255, 511, 1023, 2047, 4095, 8191, 16383, 32767, 65535 };    /* Layer I: code n -> n+1 bits */
+
+typedef struct
+{
+    int nbands, stereo_bands;            /* bands with allocation; bands coded separately per channel */
+    int nbal[32];                        /* width of the allocation field */
+    const int *levels[32];               /* allocation code -> levels */
+} orc_l12_layout;
+
+/* which table applies (minimp3.h:317-360) */
+static void orc_l12_pick_layout(const uint8_t *hdr, orc_l12_layout *L)
+{
+    int mode = (hdr[3] >> 6) & 3, sb;
+    int stereo_bands = mode == 3 ? 0 : mode == 1 ? (((hdr[3] >> 4) & 3) << 2) + 4 : 32;
+    if (orc_layer(hdr) == 1)
+    {
+        L->nbands = 32;
+        for (sb = 0; sb < 32; sb++) { L->nbal[sb] = 4; L->levels[sb] = ORC_L1; }
+    } else if (!orc_mpeg1(hdr))
+    {
+        L->nbands = 30;
+        for (sb = 0; sb < 30; sb++)
+        {
+            L->nbal[sb] = sb < 4 ? 4 : sb < 11 ? 3 : 2;
+            L->levels[sb] = sb < 4 ? ORC_L2_M0 : ORC_L2_C0;
+        }
+    } else
+    {
+        unsigned kbps = orc_kbps(hdr) >> (mode != 3);
+        int sr = (hdr[2] >> 2) & 3;
+        if (!kbps) kbps = 192;                       /* free format */
+        if (kbps < 56)
+        {
+            L->nbands = sr == 2 ? 12 : 8;            /* B.2d / B.2c */
+            for (sb = 0; sb < L->nbands; sb++) { L->nbal[sb] = sb < 2 ? 4 : 3; L->levels[sb] = ORC_L2_C0; }
+        } else
+        {
+            L->nbands = (kbps >= 96 && sr != 1) ? 30 : 27;   /* B.2b / B.2a */
+            for (sb = 0; sb < L->nbands; sb++)
+            {
+                L->nbal[sb] = sb < 11 ? 4 : sb < 23 ? 3 : 2;
+                L->levels[sb] = sb < 3 ? ORC_L2_A0 : sb < 11 ? ORC_L2_A1 : sb < 23 ? ORC_L2_A2 : ORC_L2_A3;
+            }
+        }
+    }
+    L->stereo_bands = stereo_bands < L->nbands ? stereo_bands : L->nbands;
+}
+
+/* the reference's dequantiser constants (minimp3.h:364-369): 2^-20 * 2^(-r/3) / levels, r = index mod 3, in float */
+static float orc_l12_scale(int levels, int index)
+{
+    static const float third[3] = { 9.53674316e-07f, 7.56931807e-07f, 6.00777173e-07f };
+    return third[index % 3]/(float)levels*(float)(1 << 21 >> index/3);
+}
+
+/* One Layer I / II frame: bit allocation, scalefactor selection, scalefactors, samples; then each block of 12 time
+ * slots goes through the polyphase synthesis.  Returns channel-inclusive samples written, or -1 when the frame
+ * reads past its end (the reference drops it and resyncs, minimp3.h:1796-1800). */
+static long orc_l12_frame(const uint8_t *hdr, orc_bs *bs, orc_state *st, int nch, long total, int16_t *pcm16, float *pcmf, long pcm_cap)
+{
+    orc_l12_layout L;
+    orc_qclass cls[32][2];
+    float sf[32][2][3];
+    int scfsi[32][2], sb, ch, part, layer1 = orc_layer(hdr) == 1;
+    int slots_per_read = layer1 ? 1 : 3, n_parts = layer1 ? 1 : 3, written = 0;
+    static float sample[3][2][32][12];      /* [part][ch][subband][slot] */
+    orc_l12_pick_layout(hdr, &L);
+    memset(cls, 0, sizeof(cls));
+    for (sb = 0; sb < L.nbands; sb++)
+    {
+        int code = (int)orc_get_bits(bs, L.nbal[sb]), code1 = code;
+        if (sb < L.stereo_bands) code1 = (int)orc_get_bits(bs, L.nbal[sb]);
+        cls[sb][0] = orc_l12_class(L.levels[sb][code]);
+        cls[sb][1] = orc_l12_class(L.stereo_bands ? L.levels[sb][code1] : 0);      /* joint bands: channel 1 shares the allocation */
+        if (layer1)
+        {   /* Layer I never packs samples: 3 levels are plain 2-bit codes */
+            cls[sb][0].grouped = cls[sb][1].grouped = 0;
+            if (cls[sb][0].levels == 3) cls[sb][0].bits = 2;
+            if (cls[sb][1].levels == 3) cls[sb][1].bits = 2;
+        }
+    }
+    for (sb = 0; sb < L.nbands; sb++)
+        for (ch = 0; ch < 2; ch++)
+            scfsi[sb][ch] = cls[sb][ch].levels ? (layer1 ? 2 : (int)orc_get_bits(bs, 2)) : -1;
+    for (sb = 0; sb < L.nbands; sb++)
+        for (ch = 0; ch < 2; ch++)
+        {
+            /* scfsi: 0 = three scalefactors, 1 = first shared by parts 0,1 + one more, 2 = one for all, 3 = one + one shared by parts 1,2 */
+            static const int sent[4][3] = { { 1, 1, 1 }, { 1, 0, 1 }, { 1, 0, 0 }, { 1, 1, 0 } };
+            float s = 0;
+            for (part = 0; part < 3; part++)
+            {
+                if (scfsi[sb][ch] >= 0 && sent[scfsi[sb][ch]][part])
+                    s = orc_l12_scale(cls[sb][ch].levels, (int)orc_get_bits(bs, 6));
+                sf[sb][ch][part] = s;
+            }
+        }
+    /* samples: Layer I 12 reads of one sample, Layer II 3 parts x 4 reads of three samples; subbands in the
+     * joint-stereo region are sent once and copied to channel 1 */
+    memset(sample, 0, sizeof(sample));
+    for (part = 0; part < n_parts; part++)
+    {
+        int rd, k, n_reads = layer1 ? 12 : 4;
+        for (rd = 0; rd < n_reads; rd++)
+            for (sb = 0; sb < L.nbands; sb++)
+                for (ch = 0; ch < 2; ch++)
+                {
+                    orc_qclass c = cls[sb][ch];
+                    if (!c.levels || (ch == 1 && sb >= L.stereo_bands)) continue;
+                    if (c.grouped)
+                    {
+                        unsigned code = orc_get_bits(bs, c.bits);
+                        for (k = 0; k < slots_per_read; k++, code /= (unsigned)c.levels)
+                            sample[part][ch][sb][rd*slots_per_read + k] = (float)((int)(code % (unsigned)c.levels) - c.levels/2);
+                    } else
+                        for (k = 0; k < slots_per_read; k++)
+                            sample[part][ch][sb][rd*slots_per_read + k] = (float)((int)orc_get_bits(bs, c.bits) - ((1 << (c.bits - 1)) - 1));
+                }
+        if (bs->pos > bs->limit) return -1;
+    }
+    for (part = 0; part < n_parts; part++)
+    {
+        int slot;
+        for (ch = 0; ch < nch; ch++)
+            for (slot = 0; slot < 12; slot++)
+            {
+                double S[32], out[32];
+                int j;
+                for (sb = 0; sb < 32; sb++)
+                {
+                    const int src_ch = (ch == 1 && sb >= L.stereo_bands) ? 0 : ch;
+                    /* Layer I keeps its single scalefactor in every part (minimp3.h:371-383) */
+                    S[sb] = sb < L.nbands ? (double)(sample[part][src_ch][sb][slot]*sf[sb][ch][layer1 ? 2 : part]) : 0.0;
+                }
+                orc_synth_slot(st->hist[ch], S, out);
+                for (j = 0; j < 32; j++)
+                {
+                    long idx = total + written + (long)(slot*32 + j)*nch + ch;
+                    if (idx < pcm_cap)
+                    {
+                        if (pcm16) pcm16[idx] = (j == 0 || j == 16) ? orc_round_scalar((float)out[j]) : orc_round_simd((float)out[j]);
+                        if (pcmf) pcmf[idx] = (float)out[j]*(1.0f/32768.0f);
+                    }
+                }
+            }
+        written += 384*nch;
+    }
+    return written;
+}
+
+/* ------------------------------------------------------------------ frame loop (minimp3.h:1713-1806) */
 long orc_decode_stream(const uint8_t *buf, long size, int16_t *pcm16, float *pcmf, long pcm_cap, orc_taps *taps, long *n_gc_out)
 {
     uint8_t header[4] = { 0, 0, 0, 0 };
@@ -579,9 +754,15 @@ long orc_decode_stream(const uint8_t *buf, long size, int16_t *pcm16, float *pcm
         frame_bytes_out = i + frame_size;
         pos += frame_bytes_out;
         nch = orc_mono(hdr) ? 1 : 2;
-        if (orc_layer(hdr) != 3) { free(maindata); free(st); return -6; }
         bs.buf = hdr + 4; bs.pos = 0; bs.limit = (frame_size - 4)*8;
         if (!(hdr[1] & 1)) orc_get_bits(&bs, 16);
+        if (orc_layer(hdr) != 3)
+        {
+            long n = orc_l12_frame(hdr, &bs, st, nch, total, pcm16, pcmf, pcm_cap);
+            if (n < 0) header[0] = 0;      /* overrun: frame dropped, decoder resyncs from scratch */
+            else total += n;
+            continue;
+        }
         mdb = orc_side_info(&bs, gr, hdr);
         if (mdb < 0 || bs.pos > bs.limit) { header[0] = 0; continue; }
         /* reservoir (minimp3.h:1212-1236) */

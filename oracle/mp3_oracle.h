@@ -15,8 +15,8 @@ typedef struct
 #ifdef __cplusplus
 extern "C" {
 #endif
-/* Decodes every Layer III frame of a stream the way a mp3dec_init + mp3dec_decode_frame loop does.
- * Returns channel-inclusive samples (or -6 when a Layer I/II frame is met).  pcm16 / pcmf may be NULL. */
+/* Decodes every frame of a stream the way a mp3dec_init + mp3dec_decode_frame loop does.
+ * Returns channel-inclusive samples.  pcm16 / pcmf may be NULL. */
 long orc_decode_stream(const uint8_t *buf, long size, int16_t *pcm16, float *pcmf, long pcm_cap, orc_taps *taps,
                        long *n_gc_out);
 #ifdef __cplusplus

@@ -5,7 +5,7 @@ available -- its stage taps: integers and requantised lines bit-exact, PCM withi
 import numpy as np
 import pytest
 
-from conftest import L3_CONFORMANCE, load_iso_pcm, load_vector, psnr
+from conftest import L12_CONFORMANCE, L12_REGRESSION, L3_CONFORMANCE, load_iso_pcm, load_vector, psnr
 from oracle import port
 
 
@@ -46,5 +46,23 @@ def test_port_float_output(ref_f32):
     assert np.abs(o["pcm"] - want).max() <= 1e-5
 
 
-def test_port_refuses_layer12():
-    assert port.decode_stream(load_vector("l2-fl10"))["ret"] == -6
+@pytest.mark.parametrize("name", L12_CONFORMANCE)
+def test_port_layer12_against_golden_manifest_and_iso_pcm(name, manifest):
+    """Layer I / II restated from the ISO allocation tables: sample count of the unmodified reference, PSNR against
+    the ISO conformance PCM (minimp3_test.c:417-427)."""
+    o = port.decode_stream(load_vector(name))
+    m = manifest[name]
+    assert o["ret"] == 0 and len(o["pcm"]) == m["samples"]
+    md, ps = psnr(o["pcm"], load_iso_pcm(name))
+    assert ps >= 96.0 and md <= 1
+
+
+@pytest.mark.parametrize("name", L12_CONFORMANCE + L12_REGRESSION)
+def test_port_layer12_against_reference_pcm(name, ref):
+    """every Layer I / II vector incl. the malformed ILL* ones: same frames kept and dropped, PCM within +-1 LSB"""
+    data = load_vector(name)
+    want, _ = ref.decode_frames(data)
+    o = port.decode_stream(data)
+    assert o["ret"] == 0 and len(o["pcm"]) == len(want)
+    if len(want):
+        assert np.abs(o["pcm"].astype(np.int32) - want.astype(np.int32)).max() <= 1
