@@ -131,17 +131,15 @@ int find_frame(const uint8_t *mp3, int mp3_bytes, int *free_format_bytes, int *p
 
 /* ---- bit reader (minimp3.h:248-262) ----------------------------------------------------------- */
 
-uint32_t BitReader::get(int n)
+uint32_t BitReader::get_slow(int start, int n) const
 {
-    const int start = pos;
-    pos += n;
-    if (pos > limit || n == 0) return 0;
-    /* gather the (at most 5) bytes that hold the field, then shift it out */
+    /* near the end of the frame: gather the (at most 5) bytes that hold the field, then shift it out */
+    const int end = start + n;
     const uint8_t *p = buf + (start >> 3);
-    const int last = (pos - 1) >> 3, first = start >> 3;
+    const int last = (end - 1) >> 3, first = start >> 3;
     uint64_t acc = 0;
     for (int b = first; b <= last; b++) acc = (acc << 8) | *p++;
-    const int tail = 7 - ((pos - 1) & 7);
+    const int tail = 7 - ((end - 1) & 7);
     return (uint32_t)((acc >> tail) & ((n >= 32) ? 0xFFFFFFFFull : ((1ull << n) - 1)));
 }
 
@@ -234,19 +232,30 @@ int read_side_info(BitReader *bs, GranuleSide *gr, const uint8_t *hdr)
     return main_data_begin;
 }
 
-void fill_gc_desc(GcDesc *d, const GranuleSide &g, const uint8_t *hdr, int ch, int nch, int igr, uint64_t bit_off)
+/* the header-derived part of a GcDesc, the same for every granule-channel of a frame */
+struct HdrBits
 {
-    memset(d, 0, sizeof(*d));
+    uint8_t flags0, flags1, sr_idx;
+    HdrBits(const uint8_t *hdr, int nch)
+    {
+        const bool ms = (hdr[3] & 0xE0) == 0x60;        /* joint stereo + MS bit (HDR_IS_MS_STEREO) */
+        const bool is = (hdr[3] & 0x10) != 0;           /* HDR_TEST_I_STEREO: bit is tested whatever the mode */
+        flags0 = (uint8_t)((ms ? GCF_MS_STEREO : 0) | (is ? GCF_I_STEREO : 0));
+        flags1 = (uint8_t)((hdr_is_mpeg1(hdr) ? GCF1_MPEG1 : 0) | (nch == 2 ? GCF1_STEREO : 0) |
+                           ((ms && !is && nch == 2) ? GCF1_MS_PLAIN : 0) | ((hdr[3] & 0x20) ? GCF1_MS_TEST : 0));
+        sr_idx = (uint8_t)sample_rate_class(hdr);
+    }
+};
+
+static inline void fill_gc_desc_hb(GcDesc *d, const GranuleSide &g, const HdrBits &hb, int ch, int igr, uint64_t bit_off)
+{
     d->bit_off = bit_off;
     d->part_23_length = g.part_23_length;
     d->big_values = g.big_values;
     d->scalefac_compress = g.scalefac_compress;
     d->global_gain = g.global_gain;
-    const bool ms = (hdr[3] & 0xE0) == 0x60;        /* joint stereo + MS bit (HDR_IS_MS_STEREO) */
-    const bool is = (hdr[3] & 0x10) != 0;           /* HDR_TEST_I_STEREO: bit is tested whatever the mode */
-    d->flags0 = (uint8_t)((g.block_type & 3) | (g.mixed_block_flag ? GCF_MIXED : 0) | (g.preflag ? GCF_PREFLAG : 0) |
-                          (g.scalefac_scale ? GCF_SCALEFAC_SCALE : 0) | (g.count1_table ? GCF_COUNT1_TABLE : 0) |
-                          (ms ? GCF_MS_STEREO : 0) | (is ? GCF_I_STEREO : 0));
+    d->flags0 = (uint8_t)(hb.flags0 | (g.block_type & 3) | (g.mixed_block_flag ? GCF_MIXED : 0) | (g.preflag ? GCF_PREFLAG : 0) |
+                          (g.scalefac_scale ? GCF_SCALEFAC_SCALE : 0) | (g.count1_table ? GCF_COUNT1_TABLE : 0));
     for (int i = 0; i < 3; i++)
     {
         d->table_select[i] = g.table_select[i];
@@ -256,10 +265,14 @@ void fill_gc_desc(GcDesc *d, const GranuleSide &g, const uint8_t *hdr, int ch, i
     d->scfsi = g.scfsi;
     d->n_long_sfb = g.n_long_sfb;
     d->n_short_sfb = g.n_short_sfb;
-    d->sr_idx = (uint8_t)sample_rate_class(hdr);
-    d->flags1 = (uint8_t)((hdr_is_mpeg1(hdr) ? GCF1_MPEG1 : 0) | (ch ? GCF1_CH : 0) | (nch == 2 ? GCF1_STEREO : 0) |
-                          (igr ? GCF1_GR1 : 0) | ((ms && !is && nch == 2) ? GCF1_MS_PLAIN : 0) |
-                          ((hdr[3] & 0x20) ? GCF1_MS_TEST : 0));
+    d->sr_idx = hb.sr_idx;
+    d->flags1 = (uint8_t)(hb.flags1 | (ch ? GCF1_CH : 0) | (igr ? GCF1_GR1 : 0));
+    d->pad[0] = d->pad[1] = 0;
+}
+
+void fill_gc_desc(GcDesc *d, const GranuleSide &g, const uint8_t *hdr, int ch, int nch, int igr, uint64_t bit_off)
+{
+    fill_gc_desc_hb(d, g, HdrBits(hdr, nch), ch, igr, bit_off);
 }
 
 /* ---- one mp3dec_decode_frame worth of parsing (minimp3.h:1713-1806) ---------------------------- */
@@ -576,6 +589,12 @@ void walk_stream(const uint8_t *buf, size_t size, uint8_t *md_dst, uint64_t md_b
         plan->layer = first.layer;
     }
 
+    {
+        /* one allocation per array for the common constant-bit-rate case instead of log2(n) regrowths */
+        const size_t guess = size/(size_t)std::max(first.frame_bytes, 96) + 8;
+        plan->gcs.reserve(guess*4);
+        plan->granules.reserve(guess*3);
+    }
     SyncState st;
     FrameParse fp;
     memset(&fp.info, 0, sizeof(fp.info));
@@ -609,6 +628,7 @@ void walk_stream(const uint8_t *buf, size_t size, uint8_t *md_dst, uint64_t md_b
                 if (stop) break;
                 uint64_t bit = md_base_bits + start_bits;
                 const bool istereo = (fp.hdr[3] & 0x10) && fp.nch == 2;
+                const HdrBits hb(fp.hdr, fp.nch);
                 for (int igr = 0; igr < fp.n_gr; igr++)
                 {
                     if (fp.nch == 2 && (plan->gcs.size() & 1))
@@ -631,7 +651,7 @@ void walk_stream(const uint8_t *buf, size_t size, uint8_t *md_dst, uint64_t md_b
                     {
                         GcDesc d;
                         const GranuleSide &g = fp.side[igr*fp.nch + ch];
-                        fill_gc_desc(&d, g, fp.hdr, ch, fp.nch, igr, bit);
+                        fill_gc_desc_hb(&d, g, hb, ch, igr, bit);
                         bit += g.part_23_length;
                         plan->gcs.push_back(d);
                     }

@@ -46,7 +46,24 @@ struct BitReader
     const uint8_t *buf;
     int pos, limit;
     void init(const uint8_t *data, int bytes) { buf = data; pos = 0; limit = bytes*8; }
-    uint32_t get(int n);
+    uint32_t get_slow(int start, int n) const;
+    /* 1 <= n <= 32 bits, MSB first; 0 once the frame is exhausted (minimp3.h:248-262) */
+    inline uint32_t get(int n)
+    {
+        const int start = pos;
+        pos += n;
+        if (pos > limit || n == 0) return 0;
+        const int byte0 = start >> 3;
+        if (byte0 + 8 <= (limit >> 3))
+        {
+            /* one unaligned 8-byte load inside the frame: a field fits behind any start bit */
+            uint64_t w;
+            __builtin_memcpy(&w, buf + byte0, 8);
+            w = __builtin_bswap64(w);
+            return (uint32_t)((w << (start & 7)) >> (64 - n));
+        }
+        return get_slow(start, n);
+    }
 };
 
 /* One parsed granule-channel of side info. */
