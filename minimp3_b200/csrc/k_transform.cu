@@ -289,19 +289,23 @@ __device__ __forceinline__ void fir_phase(const float *ybase, const float *fir_t
     }
 }
 
-/* the 2-of-32 outputs the reference produces through mp3d_scale_pcm (truncate(x + .5) - (x < 0)) */
+/* the 2-of-32 outputs the reference produces through mp3d_scale_pcm (truncate(x + .5) - (x < 0)).  Warp i parked
+ * the values of granule i itself (its lanes 0 and 16), so the pass is warp-local: no block barrier. */
 template <int NCH, int SLOTS>
 __device__ __forceinline__ void special_round_pass(const float *special, void *pcm, uint64_t pcm_off, int n_gr, int tid)
 {
-    const int n = n_gr*2*SLOTS;
-    for (int k = tid; k < n; k += kThreads)
+    const int i = tid >> 5, lane = tid & 31;
+    if (i >= n_gr) return;
+    __syncwarp();
+    for (int k = lane; k < 2*SLOTS; k += 32)
     {
-        const int tt = k % SLOTS, ih = k/SLOTS, h = ih & 1, i = ih >> 1;
+        const int h = k >= SLOTS ? 1 : 0, tt = k - h*SLOTS;
+        const float *sp = special + ((i*2 + h)*SLOTS + tt)*NCH;
         int16_t *p = reinterpret_cast<int16_t *>(pcm) + pcm_off + (size_t)(i*SLOTS*32 + tt*32 + h*16)*NCH;
-        const int16_t l = pcm_round_scalar(special[k*NCH]);
+        const int16_t l = pcm_round_scalar(sp[0]);
         if (NCH == 2)
         {
-            const int16_t r = pcm_round_scalar(special[k*NCH + 1]);
+            const int16_t r = pcm_round_scalar(sp[1]);
             *reinterpret_cast<uint32_t *>(p) = (uint32_t)(uint16_t)l | ((uint32_t)(uint16_t)r << 16);
         } else
             *p = l;
@@ -619,14 +623,8 @@ k_l3_transform(TransformArgs a, const uint16_t *__restrict__ reorder_inv, const 
     __syncthreads();
     MP3B_STAMP();
 
-    /* the spectra are consumed: clear the time/subband matrix that takes their place (inactive subbands stay 0) */
-    {
-        float4 *z = reinterpret_cast<float4 *>(S.x);
-        for (int k = tid; k < (kYFloats + 3)/4; k += kThreads) z[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    __syncthreads();
-    MP3B_STAMP();
-
+    /* the spectra are consumed; the time/subband matrix Y takes their place.  Phase 3b writes only the subbands
+     * of its job list, phase 4 reads exactly those (everything else counts as zero without being cleared). */
     /* ---- phase 3b: overlap with the previous granule's tail, frequency inversion, write Y[time][subband] ---- */
 #pragma unroll
     for (int r = 0; r < kJobs3; r++)
@@ -682,9 +680,12 @@ k_l3_transform(TransformArgs a, const uint16_t *__restrict__ reorder_inv, const 
                 for (int k = 0; k < 32; k++) y[k] = a.state_in[576 + (ch*15 + row)*32 + k];
                 continue;
             }
+            /* subbands this row's granule-channel has jobs for: active in the granule or in the one before it */
+            const int slot = (row < 15 ? 1 : 2 + (((row - 15)*3641) >> 16))*nch + ch;
+            const int nj = max(S.meta[slot].act, S.meta[slot - nch].act);
             float v[32];
 #pragma unroll
-            for (int k = 0; k < 32; k++) v[k] = y[k];
+            for (int k = 0; k < 32; k++) v[k] = k < nj ? y[k] : 0.f;
             dct2_32_paired(v);
 #pragma unroll
             for (int k = 0; k < 32; k++) y[k] = v[k];
@@ -699,8 +700,6 @@ k_l3_transform(TransformArgs a, const uint16_t *__restrict__ reorder_inv, const 
     else fir_phase<FLOAT_OUT, 1, 18, kRows>(S.x, S.fir_taps, special, a.pcm, tile.pcm_off, n_gr, tid);
     if (!FLOAT_OUT)
     {
-        __syncthreads();
-    MP3B_STAMP();
         if (nch == 2) special_round_pass<2, 18>(special, a.pcm, tile.pcm_off, n_gr, tid);
         else special_round_pass<1, 18>(special, a.pcm, tile.pcm_off, n_gr, tid);
     }
@@ -784,7 +783,6 @@ k_l12_synth(Synth12Args a, const float *__restrict__ fir_coef)
     else fir_phase<FLOAT_OUT, 1, 12, kRows12>(y, fir_taps, special, a.pcm, tile.pcm_off, n_gr, tid);
     if (!FLOAT_OUT)
     {
-        __syncthreads();
         if (nch == 2) special_round_pass<2, 12>(special, a.pcm, tile.pcm_off, n_gr, tid);
         else special_round_pass<1, 12>(special, a.pcm, tile.pcm_off, n_gr, tid);
     }

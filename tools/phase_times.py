@@ -20,8 +20,8 @@ p.run()
 p.sync()
 clk = p.read_tap(7)
 p.close()
-names = ["p0 desc+zero+tma issue", "p1 tma wait", "p1 ms", "p1 barrier", "phase3a imdct core", "zero Y", "phase3b overlap",
-         "phase4 dct", "phase5 fir", "special round", "end"]
+names = ["p0 desc+zero+tma issue", "p1 tma wait", "p1 ms", "p1 barrier", "phase3a imdct core", "phase3b overlap",
+         "phase4 dct", "phase5 fir + special round", "end"]
 valid = clk[:, 0] > 0
 c = clk[valid]
 nst = int((c[0] > 0).sum())
