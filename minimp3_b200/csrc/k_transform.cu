@@ -243,17 +243,26 @@ __device__ __forceinline__ void fir_phase(const float *ybase, const float *fir_t
         unsigned long long P[16];
 #pragma unroll
         for (int h = 1; h < 15; h++) P[h] = pack_f32x2(ya[h*kYPitch], yb[(h - 1)*kYPitch]);
+        static_assert(SLOTS % 2 == 0, "two time slots per round");
 #pragma unroll
-        for (int tt = 0; tt < SLOTS; tt++)
+        for (int tt = 0; tt < SLOTS; tt += 2)
         {
-            const int row = 15 + tt;
-            P[row & 15] = pack_f32x2(ya[row*kYPitch], yb[(row - 1)*kYPitch]);
-            unsigned long long acc = 0ull;
+            /* two time slots per round: their FMA chains touch disjoint (even / odd) history slots and interleave */
+            const int r0 = 15 + tt, r1 = 16 + tt;
+            P[r0 & 15] = pack_f32x2(ya[r0*kYPitch], yb[(r0 - 1)*kYPitch]);
+            P[r1 & 15] = pack_f32x2(ya[r1*kYPitch], yb[(r1 - 1)*kYPitch]);
+            unsigned long long acc0 = 0ull, acc1 = 0ull;
 #pragma unroll
-            for (int m = 0; m < 8; m++) acc = fma_f32x2(c2[m], P[(row - 2*m) & 15], acc);
+            for (int m = 0; m < 8; m++)
+            {
+                acc0 = fma_f32x2(c2[m], P[(r0 - 2*m) & 15], acc0);
+                acc1 = fma_f32x2(c2[m], P[(r1 - 2*m) & 15], acc1);
+            }
             float lo, hi;
-            unpack_f32x2(acc, lo, hi);
+            unpack_f32x2(acc0, lo, hi);
             res[ch][tt] = lo + hi;
+            unpack_f32x2(acc1, lo, hi);
+            res[ch][tt + 1] = lo + hi;
         }
     }
     if (FLOAT_OUT)
