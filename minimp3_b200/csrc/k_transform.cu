@@ -369,13 +369,19 @@ k_l3_tile_meta(TransformArgs a)
         if (lane >= dd) incl += v;
     }
     const int nj = lane < n_slots ? max(act_l, prev_act) : 0;
+    /* plain MS stereo: the two rows of a granule sit in adjacent slots when both are part of the tile */
+    const int p_gc = __shfl_xor_sync(0xffffffffu, gc, 1), p_nzl = __shfl_xor_sync(0xffffffffu, nzl, 1);
+    const bool pair_ok = nch == 2 && ms && gc >= 0 && p_gc == (gc ^ 1);
+    const int pair32 = pair_ok ? max(nzl, p_nzl) >> 5 : 0;
+    const int far = (ms && !pair_ok) ? 1 : 0;
     TileRec *rec = a.tile_recs + t;
     if (lane < MP3B_TILE_SLOTS)
     {
         TileSlot ts;
         ts.gc = gc;
-        ts.info = (uint32_t)nzl | (uint32_t)act << TSI_ACT_SHIFT | (uint32_t)bt << TSI_BT_SHIFT | (uint32_t)ms << TSI_MS_SHIFT |
-                  (uint32_t)n_long << TSI_NLONG_SHIFT | (uint32_t)(map + 1) << TSI_MAP_SHIFT;
+        ts.info = (uint32_t)(nzl >> 5) | (uint32_t)act << TSI_ACT_SHIFT | (uint32_t)bt << TSI_BT_SHIFT | (uint32_t)ms << TSI_MS_SHIFT |
+                  (uint32_t)n_long << TSI_NLONG_SHIFT | (uint32_t)(map + 1) << TSI_MAP_SHIFT |
+                  (uint32_t)pair32 << TSI_PAIR_SHIFT | (uint32_t)far << TSI_FAR_SHIFT;
         rec->slot[lane] = ts;
     }
     if (lane == 0)
@@ -470,7 +476,7 @@ k_l3_transform(TransformArgs a, const uint16_t *__restrict__ reorder_inv, const 
     if (has)
     {
         m.gc = ts.gc;
-        m.nzl = (int)(ts.info & TSI_NZL_MASK);
+        m.nzl = (int)(ts.info & TSI_NZL32_MASK) << 5;
         m.act = (int)(ts.info >> TSI_ACT_SHIFT) & 63;
         m.block_type = (int)(ts.info >> TSI_BT_SHIFT) & 3;
         m.ms = (int)(ts.info >> TSI_MS_SHIFT) & 3;
@@ -509,38 +515,19 @@ k_l3_transform(TransformArgs a, const uint16_t *__restrict__ reorder_inv, const 
     MP3B_STAMP();
     if (nch == 2)
     {
-        const int p_gc = __shfl_xor_sync(0xffffffffu, m.gc, 1), p_nzl = __shfl_xor_sync(0xffffffffu, m.nzl, 1);
-        const bool pair_ok = has && m.ms && m.gc >= 0 && p_gc == (m.gc ^ 1);
-        const int my_lim4 = pair_ok ? (max(m.nzl, p_nzl) + 3) >> 2 : 0;
-        int lim4[kU], lim_max = 0;
-#pragma unroll
-        for (int j = 0; j < kU; j++)
+        /* half a warp per granule: (L, R) <- (L + R, L - R) over the extent of the longer row, 16 bytes per lane */
+        static_assert(kU == 2, "two granules per warp, sixteen lanes each");
+        const int my_pair4 = has ? (int)((ts.info >> TSI_PAIR_SHIFT) & 31)*8 : 0;
+        const int j = lane >> 4, l16 = lane & 15;
+        const int lim4 = __shfl_sync(0xffffffffu, my_pair4, j*2);
+        float4 *l = reinterpret_cast<float4 *>(S.x + (warp + j*kW)*2*kXSlot);
+        for (int k = l16; k < lim4; k += 16)
         {
-            lim4[j] = __shfl_sync(0xffffffffu, my_lim4, j*2);
-            lim_max = max(lim_max, lim4[j]);
+            const float4 vl = l[k], vr = l[k + kXSlot/4];
+            l[k] = make_float4(vl.x + vr.x, vl.y + vr.y, vl.z + vr.z, vl.w + vr.w);
+            l[k + kXSlot/4] = make_float4(vl.x - vr.x, vl.y - vr.y, vl.z - vr.z, vl.w - vr.w);
         }
-        /* both granules of the warp in flight before anything is stored */
-        for (int k = lane; k < lim_max; k += 32)
-        {
-            float4 vl[kU], vr[kU];
-#pragma unroll
-            for (int j = 0; j < kU; j++)
-                if (k < lim4[j])
-                {
-                    const float4 *l = reinterpret_cast<const float4 *>(S.x + (warp + j*kW)*2*kXSlot);
-                    vl[j] = l[k];
-                    vr[j] = l[k + kXSlot/4];
-                }
-#pragma unroll
-            for (int j = 0; j < kU; j++)
-                if (k < lim4[j])
-                {
-                    float4 *l = reinterpret_cast<float4 *>(S.x + (warp + j*kW)*2*kXSlot);
-                    l[k] = make_float4(vl[j].x + vr[j].x, vl[j].y + vr[j].y, vl[j].z + vr[j].z, vl[j].w + vr[j].w);
-                    l[k + kXSlot/4] = make_float4(vl[j].x - vr[j].x, vl[j].y - vr[j].y, vl[j].z - vr[j].z, vl[j].w - vr[j].w);
-                }
-        }
-        unsigned far_mask = __ballot_sync(0xffffffffu, has && m.ms && !pair_ok);
+        unsigned far_mask = __ballot_sync(0xffffffffu, has && ((ts.info >> TSI_FAR_SHIFT) & 1));
         while (far_mask)
         {
             /* the other channel of the granule is not part of the tile (halo across a channel-mode change):

@@ -68,12 +68,14 @@ typedef struct
  * the row to copy and how to treat it, the prefix sums of the IMDCT job list, and the tile header. */
 #define MP3B_TILE_SLOTS ((MP3B_TILE_GRANULES + 2)*2)
 /* TileSlot.info */
-#define TSI_NZL_MASK     0x3ffu          /* bits 0..9: decoded extent in lines (multiple of 32) */
-#define TSI_ACT_SHIFT    10              /* bits 10..15: subbands that can hold non-zero lines after antialias */
-#define TSI_BT_SHIFT     16              /* bits 16..17: block type */
-#define TSI_MS_SHIFT     18              /* bits 18..19: 0 none, 1 row = L + R, 2 row = L - R */
-#define TSI_NLONG_SHIFT  20              /* bits 20..22: leading long subbands of a mixed block (0, 2, 4) */
-#define TSI_MAP_SHIFT    23              /* bits 23..27: reorder map row + 1, 0 = none */
+#define TSI_NZL32_MASK   0x1fu           /* bits 0..4: decoded extent in units of 32 lines (0..18) */
+#define TSI_ACT_SHIFT    5               /* bits 5..10: subbands that can hold non-zero lines after antialias */
+#define TSI_BT_SHIFT     11              /* bits 11..12: block type */
+#define TSI_MS_SHIFT     13              /* bits 13..14: 0 none, 1 row = L + R, 2 row = L - R */
+#define TSI_NLONG_SHIFT  15              /* bits 15..17: leading long subbands of a mixed block (0, 2, 4) */
+#define TSI_MAP_SHIFT    18              /* bits 18..22: reorder map row + 1, 0 = none */
+#define TSI_PAIR_SHIFT   23              /* bits 23..27: plain-MS pair with both rows in the tile: max extent / 32, else 0 */
+#define TSI_FAR_SHIFT    28              /* bit 28: plain-MS row whose partner row is not part of the tile */
 /* IMDCT job list of a tile: [MP3B_TILE_JOBS] entries (slot << 8 | subband), the first TileRec.n_jobs valid:
  * only subbands that are active in the granule itself or in the one before it (whose tail overlaps into it)
  * need work, everything else is exactly zero. */
