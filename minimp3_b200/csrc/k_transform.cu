@@ -831,8 +831,10 @@ void tables_free(DeviceTables *t)
 cudaError_t launch_transform(const DeviceTables &t, const TransformArgs &a, cudaStream_t s)
 {
     if (!a.n_tiles) return cudaSuccess;
-    size_t smem = sizeof(Smem);
-    if (const char *pad = getenv("MP3B_DEBUG_SMEM_PAD")) smem += (size_t)atoi(pad);   /* occupancy experiments */
+    /* MP3B_DEBUG_SMEM_PAD=<bytes> (read once): pads the dynamic shared memory to lower the CTAs per SM; used with
+     * tools/phase_times.py to time a tile that has the SM to itself */
+    static const size_t debug_pad = [] { const char *p = getenv("MP3B_DEBUG_SMEM_PAD"); return p ? (size_t)atoi(p) : (size_t)0; }();
+    const size_t smem = sizeof(Smem) + debug_pad;
     cudaError_t e;
     k_l3_tile_meta<<<(a.n_tiles + 7)/8, 256, 0, s>>>(a);
     if (a.float_output)
