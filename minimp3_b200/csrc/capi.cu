@@ -189,6 +189,7 @@ struct DeviceCtx
     DeviceTables tables{};
     cudaStream_t stream = nullptr;      /* H2D + kernels */
     cudaStream_t stream_d2h = nullptr;  /* PCM read-back, overlaps the next chunk's kernels */
+    cudaStream_t stream_h2d = nullptr;  /* chunk-pipelined calls: inputs of chunk c+1 go up while chunk c computes */
     std::mutex mu;
     std::vector<BufferSet *> free_sets;
     /* single-frame API scratch */
@@ -215,7 +216,8 @@ DeviceCtx *get_ctx(int device)
     DeviceCtx *c = new DeviceCtx();
     c->device = device;
     if (tables_upload(&c->tables) != 0 || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&c->stream_d2h, cudaStreamNonBlocking) != cudaSuccess)
+        cudaStreamCreateWithFlags(&c->stream_d2h, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&c->stream_h2d, cudaStreamNonBlocking) != cudaSuccess)
     {
         fprintf(stderr, "minimp3_b200: CUDA initialisation failed: %s\n", cudaGetErrorString(cudaGetLastError()));
         delete c;
@@ -262,7 +264,7 @@ struct mp3dec_batch_plan
     uint64_t md_bytes = 0, n_gc = 0, n_tiles = 0, n_samples = 0, n_ist = 0, n_order = 0, n_frames = 0, input_bytes = 0;
     size_t sample_size = 2;
     bool taps = false;
-    cudaEvent_t ev_kernels = nullptr, ev_d2h = nullptr;
+    cudaEvent_t ev_kernels = nullptr, ev_d2h = nullptr, ev_h2d = nullptr;
     bool d2h_started = false;
     mp3dec_batch_stats_t stats{};
 };
@@ -444,13 +446,22 @@ static mp3dec_batch_plan_t *plan_create_impl(const mp3dec_batch_stream_t *stream
     if (!ok) { *err = MP3D_E_MEMORY; mp3dec_batch_plan_destroy(P); return nullptr; }
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (!async) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, P->stream); }
-    cudaMemcpyAsync(B.d_md.p, B.h_md.p, P->md_bytes, cudaMemcpyHostToDevice, P->stream);
-    if (gcs) cudaMemcpyAsync(B.d_gcs.p, B.h_gcs.p, (size_t)gcs*sizeof(GcDesc), cudaMemcpyHostToDevice, P->stream);
-    if (tiles) cudaMemcpyAsync(B.d_tiles.p, B.h_tiles.p, (size_t)tiles*sizeof(TileDesc), cudaMemcpyHostToDevice, P->stream);
-    if (ists) cudaMemcpyAsync(B.d_istlist.p, B.h_ist.p, (size_t)ists*4, cudaMemcpyHostToDevice, P->stream);
-    if (orders) cudaMemcpyAsync(B.d_order.p, B.h_order.p, (size_t)orders*4, cudaMemcpyHostToDevice, P->stream);
-    if (l12s) cudaMemcpyAsync(B.d_l12.p, B.h_l12.p, (size_t)l12s*sizeof(L12FrameDesc), cudaMemcpyHostToDevice, P->stream);
-    if (tiles12) cudaMemcpyAsync(B.d_tiles12.p, B.h_tiles12.p, (size_t)tiles12*sizeof(TileDesc), cudaMemcpyHostToDevice, P->stream);
+    /* in a chunk-pipelined call the inputs travel on their own stream, so that they overlap the kernels of the
+     * chunk before; the plan's stream picks up behind them */
+    cudaStream_t up = (async && !opts.cuda_stream) ? ctx->stream_h2d : P->stream;
+    cudaMemcpyAsync(B.d_md.p, B.h_md.p, P->md_bytes, cudaMemcpyHostToDevice, up);
+    if (gcs) cudaMemcpyAsync(B.d_gcs.p, B.h_gcs.p, (size_t)gcs*sizeof(GcDesc), cudaMemcpyHostToDevice, up);
+    if (tiles) cudaMemcpyAsync(B.d_tiles.p, B.h_tiles.p, (size_t)tiles*sizeof(TileDesc), cudaMemcpyHostToDevice, up);
+    if (ists) cudaMemcpyAsync(B.d_istlist.p, B.h_ist.p, (size_t)ists*4, cudaMemcpyHostToDevice, up);
+    if (orders) cudaMemcpyAsync(B.d_order.p, B.h_order.p, (size_t)orders*4, cudaMemcpyHostToDevice, up);
+    if (l12s) cudaMemcpyAsync(B.d_l12.p, B.h_l12.p, (size_t)l12s*sizeof(L12FrameDesc), cudaMemcpyHostToDevice, up);
+    if (tiles12) cudaMemcpyAsync(B.d_tiles12.p, B.h_tiles12.p, (size_t)tiles12*sizeof(TileDesc), cudaMemcpyHostToDevice, up);
+    if (up != P->stream)
+    {
+        cudaEventCreateWithFlags(&P->ev_h2d, cudaEventDisableTiming);
+        cudaEventRecord(P->ev_h2d, up);
+        cudaStreamWaitEvent(P->stream, P->ev_h2d, 0);
+    }
     float h2d = 0.f;
     if (!async)
     {
@@ -708,6 +719,7 @@ void mp3dec_batch_plan_destroy(mp3dec_batch_plan_t *P)
     if (!P) return;
     if (P->ev_kernels) cudaEventDestroy(P->ev_kernels);
     if (P->ev_d2h) cudaEventDestroy(P->ev_d2h);
+    if (P->ev_h2d) cudaEventDestroy(P->ev_h2d);
     if (P->bufs) release_set(P->ctx, P->bufs);
     delete P;
 }
@@ -754,13 +766,23 @@ int mp3dec_decode_batch_cuda(const mp3dec_batch_stream_t *streams, int n_streams
             first[c + 1] = c + 1 == n_chunks ? n_streams : std::max(first[c] + 1, (int)(n_streams*acc/total_w));
         }
     }
+    static const bool dbg_timing = getenv("MP3B_DEBUG_TIMING") != nullptr;
+    const double tt0 = now_ms();
     for (int c = 0; c < n_chunks && !err; c++)
     {
+        const double a0 = now_ms();
         plans[c] = plan_create_impl(streams + first[c], first[c + 1] - first[c], opts, &err, true);
         if (!plans[c]) break;
+        const double a1 = now_ms();
         err = mp3dec_batch_plan_run(plans[c]);
+        const double a2 = now_ms();
         if (!err) err = plan_begin_fetch(plans[c], plans[c]->ctx->stream_d2h);
+        const double a3 = now_ms();
+        if (dbg_timing)
+            fprintf(stderr, "chunk %d: %d streams, create %.3f ms (walk stages %.3f), run %.3f, begin_fetch %.3f, t=%.3f\n", c,
+                    first[c + 1] - first[c], a1 - a0, plans[c]->stats.host_parse_ms, a2 - a1, a3 - a2, a3 - tt0);
     }
+    const double tt1 = now_ms();
     for (int c = 0; c < n_chunks; c++)
     {
         if (!plans[c]) continue;
@@ -769,12 +791,14 @@ int mp3dec_decode_batch_cuda(const mp3dec_batch_stream_t *streams, int n_streams
         else
             cudaStreamSynchronize(plans[c]->stream);
     }
+    const double tt2 = now_ms();
     for (int c = 0; c < n_chunks; c++)
         if (plans[c])
         {
             if (err) cudaStreamSynchronize(plans[c]->ctx->stream_d2h);
             mp3dec_batch_plan_destroy(plans[c]);
         }
+    if (dbg_timing) fprintf(stderr, "issue %.3f ms, finish %.3f ms, destroy %.3f ms\n", tt1 - tt0, tt2 - tt1, now_ms() - tt2);
     return err;
 }
 
