@@ -171,13 +171,13 @@ struct PinBuf
 struct BufferSet
 {
     PinBuf h_md, h_gcs, h_tiles, h_ist, h_order, h_pcm, h_l12, h_tiles12;
-    DevBuf d_md, d_gcs, d_tiles, d_tile_recs, d_tile_jobs, d_istlist, d_order, d_xr, d_nzl, d_istpos, d_pcm, d_l12, d_tiles12, d_sub12;
+    DevBuf d_md, d_gcs, d_tiles, d_tile_recs, d_tile_jobs, d_counter, d_istlist, d_order, d_xr, d_nzl, d_istpos, d_pcm, d_l12, d_tiles12, d_sub12;
     DevBuf d_tap_q, d_tap_scf, d_tap_sub, d_phase_clk;
     void release()
     {
         h_md.release(); h_gcs.release(); h_tiles.release(); h_ist.release(); h_order.release(); h_pcm.release(); h_l12.release(); h_tiles12.release();
         d_l12.release(); d_tiles12.release(); d_sub12.release();
-        d_md.release(); d_gcs.release(); d_tiles.release(); d_tile_recs.release(); d_tile_jobs.release(); d_istlist.release(); d_order.release(); d_xr.release(); d_nzl.release();
+        d_md.release(); d_gcs.release(); d_tiles.release(); d_tile_recs.release(); d_tile_jobs.release(); d_counter.release(); d_istlist.release(); d_order.release(); d_xr.release(); d_nzl.release();
         d_istpos.release(); d_pcm.release(); d_tap_q.release(); d_tap_scf.release(); d_tap_sub.release(); d_phase_clk.release();
     }
 };
@@ -437,7 +437,7 @@ static mp3dec_batch_plan_t *plan_create_impl(const mp3dec_batch_stream_t *stream
 
     /* ---- device buffers + H2D ---- */
     ok = B.d_md.ensure(P->md_bytes) && B.d_gcs.ensure((size_t)gcs*sizeof(GcDesc) + 64) &&
-         B.d_tiles.ensure((size_t)tiles*sizeof(TileDesc) + 64) && B.d_tile_recs.ensure((size_t)tiles*sizeof(TileRec) + 256) && B.d_tile_jobs.ensure((size_t)tiles*MP3B_TILE_JOBS*2 + 256) &&
+         B.d_tiles.ensure((size_t)tiles*sizeof(TileDesc) + 64) && B.d_tile_recs.ensure((size_t)tiles*sizeof(TileRec) + 256) && B.d_tile_jobs.ensure((size_t)tiles*MP3B_TILE_JOBS*2 + 256) && B.d_counter.ensure(256) &&
          B.d_istlist.ensure((size_t)ists*4 + 64) &&
          B.d_order.ensure((size_t)orders*4 + 64) && B.d_l12.ensure((size_t)l12s*sizeof(L12FrameDesc) + 64) &&
          B.d_tiles12.ensure((size_t)tiles12*sizeof(TileDesc) + 64) && B.d_sub12.ensure((size_t)blks*384*sizeof(float) + 64) &&
@@ -536,6 +536,7 @@ static int plan_run_stages(mp3dec_batch_plan_t *P, int stage_mask)
     ea.n_gc = (uint32_t)P->n_gc;
     ea.order = (const uint32_t *)B.d_order.p;
     ea.n_order = (uint32_t)P->n_order;
+    ea.group_counter = (uint32_t *)B.d_counter.p;
     ea.xr = (float *)B.d_xr.p;
     ea.nzl = (uint16_t *)B.d_nzl.p;
     ea.ist_pos = (uint8_t *)B.d_istpos.p;
@@ -952,7 +953,7 @@ static int decode_frame_impl(mp3dec_t *dec, const uint8_t *mp3, int mp3_bytes, v
         const size_t ss = float_output ? 4 : 2;
         const int n_samples = fp.n_gr*576*fp.nch;
         bool ok = B.h_md.ensure(md_bytes + 4*sizeof(GcDesc) + sizeof(TileDesc) + 64) && B.d_md.ensure(md_bytes) &&
-                  B.d_gcs.ensure(4*sizeof(GcDesc)) && B.d_tiles.ensure(sizeof(TileDesc)) && B.d_tile_recs.ensure(sizeof(TileRec)) && B.d_tile_jobs.ensure(MP3B_TILE_JOBS*2) && B.d_istlist.ensure(16) && B.d_order.ensure(16) &&
+                  B.d_gcs.ensure(4*sizeof(GcDesc)) && B.d_tiles.ensure(sizeof(TileDesc)) && B.d_tile_recs.ensure(sizeof(TileRec)) && B.d_tile_jobs.ensure(MP3B_TILE_JOBS*2) && B.d_counter.ensure(256) && B.d_istlist.ensure(16) && B.d_order.ensure(16) &&
                   B.d_xr.ensure(4*576*4) && B.d_nzl.ensure(16) && B.d_istpos.ensure(4*40) &&
                   B.d_pcm.ensure(2304*4) && B.h_pcm.ensure(2304*4) && ctx->d_state_in.ensure(1536*4) &&
                   ctx->d_state_out.ensure(1536*4) && ctx->h_state.ensure(2*1536*4);
@@ -995,7 +996,7 @@ static int decode_frame_impl(mp3dec_t *dec, const uint8_t *mp3, int mp3_bytes, v
         memset(&ea, 0, sizeof(ea));
         ea.md_words = (const uint32_t *)B.d_md.p; ea.md_n_words = md_bytes/4;
         ea.gcs = (const GcDesc *)B.d_gcs.p; ea.n_gc = 4;
-        ea.order = (const uint32_t *)B.d_order.p; ea.n_order = (uint32_t)n_gc;
+        ea.order = (const uint32_t *)B.d_order.p; ea.n_order = (uint32_t)n_gc; ea.group_counter = (uint32_t *)B.d_counter.p;
         ea.xr = (float *)B.d_xr.p; ea.nzl = (uint16_t *)B.d_nzl.p; ea.ist_pos = (uint8_t *)B.d_istpos.p;
         cudaError_t e = launch_entropy(ctx->tables, ea, s);
         if (e == cudaSuccess && n_ist)

@@ -80,8 +80,13 @@ __global__ void __launch_bounds__(kWarpsPerBlock*32, 2) k_l3_entropy(EntropyArgs
     WarpScratch &W = scratch[warp];
     const uint32_t n_groups = (a.n_order + 31)/32;
 
-    for (uint32_t group = blockIdx.x*kWarpsPerBlock + warp; group < n_groups; group += gridDim.x*kWarpsPerBlock)
+    /* the first group of a warp is fixed, further ones come from a global counter: SMs differ in speed by ~10 %
+     * and groups in length, a static split would wait for the slowest warp.  The claim is issued before the group
+     * is decoded, so its round trip is free. */
+    const uint32_t n_warps = gridDim.x*kWarpsPerBlock;
+    for (uint32_t group = blockIdx.x*kWarpsPerBlock + warp, claimed = 0; group < n_groups; group = claimed)
     {
+        if (lane == 0) claimed = atomicAdd(a.group_counter, 1u) + n_warps;
         const uint32_t item = group*32 + lane;
         const bool valid = item < a.n_order;
         const uint32_t gc = valid ? __ldg(a.order + item) : 0u;
@@ -154,7 +159,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock*32, 2) k_l3_entropy(EntropyArgs
         }
         /* ---- per-row extent for the consumer ---- */
         if (valid) a.nzl[gc] = (uint16_t)((dec.extent + 31) & ~31);
-        __syncwarp();
+        claimed = __shfl_sync(0xffffffffu, claimed, 0);
     }
 }
 
@@ -173,6 +178,7 @@ cudaError_t launch_entropy(const DeviceTables &, const EntropyArgs &a, cudaStrea
     uint32_t blocks = (n_groups + kWarpsPerBlock - 1)/kWarpsPerBlock;
     const uint32_t max_blocks = (uint32_t)sms*2;
     if (blocks > max_blocks) blocks = max_blocks;
+    if (cudaMemsetAsync(a.group_counter, 0, sizeof(uint32_t), s) != cudaSuccess) return cudaGetLastError();
     k_l3_entropy<<<blocks, kWarpsPerBlock*32, smem, s>>>(a);
     return cudaGetLastError();
 }

@@ -25,6 +25,7 @@ struct EntropyArgs
     uint32_t n_gc;                /* multiple of 2; stereo pairs start at even indices */
     const uint32_t *order;        /* lane order: granule-channel index handled by work item k */
     uint32_t n_order;
+    uint32_t *group_counter;      /* scratch word: launch_entropy clears it, the warps claim their next 32 work items from it */
     float *xr;                    /* [n_gc][576] */
     uint16_t *nzl;                /* [n_gc] lines written per row (multiple of 32) */
     uint8_t *ist_pos;             /* [n_gc][40] written for intensity-stereo frames (and in tap mode) */
