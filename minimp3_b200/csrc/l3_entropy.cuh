@@ -298,6 +298,11 @@ struct GranuleDecoder
     {
         v0 = v1 = 0.f;
         q0 = q1 = 0;
+#if defined(__CUDA_ARCH__)
+        /* the tables and the scalefactor scratch live in shared memory on the device: lets the compiler use LDS */
+        __builtin_assume(__isShared(T.lut)); __builtin_assume(__isShared(T.pow43)); __builtin_assume(__isShared(T.tabinfo));
+        __builtin_assume(__isShared(sfbw)); __builtin_assume(__isShared(iscf));
+#endif
         const int this_line = line;
         line += 2;
         if (mode == EMODE_DONE) return;
