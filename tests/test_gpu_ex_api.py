@@ -132,3 +132,20 @@ def test_load_buf_progress_callback(name, m, ref):
     ret, part, _ = m.mp3dec_load_buf(data, progress=lambda size, off, fi: seen.append(off) or (5 if len(seen) == 3 else 0))
     assert ret == 5 and len(seen) == 3 and 0 < len(part) < len(pcm)
     assert np.array_equal(part, pcm[:len(part)])
+
+
+def test_plain_c_caller(tmp_path, manifest, ref):
+    """examples/decode_file.c (C99, only the public header): mp3dec_load_buf and the README frame loop."""
+    import subprocess
+    from test_abi import build_c_example
+    exe = build_c_example(str(tmp_path))
+    name = "l3-compl"
+    out = str(tmp_path / "out.pcm")
+    line = subprocess.check_output([exe, vector_path(name), out]).decode()
+    kv = dict(t.split("=") for t in line.split())
+    mf = manifest[name]
+    assert int(kv["samples"]) == mf["load_samples"] and int(kv["frame_loop_samples"]) == mf["samples"]
+    assert int(kv["rate"]) == mf["hz"] and int(kv["layer"]) == 3
+    pcm = np.fromfile(out, dtype="<i2")
+    _, want, _ = ref.load_buf(load_vector(name))
+    assert len(pcm) == len(want) and np.abs(pcm.astype(np.int32) - want.astype(np.int32)).max() <= 1
