@@ -48,17 +48,18 @@ def test_no_cpu_fallback_in_product():
                 assert not pat.search(src), f
 
 
-def build_c_example(out_dir):
-    """examples/decode_file.c as a maintainer would build it: plain C99, the public header, -lminimp3_b200."""
+def build_c_example(out_dir, name="decode_file"):
+    """examples/<name>.c as a maintainer would build it: plain C99, the public header, -lminimp3_b200."""
     import subprocess
     build_lib()
-    exe = os.path.join(out_dir, "decode_file")
+    exe = os.path.join(out_dir, name)
     libdir = os.path.dirname(m.LIB_PATH)
     subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I" + os.path.join(conftest.ROOT, "include"),
-                           os.path.join(conftest.ROOT, "examples", "decode_file.c"), "-L" + libdir, "-lminimp3_b200",
+                           os.path.join(conftest.ROOT, "examples", name + ".c"), "-L" + libdir, "-lminimp3_b200",
                            "-Wl,-rpath," + libdir, "-o", exe])
     return exe
 
 
-def test_c_caller_compiles_against_the_header(tmp_path):
+def test_c_callers_compile_against_the_header(tmp_path):
     assert os.path.exists(build_c_example(str(tmp_path)))
+    assert os.path.exists(build_c_example(str(tmp_path), "decode_batch"))

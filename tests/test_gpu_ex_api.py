@@ -149,3 +149,18 @@ def test_plain_c_caller(tmp_path, manifest, ref):
     pcm = np.fromfile(out, dtype="<i2")
     _, want, _ = ref.load_buf(load_vector(name))
     assert len(pcm) == len(want) and np.abs(pcm.astype(np.int32) - want.astype(np.int32)).max() <= 1
+
+
+def test_plain_c_batch_caller(tmp_path, manifest):
+    """examples/decode_batch.c: per file what mp3dec_load_buf reports (return code, format, sample count)"""
+    import subprocess
+    from test_abi import build_c_example
+    exe = build_c_example(str(tmp_path), "decode_batch")
+    names = ["l3-compl", "l3-nonstandard-sin1k0db_lame_vbrtag", "l2-fl10", "l3-compl", "l1-fl1"]
+    lines = subprocess.check_output([exe] + [vector_path(n) for n in names]).decode().strip().splitlines()
+    assert len(lines) == len(names)
+    for n, line in zip(names, lines):
+        kv = dict(t.split("=") for t in line.split()[1:])
+        mf = manifest[n]
+        assert int(kv["ret"]) == mf["load_ret"] and int(kv["samples"]) == mf["load_samples"] and int(kv["rate"]) == mf["hz"]
+    assert lines[0].split()[1:] == lines[3].split()[1:]          # the same file twice decodes to the same PCM
