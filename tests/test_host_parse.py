@@ -148,3 +148,39 @@ def test_corrupted_streams_walk_like_the_reference(name, ref):
         assert w["info"]["frames"] == len(frames), trial
         assert w["info"]["frames_decoded"] == sum(1 for f in frames if f.samples), trial
         assert w["info"]["samples_decoded"] == len(pcm), trial
+
+
+def test_fuzzed_streams_walk_like_the_reference(ref):
+    """Random junk with planted sync words, spliced / cut / duplicated real streams, streams entered mid-frame:
+    the walker keeps and drops the same frames as mp3dec_load_buf (return code, sample count, format)."""
+    rng = np.random.default_rng(12345)
+    base = load_vector("l3-compl")
+    for t in range(160):
+        kind = t % 4
+        if kind == 0:
+            n = int(rng.integers(1, 20000))
+            b = bytearray(rng.integers(0, 256, n, dtype=np.uint8).tobytes())
+            for _ in range(int(rng.integers(0, 40))):
+                p = int(rng.integers(0, max(1, n - 4)))
+                b[p:p + 2] = bytes([0xFF, int(rng.choice([0xFB, 0xFA, 0xF3, 0xE3, 0xFD, 0xFC]))])
+        elif kind == 1:
+            b = bytearray(base[:int(rng.integers(2000, len(base)))])
+            for _ in range(int(rng.integers(1, 6))):
+                p, n = int(rng.integers(0, len(b) - 200)), int(rng.integers(1, 200))
+                b[p:p + n] = rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+        elif kind == 2:
+            b = bytearray(base)
+            for _ in range(int(rng.integers(1, 4))):
+                p, n = int(rng.integers(0, len(b) - 500)), int(rng.integers(1, 500))
+                if rng.random() < 0.5:
+                    del b[p:p + n]
+                else:
+                    b[p:p] = b[p:p + n]
+        else:
+            b = bytearray(base[int(rng.integers(0, 3000)):])
+        data = bytes(b)
+        ret, pcm, info = ref.load_buf(data)
+        wi = harness.walk(data)["info"]
+        assert (wi["ret"], wi["out_samples"]) == (ret, len(pcm)), (t, kind)
+        if len(pcm):
+            assert (wi["hz"], wi["channels"]) == (info["hz"], info["channels"]), (t, kind)
