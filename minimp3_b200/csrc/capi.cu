@@ -952,12 +952,15 @@ static int decode_frame_impl(mp3dec_t *dec, const uint8_t *mp3, int mp3_bytes, v
         const size_t md_bytes = round_up((size_t)md_len + 64, 16);
         const size_t ss = float_output ? 4 : 2;
         const int n_samples = fp.n_gr*576*fp.nch;
-        bool ok = B.h_md.ensure(md_bytes + 4*sizeof(GcDesc) + sizeof(TileDesc) + 64) && B.d_md.ensure(md_bytes) &&
+        /* 4 KB behind the payload: a damaged granule can ask the Huffman decoder for up to 288 pairs of 47 bits */
+        const size_t md_cap_before = B.d_md.cap;
+        bool ok = B.h_md.ensure(md_bytes + 4*sizeof(GcDesc) + sizeof(TileDesc) + 64) && B.d_md.ensure(md_bytes + 4096) &&
                   B.d_gcs.ensure(4*sizeof(GcDesc)) && B.d_tiles.ensure(sizeof(TileDesc)) && B.d_tile_recs.ensure(sizeof(TileRec)) && B.d_tile_jobs.ensure(MP3B_TILE_JOBS*2) && B.d_counter.ensure(256) && B.d_istlist.ensure(16) && B.d_order.ensure(16) &&
                   B.d_xr.ensure(4*576*4) && B.d_nzl.ensure(16) && B.d_istpos.ensure(4*40) &&
                   B.d_pcm.ensure(2304*4) && B.h_pcm.ensure(2304*4) && ctx->d_state_in.ensure(1536*4) &&
                   ctx->d_state_out.ensure(1536*4) && ctx->h_state.ensure(2*1536*4);
         if (!ok) return 0;
+        if (B.d_md.cap != md_cap_before) cudaMemset(B.d_md.p, 0, B.d_md.cap);   /* fresh allocation: defined guard bytes */
         uint8_t *h = (uint8_t *)B.h_md.p;
         memcpy(h, maindata, md_bytes);
         GcDesc gcs[4];
