@@ -170,14 +170,14 @@ struct PinBuf
 /* all device + pinned memory of one in-flight batch; recycled between calls */
 struct BufferSet
 {
-    PinBuf h_md, h_gcs, h_tiles, h_ist, h_order, h_pcm, h_l12, h_tiles12;
-    DevBuf d_md, d_gcs, d_tiles, d_tile_recs, d_tile_jobs, d_counter, d_istlist, d_order, d_xr, d_nzl, d_istpos, d_pcm, d_l12, d_tiles12, d_sub12;
+    PinBuf h_md, h_gcs, h_frames, h_tiles, h_ist, h_order, h_pcm, h_l12, h_tiles12;
+    DevBuf d_md, d_gcs, d_frames, d_tiles, d_tile_recs, d_tile_jobs, d_counter, d_istlist, d_order, d_xr, d_nzl, d_istpos, d_pcm, d_l12, d_tiles12, d_sub12;
     DevBuf d_tap_q, d_tap_scf, d_tap_sub, d_phase_clk;
     void release()
     {
-        h_md.release(); h_gcs.release(); h_tiles.release(); h_ist.release(); h_order.release(); h_pcm.release(); h_l12.release(); h_tiles12.release();
+        h_md.release(); h_gcs.release(); h_frames.release(); h_tiles.release(); h_ist.release(); h_order.release(); h_pcm.release(); h_l12.release(); h_tiles12.release();
         d_l12.release(); d_tiles12.release(); d_sub12.release();
-        d_md.release(); d_gcs.release(); d_tiles.release(); d_tile_recs.release(); d_tile_jobs.release(); d_counter.release(); d_istlist.release(); d_order.release(); d_xr.release(); d_nzl.release();
+        d_md.release(); d_gcs.release(); d_frames.release(); d_tiles.release(); d_tile_recs.release(); d_tile_jobs.release(); d_counter.release(); d_istlist.release(); d_order.release(); d_xr.release(); d_nzl.release();
         d_istpos.release(); d_pcm.release(); d_tap_q.release(); d_tap_scf.release(); d_tap_sub.release(); d_phase_clk.release();
     }
 };
@@ -259,7 +259,7 @@ struct mp3dec_batch_plan
     cudaStream_t stream = nullptr;
     int n_streams = 0;
     std::vector<StreamPlan> plans;
-    std::vector<uint64_t> md_base, gc_base, tile_base, pcm_base, ist_base, order_base, l12_base, blk_base, tile12_base;
+    std::vector<uint64_t> md_base, gc_base, fr_base, tile_base, pcm_base, ist_base, order_base, l12_base, blk_base, tile12_base;
     uint64_t n_l12 = 0, n_blk = 0, n_tiles12 = 0;
     uint64_t md_bytes = 0, n_gc = 0, n_tiles = 0, n_samples = 0, n_ist = 0, n_order = 0, n_frames = 0, input_bytes = 0;
     size_t sample_size = 2;
@@ -340,6 +340,7 @@ static mp3dec_batch_plan_t *plan_create_impl(const mp3dec_batch_stream_t *stream
     WalkOptions wopt;
     wopt.raw_frames = opts.raw_frames != 0;
     wopt.allow_mono_stereo = opts.allow_mono_stereo_transition != 0;
+    wopt.device_side_info = true;        /* descriptors are produced on the GPU from FrameRec records (k_sideinfo.cu) */
     uint8_t *h_md = (uint8_t *)B.h_md.p;
     parallel_for(n_streams, opts.host_threads, [&](int i) {
         uint8_t *dst = h_md + P->md_base[i];
@@ -354,7 +355,8 @@ static mp3dec_batch_plan_t *plan_create_impl(const mp3dec_batch_stream_t *stream
     P->gc_base.resize(n_streams + 1); P->tile_base.resize(n_streams + 1);
     P->pcm_base.resize(n_streams + 1); P->ist_base.resize(n_streams + 1); P->order_base.resize(n_streams + 1);
     P->l12_base.resize(n_streams + 1); P->blk_base.resize(n_streams + 1); P->tile12_base.resize(n_streams + 1);
-    uint64_t gcs = 0, tiles = 0, samples = 0, ists = 0, orders = 0, l12s = 0, blks = 0, tiles12 = 0;
+    uint64_t gcs = 0, tiles = 0, samples = 0, ists = 0, orders = 0, l12s = 0, blks = 0, tiles12 = 0, frs = 0;
+    P->fr_base.resize(n_streams + 1);
     for (int i = 0; i < n_streams; i++)
     {
         const StreamPlan &sp = P->plans[i];
@@ -362,7 +364,9 @@ static mp3dec_batch_plan_t *plan_create_impl(const mp3dec_batch_stream_t *stream
         orders += sp.order.size();
         P->l12_base[i] = l12s; P->blk_base[i] = blks; P->tile12_base[i] = tiles12;
         l12s += sp.l12_frames.size(); blks += sp.n_blockch; tiles12 += sp.tiles12.size();
-        gcs += round_up(sp.gcs.size(), 2);
+        gcs += round_up((size_t)sp.n_gc, 2);
+        P->fr_base[i] = frs;
+        frs += sp.frame_recs.size();
         tiles += sp.tiles.size();
         samples += sp.samples_decoded;
         ists += sp.istereo_gcs.size();
@@ -374,11 +378,11 @@ static mp3dec_batch_plan_t *plan_create_impl(const mp3dec_batch_stream_t *stream
     P->n_l12 = l12s; P->n_blk = blks; P->n_tiles12 = tiles12;
     if (gcs >= (1ull << 31)) { *err = MP3D_E_PARAM; mp3dec_batch_plan_destroy(P); return nullptr; }
 
-    bool ok = B.h_gcs.ensure((size_t)gcs*sizeof(GcDesc) + 64) && B.h_tiles.ensure((size_t)tiles*sizeof(TileDesc) + 64) &&
+    bool ok = B.h_frames.ensure((size_t)frs*sizeof(FrameRec) + 64) && B.h_tiles.ensure((size_t)tiles*sizeof(TileDesc) + 64) &&
               B.h_ist.ensure((size_t)ists*4 + 64) && B.h_order.ensure((size_t)orders*4 + 64) &&
               B.h_l12.ensure((size_t)l12s*sizeof(L12FrameDesc) + 64) && B.h_tiles12.ensure((size_t)tiles12*sizeof(TileDesc) + 64);
     if (!ok) { *err = MP3D_E_MEMORY; mp3dec_batch_plan_destroy(P); return nullptr; }
-    GcDesc *h_gcs = (GcDesc *)B.h_gcs.p;
+    FrameRec *h_frames = (FrameRec *)B.h_frames.p;
     TileDesc *h_tiles = (TileDesc *)B.h_tiles.p;
     uint32_t *h_ist = (uint32_t *)B.h_ist.p;
     uint32_t *h_order = (uint32_t *)B.h_order.p;
@@ -387,13 +391,11 @@ static mp3dec_batch_plan_t *plan_create_impl(const mp3dec_batch_stream_t *stream
     parallel_for(n_streams, opts.host_threads, [&](int i) {
         StreamPlan &sp = P->plans[i];
         const uint64_t gb = P->gc_base[i];
-        if (!sp.gcs.empty()) memcpy(h_gcs + gb, sp.gcs.data(), sp.gcs.size()*sizeof(GcDesc));
-        if (sp.gcs.size() & 1)
+        for (size_t k = 0; k < sp.frame_recs.size(); k++)
         {
-            GcDesc pad;
-            memset(&pad, 0, sizeof(pad));
-            pad.flags1 = GCF1_MPEG1;
-            h_gcs[gb + sp.gcs.size()] = pad;
+            FrameRec r = sp.frame_recs[k];
+            r.gc_first += (uint32_t)gb;
+            h_frames[P->fr_base[i] + k] = r;
         }
         for (size_t k = 0; k < sp.tiles.size(); k++)
         {
@@ -429,6 +431,8 @@ static mp3dec_batch_plan_t *plan_create_impl(const mp3dec_batch_stream_t *stream
         std::vector<TileDesc>().swap(sp.tiles12);
         /* descriptor vectors are no longer needed on the host */
         std::vector<GcDesc>().swap(sp.gcs);
+        std::vector<FrameRec>().swap(sp.frame_recs);
+        std::vector<uint16_t>().swap(sp.gc_len);
         std::vector<TileDesc>().swap(sp.tiles);
         std::vector<GranuleRef>().swap(sp.granules);
         std::vector<uint32_t>().swap(sp.istereo_gcs);
@@ -436,7 +440,7 @@ static mp3dec_batch_plan_t *plan_create_impl(const mp3dec_batch_stream_t *stream
     const double t1 = now_ms();
 
     /* ---- device buffers + H2D ---- */
-    ok = B.d_md.ensure(P->md_bytes) && B.d_gcs.ensure((size_t)gcs*sizeof(GcDesc) + 64) &&
+    ok = B.d_md.ensure(P->md_bytes) && B.d_gcs.ensure((size_t)gcs*sizeof(GcDesc) + 64) && B.d_frames.ensure((size_t)frs*sizeof(FrameRec) + 64) &&
          B.d_tiles.ensure((size_t)tiles*sizeof(TileDesc) + 64) && B.d_tile_recs.ensure((size_t)tiles*sizeof(TileRec) + 256) && B.d_tile_jobs.ensure((size_t)tiles*MP3B_TILE_JOBS*2 + 256) && B.d_counter.ensure(256) &&
          B.d_istlist.ensure((size_t)ists*4 + 64) &&
          B.d_order.ensure((size_t)orders*4 + 64) && B.d_l12.ensure((size_t)l12s*sizeof(L12FrameDesc) + 64) &&
@@ -450,7 +454,7 @@ static mp3dec_batch_plan_t *plan_create_impl(const mp3dec_batch_stream_t *stream
      * chunk before; the plan's stream picks up behind them */
     cudaStream_t up = (async && !opts.cuda_stream) ? ctx->stream_h2d : P->stream;
     cudaMemcpyAsync(B.d_md.p, B.h_md.p, P->md_bytes, cudaMemcpyHostToDevice, up);
-    if (gcs) cudaMemcpyAsync(B.d_gcs.p, B.h_gcs.p, (size_t)gcs*sizeof(GcDesc), cudaMemcpyHostToDevice, up);
+    if (frs) cudaMemcpyAsync(B.d_frames.p, B.h_frames.p, (size_t)frs*sizeof(FrameRec), cudaMemcpyHostToDevice, up);
     if (tiles) cudaMemcpyAsync(B.d_tiles.p, B.h_tiles.p, (size_t)tiles*sizeof(TileDesc), cudaMemcpyHostToDevice, up);
     if (ists) cudaMemcpyAsync(B.d_istlist.p, B.h_ist.p, (size_t)ists*4, cudaMemcpyHostToDevice, up);
     if (orders) cudaMemcpyAsync(B.d_order.p, B.h_order.p, (size_t)orders*4, cudaMemcpyHostToDevice, up);
@@ -461,6 +465,13 @@ static mp3dec_batch_plan_t *plan_create_impl(const mp3dec_batch_stream_t *stream
         cudaEventCreateWithFlags(&P->ev_h2d, cudaEventDisableTiming);
         cudaEventRecord(P->ev_h2d, up);
         cudaStreamWaitEvent(P->stream, P->ev_h2d, 0);
+    }
+    /* side info -> descriptors, once per plan (they stay resident for every run of the plan) */
+    if (frs && launch_side_info((const FrameRec *)B.d_frames.p, (uint32_t)frs, (GcDesc *)B.d_gcs.p, P->stream) != cudaSuccess)
+    {
+        *err = MP3D_E_CUDA;
+        mp3dec_batch_plan_destroy(P);
+        return nullptr;
     }
     float h2d = 0.f;
     if (!async)
@@ -484,7 +495,7 @@ static mp3dec_batch_plan_t *plan_create_impl(const mp3dec_batch_stream_t *stream
     P->stats.n_tiles = tiles;
     P->stats.n_istereo_granules = ists;
     P->stats.n_frames = P->n_frames;
-    P->stats.h2d_bytes = P->md_bytes + gcs*sizeof(GcDesc) + tiles*sizeof(TileDesc) + ists*4 + orders*4 +
+    P->stats.h2d_bytes = P->md_bytes + frs*sizeof(FrameRec) + tiles*sizeof(TileDesc) + ists*4 + orders*4 +
                          l12s*sizeof(L12FrameDesc) + tiles12*sizeof(TileDesc);
     P->stats.kernels_per_run = (orders ? 1 : 0) + (ists ? 1 : 0) + (tiles ? 2 : 0) + (l12s ? 1 : 0) + (tiles12 ? 1 : 0);
     P->stats.host_parse_ms = t1 - t0;

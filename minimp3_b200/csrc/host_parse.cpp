@@ -145,130 +145,10 @@ uint32_t BitReader::get_slow(int start, int n) const
 
 /* ---- side info (minimp3.h:484-607) ------------------------------------------------------------- */
 
-int sample_rate_class(const uint8_t *hdr)
-{
-    /* MPEG-2.5: 0 (11025, 12000), 1 (8000); MPEG-2: 2, 3, 4; MPEG-1: 5, 6, 7 */
-    int version_steps = ((hdr[1] >> 3) & 1) + ((hdr[1] >> 4) & 1);
-    int idx = ((hdr[2] >> 2) & 3) + version_steps*3;
-    return idx - (idx != 0);
-}
+int sample_rate_class(const uint8_t *hdr) { return si_sample_rate_class(hdr); }
 
-int read_side_info(BitReader *bs, GranuleSide *gr, const uint8_t *hdr)
-{
-    const bool mpeg1 = hdr_is_mpeg1(hdr), mono = hdr_is_mono(hdr);
-    int entries = mono ? 1 : 2;
-    unsigned scfsi = 0;
-    int main_data_begin, part_23_sum = 0;
-
-    if (mpeg1)
-    {
-        entries *= 2;
-        main_data_begin = (int)bs->get(9);
-        /* private bits are read together with scfsi and leak into granule 0 (quirk kept on purpose) */
-        scfsi = bs->get(7 + entries);
-    } else
-    {
-        main_data_begin = (int)(bs->get(8 + entries) >> entries);
-    }
-
-    for (int e = 0; e < entries; e++, gr++)
-    {
-        if (mono) scfsi <<= 4;
-        gr->part_23_length = (uint16_t)bs->get(12);
-        part_23_sum += gr->part_23_length;
-        gr->big_values = (uint16_t)bs->get(9);
-        if (gr->big_values > 288) return -1;
-        gr->global_gain = (uint8_t)bs->get(8);
-        gr->scalefac_compress = (uint16_t)bs->get(mpeg1 ? 4 : 9);
-        gr->n_long_sfb = 22;
-        gr->n_short_sfb = 0;
-        unsigned tables;
-        if (bs->get(1))   /* window switching */
-        {
-            gr->block_type = (uint8_t)bs->get(2);
-            if (!gr->block_type) return -1;
-            gr->mixed_block_flag = (uint8_t)bs->get(1);
-            gr->region_count[0] = 7;
-            gr->region_count[1] = 255;
-            gr->region_count[2] = 0;
-            if (gr->block_type == 2)
-            {
-                scfsi &= 0x0F0F;
-                if (!gr->mixed_block_flag)
-                {
-                    gr->region_count[0] = 8;
-                    gr->n_long_sfb = 0;
-                    gr->n_short_sfb = 39;
-                } else
-                {
-                    gr->n_long_sfb = mpeg1 ? 8 : 6;
-                    gr->n_short_sfb = 30;
-                }
-            }
-            tables = bs->get(10) << 5;
-            gr->subblock_gain[0] = (uint8_t)bs->get(3);
-            gr->subblock_gain[1] = (uint8_t)bs->get(3);
-            gr->subblock_gain[2] = (uint8_t)bs->get(3);
-        } else
-        {
-            gr->block_type = 0;
-            gr->mixed_block_flag = 0;
-            tables = bs->get(15);
-            gr->region_count[0] = (uint8_t)bs->get(4);
-            gr->region_count[1] = (uint8_t)bs->get(3);
-            gr->region_count[2] = 255;
-            gr->subblock_gain[0] = gr->subblock_gain[1] = gr->subblock_gain[2] = 0;
-        }
-        gr->table_select[0] = (uint8_t)(tables >> 10);
-        gr->table_select[1] = (uint8_t)((tables >> 5) & 31);
-        gr->table_select[2] = (uint8_t)(tables & 31);
-        gr->preflag = mpeg1 ? (uint8_t)bs->get(1) : (uint8_t)(gr->scalefac_compress >= 500);
-        gr->scalefac_scale = (uint8_t)bs->get(1);
-        gr->count1_table = (uint8_t)bs->get(1);
-        gr->scfsi = (uint8_t)((scfsi >> 12) & 15);
-        scfsi <<= 4;
-    }
-    if (part_23_sum + bs->pos > bs->limit + main_data_begin*8) return -1;
-    return main_data_begin;
-}
-
-/* the header-derived part of a GcDesc, the same for every granule-channel of a frame */
-struct HdrBits
-{
-    uint8_t flags0, flags1, sr_idx;
-    HdrBits(const uint8_t *hdr, int nch)
-    {
-        const bool ms = (hdr[3] & 0xE0) == 0x60;        /* joint stereo + MS bit (HDR_IS_MS_STEREO) */
-        const bool is = (hdr[3] & 0x10) != 0;           /* HDR_TEST_I_STEREO: bit is tested whatever the mode */
-        flags0 = (uint8_t)((ms ? GCF_MS_STEREO : 0) | (is ? GCF_I_STEREO : 0));
-        flags1 = (uint8_t)((hdr_is_mpeg1(hdr) ? GCF1_MPEG1 : 0) | (nch == 2 ? GCF1_STEREO : 0) |
-                           ((ms && !is && nch == 2) ? GCF1_MS_PLAIN : 0) | ((hdr[3] & 0x20) ? GCF1_MS_TEST : 0));
-        sr_idx = (uint8_t)sample_rate_class(hdr);
-    }
-};
-
-static inline void fill_gc_desc_hb(GcDesc *d, const GranuleSide &g, const HdrBits &hb, int ch, int igr, uint64_t bit_off)
-{
-    d->bit_off = bit_off;
-    d->part_23_length = g.part_23_length;
-    d->big_values = g.big_values;
-    d->scalefac_compress = g.scalefac_compress;
-    d->global_gain = g.global_gain;
-    d->flags0 = (uint8_t)(hb.flags0 | (g.block_type & 3) | (g.mixed_block_flag ? GCF_MIXED : 0) | (g.preflag ? GCF_PREFLAG : 0) |
-                          (g.scalefac_scale ? GCF_SCALEFAC_SCALE : 0) | (g.count1_table ? GCF_COUNT1_TABLE : 0));
-    for (int i = 0; i < 3; i++)
-    {
-        d->table_select[i] = g.table_select[i];
-        d->region_count[i] = g.region_count[i];
-        d->subblock_gain[i] = g.subblock_gain[i];
-    }
-    d->scfsi = g.scfsi;
-    d->n_long_sfb = g.n_long_sfb;
-    d->n_short_sfb = g.n_short_sfb;
-    d->sr_idx = hb.sr_idx;
-    d->flags1 = (uint8_t)(hb.flags1 | (ch ? GCF1_CH : 0) | (igr ? GCF1_GR1 : 0));
-    d->pad[0] = d->pad[1] = 0;
-}
+int read_side_info(BitReader *bs, GranuleSide *gr, const uint8_t *hdr) { return read_side_info_t<true>(bs, gr, hdr); }
+int read_side_info_lite(BitReader *bs, GranuleSide *gr, const uint8_t *hdr) { return read_side_info_lite_t(bs, gr, hdr); }
 
 void fill_gc_desc(GcDesc *d, const GranuleSide &g, const uint8_t *hdr, int ch, int nch, int igr, uint64_t bit_off)
 {
@@ -277,7 +157,7 @@ void fill_gc_desc(GcDesc *d, const GranuleSide &g, const uint8_t *hdr, int ch, i
 
 /* ---- one mp3dec_decode_frame worth of parsing (minimp3.h:1713-1806) ---------------------------- */
 
-void parse_frame(SyncState *st, const uint8_t *mp3, int mp3_bytes, FrameParse *out, bool headers_only)
+void parse_frame(SyncState *st, const uint8_t *mp3, int mp3_bytes, FrameParse *out, bool headers_only, bool lite_side_info)
 {
     int i = 0, frame_size = 0;
     out->samples = 0;
@@ -350,7 +230,8 @@ void parse_frame(SyncState *st, const uint8_t *mp3, int mp3_bytes, FrameParse *o
         return;
     }
 
-    int mdb = read_side_info(&bs, out->side, hdr);
+    out->side_info = bs.buf + bs.pos/8;
+    int mdb = lite_side_info ? read_side_info_lite(&bs, out->side, hdr) : read_side_info(&bs, out->side, hdr);
     if (mdb < 0 || bs.pos > bs.limit)
     {
         st->header[0] = 0;               /* mp3dec_init: next call resyncs and clears all state */
@@ -522,13 +403,25 @@ static void build_tiles(StreamPlan *plan, int tile_granules)
  * 32 lanes of a warp run about the same number of Huffman iterations (counting sort on part_23_length). */
 static void build_order(StreamPlan *plan)
 {
+    uint32_t count[257];
+    memset(count, 0, sizeof(count));
+    if (!plan->gc_len.empty() || plan->gcs.empty())
+    {
+        /* device_side_info: lengths were kept per descriptor slot, 0xFFFF marks the padding slots */
+        const size_t n = plan->gc_len.size();
+        for (size_t i = 0; i < n; i++)
+            if (plan->gc_len[i] != 0xFFFF) count[(plan->gc_len[i] >> 4) + 1]++;
+        for (int b = 0; b < 256; b++) count[b + 1] += count[b];
+        plan->order.resize(count[256]);
+        for (size_t i = 0; i < n; i++)
+            if (plan->gc_len[i] != 0xFFFF) plan->order[count[plan->gc_len[i] >> 4]++] = (uint32_t)i;
+        return;
+    }
     const size_t n = plan->gcs.size();
     std::vector<uint8_t> real(n, 0);
     for (const GranuleRef &g : plan->granules)
         if (!g.kind)
             for (int c = 0; c < g.nch; c++) real[g.gc + c] = 1;
-    uint32_t count[257];
-    memset(count, 0, sizeof(count));
     for (size_t i = 0; i < n; i++)
         if (real[i]) count[(plan->gcs[i].part_23_length >> 4) + 1]++;
     for (int b = 0; b < 256; b++) count[b + 1] += count[b];
@@ -592,7 +485,8 @@ void walk_stream(const uint8_t *buf, size_t size, uint8_t *md_dst, uint64_t md_b
     {
         /* one allocation per array for the common constant-bit-rate case instead of log2(n) regrowths */
         const size_t guess = size/(size_t)std::max(first.frame_bytes, 96) + 8;
-        plan->gcs.reserve(guess*4);
+        if (opt.device_side_info) { plan->frame_recs.reserve(guess); plan->gc_len.reserve(guess*4); }
+        else plan->gcs.reserve(guess*4);
         plan->granules.reserve(guess*3);
     }
     SyncState st;
@@ -605,7 +499,7 @@ void walk_stream(const uint8_t *buf, size_t size, uint8_t *md_dst, uint64_t md_b
     bool pending_reset = true;           /* first decoded granule starts from zero state */
     do
     {
-        parse_frame(&st, buf, (int)std::min(size, (size_t)INT_MAX), &fp);
+        parse_frame(&st, buf, (int)std::min(size, (size_t)INT_MAX), &fp, false, opt.device_side_info);
         plan->frames++;
         if (fp.reset || fp.init_only) pending_reset = true;
         if (fp.reset) { /* reservoir emptied: earlier main data can no longer be referenced */ }
@@ -629,32 +523,61 @@ void walk_stream(const uint8_t *buf, size_t size, uint8_t *md_dst, uint64_t md_b
                 uint64_t bit = md_base_bits + start_bits;
                 const bool istereo = (fp.hdr[3] & 0x10) && fp.nch == 2;
                 const HdrBits hb(fp.hdr, fp.nch);
+                FrameRec rec;
+                bool padded = false;
                 for (int igr = 0; igr < fp.n_gr; igr++)
                 {
-                    if (fp.nch == 2 && (plan->gcs.size() & 1))
+                    if (fp.nch == 2 && (plan->n_gc & 1))
                     {
-                        /* keep stereo pairs on even indices (the entropy kernel pairs lanes 2k, 2k+1 for MS) */
-                        GcDesc pad;
-                        memset(&pad, 0, sizeof(pad));
-                        pad.flags1 = GCF1_MPEG1;
-                        plan->gcs.push_back(pad);
+                        /* keep stereo pairs on even indices (MS / intensity partners are gc ^ 1) */
+                        padded = true;
+                        if (opt.device_side_info) plan->gc_len.push_back(0xFFFF);
+                        else
+                        {
+                            GcDesc pad;
+                            memset(&pad, 0, sizeof(pad));
+                            pad.flags1 = GCF1_MPEG1;
+                            plan->gcs.push_back(pad);
+                        }
+                        plan->n_gc++;
                     }
                     GranuleRef gref;
-                    gref.gc = (uint32_t)plan->gcs.size();
+                    gref.gc = plan->n_gc;
                     gref.nch = (uint8_t)fp.nch;
                     gref.reset = pending_reset ? 1 : 0;
                     gref.kind = 0;
                     pending_reset = false;
                     plan->granules.push_back(gref);
                     if (istereo) plan->istereo_gcs.push_back(gref.gc);
+                    if (igr == 0) rec.gc_first = gref.gc;
                     for (int ch = 0; ch < fp.nch; ch++)
                     {
-                        GcDesc d;
                         const GranuleSide &g = fp.side[igr*fp.nch + ch];
-                        fill_gc_desc_hb(&d, g, hb, ch, igr, bit);
+                        if (opt.device_side_info) plan->gc_len.push_back(g.part_23_length);
+                        else
+                        {
+                            GcDesc d;
+                            fill_gc_desc_hb(&d, g, hb, ch, igr, bit);
+                            plan->gcs.push_back(d);
+                        }
                         bit += g.part_23_length;
-                        plan->gcs.push_back(d);
+                        plan->n_gc++;
                     }
+                }
+                if (opt.device_side_info)
+                {
+                    /* the GPU parses the side info itself (k_l3_side_info): hand it the bytes */
+                    rec.md_bit = md_base_bits + start_bits;
+                    memcpy(rec.hdr, fp.hdr, 4);
+                    rec.nch = (uint8_t)fp.nch;
+                    rec.n_gr = (uint8_t)fp.n_gr;
+                    memset(rec.pad, 0, sizeof(rec.pad));
+                    rec.pad[0] = padded ? 1 : 0;       /* one slot was skipped right in front of granule 0 */
+                    const size_t room = (size_t)(fp.payload + fp.payload_bytes - fp.side_info);
+                    memcpy(rec.si, fp.side_info, std::min<size_t>(32, room));
+                    if (room < 32) memset(rec.si + room, 0, 32 - room);
+                    memset(rec.pad2, 0, sizeof(rec.pad2));
+                    plan->frame_recs.push_back(rec);
                 }
                 plan->frames_decoded++;
                 if (opt.raw_frames && !plan->hz)

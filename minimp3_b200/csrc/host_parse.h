@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "l3_types.h"
+#include "l3_sideinfo.cuh"
 
 namespace mp3b {
 
@@ -66,17 +67,10 @@ struct BitReader
     }
 };
 
-/* One parsed granule-channel of side info. */
-struct GranuleSide
-{
-    uint16_t part_23_length, big_values, scalefac_compress;
-    uint8_t global_gain, block_type, mixed_block_flag, n_long_sfb, n_short_sfb;
-    uint8_t table_select[3], region_count[3], subblock_gain[3];
-    uint8_t preflag, scalefac_scale, count1_table, scfsi;
-};
-
 /* returns main_data_begin or -1 (minimp3.h:484-607) */
 int read_side_info(BitReader *bs, GranuleSide *gr, const uint8_t *hdr);
+/* same decision and bit position, only part_23_length / big_values / block_type filled in (l3_sideinfo.cuh) */
+int read_side_info_lite(BitReader *bs, GranuleSide *gr, const uint8_t *hdr);
 int sample_rate_class(const uint8_t *hdr);   /* 0..7, row of the sfb tables */
 
 /* A decoded granule of the stream in output order. */
@@ -98,7 +92,10 @@ struct StreamPlan
     uint64_t out_samples = 0;    /* samples delivered to the caller after skip/cut */
     int channels = 0, hz = 0, layer = 0, avg_bitrate_kbps = 0;
     /* device work */
-    std::vector<GcDesc> gcs;
+    std::vector<GcDesc> gcs;               /* host-side descriptors (single-frame API, CPU harness) ... */
+    std::vector<FrameRec> frame_recs;      /* ... or, with WalkOptions.device_side_info, the frames k_l3_side_info turns into them */
+    std::vector<uint16_t> gc_len;          /* device_side_info: part_23_length per descriptor slot, 0xFFFF = padding slot */
+    uint32_t n_gc = 0;                     /* descriptor slots of the stream (= gcs.size() in host mode) */
     std::vector<GranuleRef> granules;
     std::vector<TileDesc> tiles;
     std::vector<L12FrameDesc> l12_frames;  /* Layer I/II frames; block indices stream-relative */
@@ -116,6 +113,7 @@ struct WalkOptions
     bool raw_frames = false;            /* plain mp3dec_decode_frame loop: no tag skipping / VBR-tag trimming */
     bool allow_mono_stereo = false;     /* MINIMP3_ALLOW_MONO_STEREO_TRANSITION */
     int tile_granules = MP3B_TILE_GRANULES;
+    bool device_side_info = false;      /* emit FrameRec records instead of GcDesc: the GPU parses the side info */
 };
 
 /*
@@ -161,11 +159,13 @@ struct FrameParse
     bool success = false;       /* reservoir holds main_data_begin bytes (Layer III) / payload not overrun (I/II) */
     GranuleSide side[4];
     const uint8_t *hdr = nullptr;
+    const uint8_t *side_info = nullptr; /* first byte of the side info (behind header and CRC) */
 };
 
 /* One mp3dec_decode_frame call worth of parsing (no PCM).  Updates st->header/free_format_bytes and, for
  * Layer III, st->reserv exactly as L3_restore_reservoir / L3_save_reservoir would. */
-void parse_frame(SyncState *st, const uint8_t *mp3, int mp3_bytes, FrameParse *out, bool headers_only = false);
+void parse_frame(SyncState *st, const uint8_t *mp3, int mp3_bytes, FrameParse *out, bool headers_only = false,
+                 bool lite_side_info = false);
 
 void fill_gc_desc(GcDesc *d, const GranuleSide &g, const uint8_t *hdr, int ch, int nch, int igr, uint64_t bit_off);
 

@@ -90,6 +90,8 @@ void tables_free(DeviceTables *t);
 
 cudaError_t launch_entropy(const DeviceTables &t, const EntropyArgs &a, cudaStream_t s);
 cudaError_t launch_intensity_stereo(const DeviceTables &t, const StereoArgs &a, cudaStream_t s);
+/* Layer III side info of n_frames frames -> their GcDesc records (k_sideinfo.cu) */
+cudaError_t launch_side_info(const FrameRec *frames, uint32_t n_frames, GcDesc *gcs, cudaStream_t s);
 cudaError_t launch_transform(const DeviceTables &t, const TransformArgs &a, cudaStream_t s);
 cudaError_t launch_l12_dequant(const Layer12Args &a, cudaStream_t s);
 cudaError_t launch_l12_synth(const DeviceTables &t, const Synth12Args &a, cudaStream_t s);

@@ -95,6 +95,19 @@ typedef struct
     uint8_t  pad2[256 - MP3B_TILE_SLOTS*8 - 16];
 } TileRec;
 
+/* One decodable Layer III frame as the walker hands it to k_l3_side_info: the raw side-info bytes and where its
+ * descriptors and its main data go.  Granule 0 of the frame owns descriptors gc_first .. gc_first+nch-1,
+ * granule 1 (MPEG-1) the next nch. */
+typedef struct
+{
+    uint64_t md_bit;             /* absolute bit offset of the frame's main data in the main-data buffer */
+    uint32_t gc_first;
+    uint8_t  hdr[4];
+    uint8_t  nch, n_gr, pad[6];
+    uint8_t  si[32];             /* side info as it follows the header (and the optional CRC) */
+    uint8_t  pad2[8];
+} FrameRec;
+
 
 /* One Layer I / II frame (minimp3.h:1783-1802): payload position + header; its output is n_blocks blocks of
  * 12 time slots x 32 subbands per channel in the subband buffer sub12[block-channel][12][32]. */

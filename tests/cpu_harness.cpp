@@ -48,6 +48,7 @@ static void ensure_tables()
 extern "C" {
 
 int h_sizeof_gcdesc() { return (int)sizeof(GcDesc); }
+int h_sizeof_framerec() { return (int)sizeof(FrameRec); }
 int h_sizeof_tiledesc() { return (int)sizeof(TileDesc); }
 
 /* scalars: [0] ret [1] samples_decoded [2] out_skip [3] out_samples [4] channels [5] hz [6] layer
@@ -77,6 +78,43 @@ int h_walk(const uint8_t *buf, size_t size, int raw, int allow, GcDesc *gcs_out,
         }
     if (md_out) memcpy(md_out, md.data(), size + 16);
     return 0;
+}
+
+/* The walker in device_side_info mode + the GPU's descriptor builder (frame_descs, l3_sideinfo.cuh) run on the host:
+ * gcs_out receives what k_l3_side_info would write, order_out the lane order.  scalars as h_walk (n_gc in [11]). */
+int h_walk_frame_recs(const uint8_t *buf, size_t size, int raw, int allow, GcDesc *gcs_out, int gcs_cap, uint32_t *order_out,
+                      int order_cap, int64_t *scalars)
+{
+    StreamPlan plan;
+    WalkOptions opt;
+    opt.raw_frames = raw != 0;
+    opt.allow_mono_stereo = allow != 0;
+    opt.device_side_info = true;
+    std::vector<uint8_t> md(size + 64, 0);
+    walk_stream(buf, size, md.data(), 0, opt, &plan);
+    scalars[0] = plan.ret; scalars[1] = (int64_t)plan.samples_decoded; scalars[2] = (int64_t)plan.out_skip;
+    scalars[3] = (int64_t)plan.out_samples; scalars[4] = plan.channels; scalars[5] = plan.hz; scalars[6] = plan.layer;
+    scalars[7] = plan.avg_bitrate_kbps; scalars[8] = (int64_t)plan.main_data_bytes; scalars[9] = plan.frames;
+    scalars[10] = plan.frames_decoded; scalars[11] = (int64_t)plan.n_gc; scalars[12] = (int64_t)plan.tiles.size();
+    scalars[13] = (int64_t)plan.granules.size(); scalars[14] = (int64_t)plan.istereo_gcs.size();
+    if (!plan.gcs.empty() || plan.gc_len.size() != plan.n_gc) return -1;
+    for (const FrameRec &fr : plan.frame_recs)
+    {
+        GcDesc d[4];
+        const int n = frame_descs(fr, d);
+        if (n != fr.n_gr*fr.nch) return -2;
+        for (int k = 0; k < n; k++)
+            if ((int)(fr.gc_first + k) < gcs_cap) gcs_out[fr.gc_first + k] = d[k];
+        if (fr.pad[0] && (int)fr.gc_first - 1 < gcs_cap)
+        {
+            GcDesc pad;
+            memset(&pad, 0, sizeof(pad));
+            pad.flags1 = GCF1_MPEG1;
+            gcs_out[fr.gc_first - 1] = pad;
+        }
+    }
+    if (order_out) for (size_t i = 0; i < plan.order.size() && (int)i < order_cap; i++) order_out[i] = plan.order[i];
+    return (int)plan.order.size();
 }
 
 /* the per-lane entropy decode, one granule-channel after the other */

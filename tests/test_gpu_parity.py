@@ -346,3 +346,19 @@ def test_fuzzed_batch_decodes_without_faults(m, ref):
         else:
             close += 1
     assert close >= len(datas)*0.8
+
+
+@pytest.mark.parametrize("name", L3_CONFORMANCE)
+def test_device_side_info_matches_host_parse(name, m):
+    """the descriptors k_l3_side_info builds on the GPU from the raw side-info bytes are byte for byte
+    those of the full host parse (tests/harness.py walks the stream with the host-side reader)."""
+    import harness
+    data = load_vector(name)
+    want = np.ascontiguousarray(harness.walk(data, raw=True)["gcs"])
+    p = m.BatchPlan([data], raw_frames=True)
+    p.run()
+    p.sync()
+    desc = np.ascontiguousarray(p.read_tap(4))
+    p.close()
+    assert len(desc) >= len(want) and len(want) > 0
+    assert desc[:len(want)].tobytes() == want.tobytes()

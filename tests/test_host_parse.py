@@ -180,7 +180,45 @@ def test_fuzzed_streams_walk_like_the_reference(ref):
             b = bytearray(base[int(rng.integers(0, 3000)):])
         data = bytes(b)
         ret, pcm, info = ref.load_buf(data)
-        wi = harness.walk(data)["info"]
+        w = harness.walk(data)
+        wi = w["info"]
         assert (wi["ret"], wi["out_samples"]) == (ret, len(pcm)), (t, kind)
         if len(pcm):
             assert (wi["hz"], wi["channels"]) == (info["hz"], info["channels"]), (t, kind)
+        # the batch path's walker (lite side info + frame records) keeps the same frames and builds the same records
+        import ctypes as C
+        L = harness.lib()
+        L.h_walk_frame_recs.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+        n = len(w["gcs"])
+        gcs = np.zeros(max(1, n), harness.GCDESC_DTYPE)
+        sc = np.zeros(16, np.int64)
+        buf = np.frombuffer(data, dtype=np.uint8) if len(data) else np.zeros(1, np.uint8)
+        assert L.h_walk_frame_recs(buf.ctypes.data, len(data), 0, 0, gcs.ctypes.data, n, None, 0, sc.ctypes.data) >= 0
+        assert [int(v) for v in sc[:15]] == list(wi.values()), (t, kind)
+        assert gcs[:n].tobytes() == np.ascontiguousarray(w["gcs"]).tobytes(), (t, kind)
+
+
+@pytest.mark.parametrize("name", L3_CONFORMANCE + ["l3-nonstandard-big-iscf", "l3-nonstandard-compl-sideinfo-bigvalues",
+                                                   "l3-nonstandard-compl-sideinfo-blocktype", "l3-nonstandard-sideinfo-size"])
+def test_frame_records_give_the_same_descriptors(name):
+    """in the batch path the walker reads only a third of the side info (read_side_info_lite_t) and hands
+    the raw bytes to the GPU; the descriptors k_l3_side_info builds from them (same code, run on the host here), the
+    bookkeeping and the lane order must be exactly those of the full host parse."""
+    import ctypes as C
+    data = load_vector(name)
+    for raw in (0, 1):
+        w = harness.walk(data, raw=bool(raw), allow=True)
+        L = harness.lib()
+        L.h_walk_frame_recs.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+        assert L.h_sizeof_framerec() == 64
+        buf = np.frombuffer(data, dtype=np.uint8)
+        n = len(w["gcs"])
+        gcs = np.zeros(max(1, n), harness.GCDESC_DTYPE)
+        order = np.zeros(max(1, n), np.uint32)
+        sc = np.zeros(16, np.int64)
+        n_order = L.h_walk_frame_recs(buf.ctypes.data, len(data), raw, 1, gcs.ctypes.data, n, order.ctypes.data, n, sc.ctypes.data)
+        assert n_order >= 0
+        keys = ["ret", "samples_decoded", "out_skip", "out_samples", "channels", "hz", "layer", "avg_bitrate_kbps",
+                "main_data_bytes", "frames", "frames_decoded", "n_gc", "n_tiles", "n_granules", "n_istereo"]
+        assert {k: int(sc[i]) for i, k in enumerate(keys)} == w["info"]
+        assert gcs[:n].tobytes() == np.ascontiguousarray(w["gcs"]).tobytes()
