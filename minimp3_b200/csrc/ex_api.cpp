@@ -1,6 +1,7 @@
 /*
- * ex_api.cpp -- the iterate / streaming / seek entry points of minimp3_ex.h on top of this library's frame API
- * (every PCM sample still comes out of the CUDA kernels through mp3dec_decode_frame).
+ * ex_api.cpp -- the iterate / streaming / seek entry points of minimp3_ex.h on top of this library's batch and frame
+ * APIs (every PCM sample comes out of the CUDA kernels: look-ahead windows through mp3dec_decode_batch_cuda, single
+ * frames through mp3dec_decode_frame).
  *
  * Host control logic restated from /root/reference/minimp3_ex.h: mp3dec_iterate_buf (:527-564),
  * mp3dec_load_index (:641-698), mp3dec_ex_open_buf (:700-717), mp3dec_ex_seek incl. the bit-reservoir pre-roll
@@ -14,6 +15,9 @@
 #include <string.h>
 
 #include <algorithm>
+#include <mutex>
+#include <unordered_map>
+#include <vector>
 
 #include "host_parse.h"
 
@@ -133,10 +137,13 @@ size_t idx_search(mp3dec_index_t *idx, uint64_t position)   /* minimp3_ex.h:720-
     return index;
 }
 
+void drop_window(const void *owner);
+
 template <class S>
 int ex_open_buf(ExT<S> *dec, const uint8_t *buf, size_t buf_size, int flags)
 {
     if (!dec || !buf || (size_t)-1 == buf_size || (flags & (~MP3D_FLAGS_MASK))) return MP3D_E_PARAM;
+    drop_window(dec);            /* the object may be reused without a close */
     memset(dec, 0, sizeof(*dec));
     dec->file.buffer = buf;
     dec->file.size = buf_size;
@@ -231,6 +238,170 @@ do_exit:
     return 0;
 }
 
+
+/* ---- look-ahead windows for the streaming API ---------------------------------------------------------------
+ * mp3dec_ex_read* decodes frame after frame from dec->offset, always starting from a freshly initialised decoder
+ * (open and every seek end in mp3dec_init, minimp3_ex.h:717, 892).  Instead of one GPU round trip per frame, the
+ * frames of a window are decoded in ONE batch call in raw-frame mode -- which is defined as exactly that frame
+ * loop -- and handed out one by one.  When a window is used up the next one starts kPreroll frames early with a
+ * fresh decoder and drops their output: the overlap / synthesis state of the decoder only reaches one granule
+ * back and the bit reservoir at most 511 bytes, so from there on the samples are those of the uninterrupted loop
+ * (the same argument the reference's own seek relies on, minimp3_ex.h:826-871). */
+struct WindowFrame
+{
+    uint64_t off;               /* file offset the frame call starts at */
+    mp3dec_frame_info_t info;   /* what mp3dec_decode_frame reports for it */
+    int samples;                /* per channel, 0 if nothing was produced */
+    bool found;                 /* false: no frame in the rest of the input, only info.frame_bytes is reported */
+    size_t pcm_pos;             /* first sample in the window's PCM */
+};
+
+struct Window
+{
+    std::vector<WindowFrame> frames;
+    void *pcm = nullptr;        /* malloc()ed by the batch call */
+    size_t next = 0;            /* next frame to hand out */
+    ~Window() { free(pcm); }
+};
+
+constexpr size_t kPreroll = 16;
+
+/* frames per window; MP3B_DEBUG_WINDOW_FRAMES shrinks it so that tests cross many window boundaries */
+size_t window_frames()
+{
+    const char *e = getenv("MP3B_DEBUG_WINDOW_FRAMES");
+    const long v = e ? atol(e) : 0;
+    return v > 0 ? (size_t)v : (size_t)4096;
+}
+
+std::mutex g_win_mu;
+std::unordered_map<const void *, Window *> g_windows;
+
+void drop_window(const void *owner)
+{
+    std::lock_guard<std::mutex> lock(g_win_mu);
+    auto it = g_windows.find(owner);
+    if (it != g_windows.end()) { delete it->second; g_windows.erase(it); }
+}
+
+Window *find_window(const void *owner)
+{
+    std::lock_guard<std::mutex> lock(g_win_mu);
+    auto it = g_windows.find(owner);
+    return it == g_windows.end() ? nullptr : it->second;
+}
+
+/* decodes the frames of buf[start, end) that a fresh decoder would, at most max_frames of them */
+template <class S>
+Window *build_window(const uint8_t *buf, uint64_t start, uint64_t end, size_t max_frames)
+{
+    Window *w = new Window();
+    SyncState st;
+    FrameParse fp;
+    memset(&fp.info, 0, sizeof(fp.info));
+    uint64_t off = start;
+    size_t pcm_pos = 0;
+    while (off < end && w->frames.size() < max_frames)
+    {
+        parse_frame(&st, buf + off, (int)std::min<uint64_t>(end - off, (uint64_t)INT_MAX), &fp);
+        if (!fp.info.frame_bytes) break;
+        WindowFrame f;
+        f.off = off;
+        f.info.frame_bytes = fp.info.frame_bytes; f.info.frame_offset = fp.info.frame_offset;
+        f.info.channels = fp.info.channels; f.info.hz = fp.info.hz; f.info.layer = fp.info.layer;
+        f.info.bitrate_kbps = fp.info.bitrate_kbps;
+        f.samples = fp.samples;
+        f.found = fp.hdr != nullptr;
+        f.pcm_pos = pcm_pos;
+        pcm_pos += (size_t)fp.samples*(size_t)fp.info.channels;
+        w->frames.push_back(f);
+        off += (uint64_t)fp.info.frame_bytes;
+    }
+    if (w->frames.empty()) { delete w; return nullptr; }
+    mp3dec_batch_stream_t s = { buf + start, (size_t)(off - start) };
+    mp3dec_batch_opts_t o;
+    memset(&o, 0, sizeof(o));
+    o.float_output = sizeof(S) == 4;
+    o.raw_frames = 1;
+    o.output = MP3D_BATCH_OUT_MALLOC;
+    o.host_threads = 1;
+    mp3dec_file_info_t fi;
+    memset(&fi, 0, sizeof(fi));
+    int ret = 0;
+    if (mp3dec_decode_batch_cuda(&s, 1, &fi, &ret, &o) || ret || fi.samples != pcm_pos)
+    {
+        free(fi.buffer);
+        delete w;
+        return nullptr;       /* caller falls back to the frame-by-frame path */
+    }
+    w->pcm = fi.buffer;
+    return w;
+}
+
+/* mp3dec_decode_frame(&dec->mp3d, file + dec->offset, ...) served from a look-ahead window */
+template <class S>
+int window_decode_frame(ExT<S> *dec, uint64_t end_offset, S *pcm, mp3dec_frame_info_t *info)
+{
+    const uint8_t *buf = dec->file.buffer;
+    Window *w = find_window(dec);
+    const bool fresh = dec->mp3d.header[0] == 0;      /* mp3dec_init since the last frame: open or seek */
+    if (w && !fresh && w->next < w->frames.size() && w->frames[w->next].off == dec->offset)
+    {
+        /* the usual case: the next frame of the window */
+    } else if (w && !fresh && w->next == w->frames.size() && w->next > 0 &&
+               w->frames.back().off + (uint64_t)w->frames.back().info.frame_bytes == dec->offset)
+    {
+        /* window used up: the next one re-decodes the last kPreroll frames for the decoder state */
+        const size_t back = std::min(kPreroll, w->frames.size());
+        const uint64_t restart = w->frames[w->frames.size() - back].off;
+        Window *nw = build_window<S>(buf, restart, end_offset, window_frames() + back);
+        drop_window(dec);
+        w = nullptr;
+        if (nw)
+        {
+            size_t k = 0;
+            while (k < nw->frames.size() && nw->frames[k].off < dec->offset) k++;
+            if (k < nw->frames.size() && nw->frames[k].off == dec->offset)
+            {
+                nw->next = k;
+                std::lock_guard<std::mutex> lock(g_win_mu);
+                g_windows[dec] = nw;
+                w = nw;
+            } else
+                delete nw;
+        }
+    } else
+    {
+        /* fresh decoder (or a position the window does not cover): new window from here */
+        drop_window(dec);
+        w = nullptr;
+        if (fresh)
+        {
+            Window *nw = build_window<S>(buf, dec->offset, end_offset, window_frames());
+            if (nw)
+            {
+                std::lock_guard<std::mutex> lock(g_win_mu);
+                g_windows[dec] = nw;
+                w = nw;
+            }
+        }
+    }
+    if (!w || w->next >= w->frames.size())
+    {
+        /* no window: one frame through the GPU frame API, state in dec->mp3d as usual */
+        drop_window(dec);
+        return decode_frame(&dec->mp3d, buf + dec->offset, (int)std::min<uint64_t>(end_offset - dec->offset, (uint64_t)INT_MAX), pcm, info);
+    }
+    const WindowFrame &f = w->frames[w->next++];
+    if (f.found) *info = f.info;
+    else info->frame_bytes = f.info.frame_bytes;      /* mp3dec_decode_frame leaves the other fields alone (minimp3.h:1736-1740) */
+    if (f.samples)
+        memcpy(pcm, (const S *)w->pcm + f.pcm_pos, (size_t)f.samples*(size_t)f.info.channels*sizeof(S));
+    /* the decoder is no longer "fresh"; its carried state lives in the window, not in dec->mp3d */
+    dec->mp3d.header[0] = 0xff;
+    return f.samples;
+}
+
 template <class S>
 size_t ex_read_frame(ExT<S> *dec, S **buf, mp3dec_frame_info_t *frame_info, size_t max_samples)
 {
@@ -248,7 +419,7 @@ size_t ex_read_frame(ExT<S> *dec, S **buf, mp3dec_frame_info_t *frame_info, size
         const uint8_t *dec_buf = dec->file.buffer + dec->offset;
         uint64_t buf_size = end_offset - dec->offset;
         if (!buf_size) return 0;
-        dec->buffer_samples = decode_frame(&dec->mp3d, dec_buf, (int)std::min<uint64_t>(buf_size, (uint64_t)INT_MAX), dec->buffer, frame_info);
+        dec->buffer_samples = window_decode_frame(dec, end_offset, dec->buffer, frame_info);
         dec->buffer_consumed = 0;
         if (dec->info.hz != frame_info->hz || dec->info.layer != frame_info->layer)
         {
@@ -313,6 +484,7 @@ template <class S>
 void ex_close(ExT<S> *dec)
 {
     if (!dec) return;
+    drop_window(dec);
     if (dec->is_file && dec->file.buffer) free((void *)dec->file.buffer);
     if (dec->index.frames) free(dec->index.frames);
     memset(dec, 0, sizeof(*dec));

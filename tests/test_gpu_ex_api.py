@@ -164,3 +164,33 @@ def test_plain_c_batch_caller(tmp_path, manifest):
         mf = manifest[n]
         assert int(kv["ret"]) == mf["load_ret"] and int(kv["samples"]) == mf["load_samples"] and int(kv["rate"]) == mf["hz"]
     assert lines[0].split()[1:] == lines[3].split()[1:]          # the same file twice decodes to the same PCM
+
+
+@pytest.mark.parametrize("name,window", [("l3-compl", 7), ("l3-he_mode", 20), ("l3-sin1k0db", 33), ("M2L3_bitrate_16_all", 16),
+                                         ("l2-fl10", 5), ("l3-test45", 50)])
+def test_streaming_across_look_ahead_windows(name, window, m, ref, monkeypatch):
+    """mp3dec_ex_read decodes look-ahead windows in one batch each; a window that starts mid-stream re-decodes 16
+    frames for the decoder state.  With tiny windows (many boundaries) the stream is still the reference's."""
+    monkeypatch.setenv("MP3B_DEBUG_WINDOW_FRAMES", str(window))
+    data = load_vector(name)
+    for portion in (1000, 1152, 3463):          # the reference's end-of-stream error depends on how reads align with frames
+        want, tot_r, oret_r, lerr_r, ch_r, hz_r = ref_ex(ref, data, SEEK_TO_SAMPLE | ALLOW_TRANSITION, 0, portion)
+        got, tot, oret, lerr, ch, hz = our_ex(m, data, SEEK_TO_SAMPLE | ALLOW_TRANSITION, 0, portion)
+        assert (tot, oret, lerr, ch, hz) == (tot_r, oret_r, lerr_r, ch_r, hz_r) and len(got) == len(want), portion
+        assert np.abs(got.astype(np.int32) - want.astype(np.int32)).max() <= 1
+    # and after a seek into the middle
+    pos = (len(want)//3) & ~1
+    want2 = ref_ex(ref, data, SEEK_TO_SAMPLE | ALLOW_TRANSITION, pos, 777)[0]
+    got2 = our_ex(m, data, SEEK_TO_SAMPLE | ALLOW_TRANSITION, pos, 777)[0]
+    assert len(got2) == len(want2) and np.abs(got2.astype(np.int32) - want2.astype(np.int32)).max() <= 1
+
+
+def test_streaming_speed_uses_windows(m):
+    """whole-stream read through mp3dec_ex_read: far less than one GPU round trip (~50 us) per frame"""
+    import time
+    data = load_vector("l3-sin1k0db")
+    our_ex(m, data, SEEK_TO_SAMPLE, 0, 4096)
+    t0 = time.perf_counter()
+    got = our_ex(m, data, SEEK_TO_SAMPLE, 0, 4096)[0]
+    dt = time.perf_counter() - t0
+    assert len(got) == 725760 and dt < 0.010*3, dt
