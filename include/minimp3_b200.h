@@ -76,8 +76,8 @@ void mp3dec_f32_to_s16(const float *in, int16_t *out, int num_samples);   /* min
 /* ---- whole-buffer API: minimp3_ex.h:98,101 ----------------------------------------------------- */
 int mp3dec_detect_buf(const uint8_t *buf, size_t buf_size);
 /* info->buffer is malloc()ed, caller free()s (README.md:258-259).  Without progress_cb the stream is decoded as
- * one GPU batch; with progress_cb (minimp3_ex.h:52, 504-509) it is decoded frame by frame so that the callback sees
- * every decoded frame in order and a non-zero return stops the decode and is returned. */
+ * one GPU batch; with progress_cb (minimp3_ex.h:52, 504-509) the frames come out of look-ahead windows so that the
+ * callback sees every decoded frame in order and a non-zero return stops the load and is returned. */
 int mp3dec_load_buf(mp3dec_t *dec, const uint8_t *buf, size_t buf_size, mp3dec_file_info_t *info, MP3D_PROGRESS_CB progress_cb, void *user_data);
 #ifndef MINIMP3_FLOAT_OUTPUT
 int mp3dec_load_buf_f32(mp3dec_t *dec, const uint8_t *buf, size_t buf_size, mp3dec_file_info_t *info, MP3D_PROGRESS_CB progress_cb, void *user_data);

@@ -603,17 +603,24 @@ int load_buf_frames(mp3dec_t *dec, const uint8_t *buf, size_t buf_size, mp3dec_f
     info->layer = fi.layer;
     size_t n_samples = 0, avg_kbps = 0, frames = 0;
     int ret = 0;
+    /* the frames come out of look-ahead windows (one GPU batch per 4096 frames), the callback still sees them one
+     * by one: a cancelled load has merely decoded a little ahead */
+    ExT<S> *reader = (ExT<S> *)calloc(1, sizeof(ExT<S>));
+    if (!reader) { free(out); return MP3D_E_MEMORY; }
+    reader->file.buffer = buf;
+    reader->file.size = buf_size;
+    const uint64_t stream_end = buf_size;
     do
     {
         if (allocated - n_samples*sizeof(S) < MINIMP3_MAX_SAMPLES_PER_FRAME*sizeof(S))
         {
             allocated *= 2;
             S *grown = (S *)realloc(out, allocated);
-            if (!grown) { free(out); return MP3D_E_MEMORY; }
+            if (!grown) { free(out); drop_window(reader); free(reader); return MP3D_E_MEMORY; }
             out = grown;
         }
-        size_t samples = (size_t)decode_frame(dec, buf, (int)std::min(buf_size, (size_t)INT_MAX), out + n_samples, &fi);
-        buf += fi.frame_bytes;
+        size_t samples = (size_t)window_decode_frame(reader, stream_end, out + n_samples, &fi);
+        reader->offset += (uint64_t)fi.frame_bytes;
         buf_size -= fi.frame_bytes;
         if (samples)
         {
@@ -634,6 +641,9 @@ int load_buf_frames(mp3dec_t *dec, const uint8_t *buf, size_t buf_size, mp3dec_f
             if (ret) break;
         }
     } while (fi.frame_bytes);
+    drop_window(reader);
+    free(reader);
+    (void)dec;
     if (detected_samples && n_samples > detected_samples) n_samples = (size_t)detected_samples;
     if (allocated != n_samples*sizeof(S))
     {
