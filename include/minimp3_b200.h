@@ -65,8 +65,10 @@ extern "C" {
 
 /* ---- frame API: minimp3.h:29-36 ------------------------------------------------------------- */
 void mp3dec_init(mp3dec_t *dec);
-/* returns samples per channel (0 / 576 / 1152); info->frame_bytes = bytes to drop.  pcm may be NULL
- * (parse only).  Layers I, II and III are all decoded on the GPU. */
+/* returns samples per channel (0 / 384 / 576 / 1152); info->frame_bytes = bytes to drop.  pcm may be NULL
+ * (parse only).  Layers I, II and III are all decoded on the GPU.  A freshly initialised decoder that is handed a
+ * buffer with many frames decodes them as one look-ahead window; calls that continue where the previous frame ended
+ * are answered from it (MP3B_FRAME_LOOKAHEAD=0 turns this off). */
 int mp3dec_decode_frame(mp3dec_t *dec, const uint8_t *mp3, int mp3_bytes, mp3d_sample_t *pcm, mp3dec_frame_info_t *info);
 #ifndef MINIMP3_FLOAT_OUTPUT
 int mp3dec_decode_frame_f32(mp3dec_t *dec, const uint8_t *mp3, int mp3_bytes, float *pcm, mp3dec_frame_info_t *info);

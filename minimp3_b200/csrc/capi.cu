@@ -1063,14 +1063,28 @@ static int decode_frame_impl(mp3dec_t *dec, const uint8_t *mp3, int mp3_bytes, v
     return result;
 }
 
+/* one frame, one GPU round trip, state in *dec (what the look-ahead layer in ex_api.cpp falls back to) */
+__attribute__((visibility("hidden"))) int mp3dec_decode_frame_direct(mp3dec_t *dec, const uint8_t *mp3, int mp3_bytes, void *pcm,
+                                                                     mp3dec_frame_info_t *info, int float_output)
+{
+    return decode_frame_impl(dec, mp3, mp3_bytes, pcm, info, float_output);
+}
+
+/* csrc/ex_api.cpp: serves the call from a look-ahead window when the caller walks a buffer frame by frame;
+ * returns -1 when the call has to go through the direct path */
+__attribute__((visibility("hidden"))) int mp3dec_frame_lookahead(mp3dec_t *dec, const uint8_t *mp3, int mp3_bytes, void *pcm,
+                                                                 mp3dec_frame_info_t *info, int float_output);
+
 int mp3dec_decode_frame(mp3dec_t *dec, const uint8_t *mp3, int mp3_bytes, int16_t *pcm, mp3dec_frame_info_t *info)
 {
-    return decode_frame_impl(dec, mp3, mp3_bytes, pcm, info, 0);
+    const int n = mp3dec_frame_lookahead(dec, mp3, mp3_bytes, pcm, info, 0);
+    return n >= 0 ? n : decode_frame_impl(dec, mp3, mp3_bytes, pcm, info, 0);
 }
 
 int mp3dec_decode_frame_f32(mp3dec_t *dec, const uint8_t *mp3, int mp3_bytes, float *pcm, mp3dec_frame_info_t *info)
 {
-    return decode_frame_impl(dec, mp3, mp3_bytes, pcm, info, 1);
+    const int n = mp3dec_frame_lookahead(dec, mp3, mp3_bytes, pcm, info, 1);
+    return n >= 0 ? n : decode_frame_impl(dec, mp3, mp3_bytes, pcm, info, 1);
 }
 
 }  // extern "C"

@@ -26,6 +26,8 @@
 using namespace mp3b;
 
 extern "C" int mp3dec_decode_frame_f32(mp3dec_t *dec, const uint8_t *mp3, int mp3_bytes, float *pcm, mp3dec_frame_info_t *info);
+extern "C" __attribute__((visibility("hidden"))) int mp3dec_decode_frame_direct(mp3dec_t *dec, const uint8_t *mp3, int mp3_bytes, void *pcm,
+                                                                                mp3dec_frame_info_t *info, int float_output);
 
 namespace {
 
@@ -47,13 +49,14 @@ struct ExT   /* mp3dec_ex_t with sample type S (minimp3_ex.h:74-88) */
 };
 static_assert(sizeof(ExT<int16_t>) == sizeof(mp3dec_ex_t), "mp3dec_ex_t layout");
 
+/* the streaming API keeps its own look-ahead windows: its single-frame calls go straight to the GPU frame path */
 inline int decode_frame(mp3dec_t *d, const uint8_t *p, int n, int16_t *pcm, mp3dec_frame_info_t *info)
 {
-    return mp3dec_decode_frame(d, p, n, pcm, info);
+    return mp3dec_decode_frame_direct(d, p, n, pcm, info, 0);
 }
 inline int decode_frame(mp3dec_t *d, const uint8_t *p, int n, float *pcm, mp3dec_frame_info_t *info)
 {
-    return mp3dec_decode_frame_f32(d, p, n, pcm, info);
+    return mp3dec_decode_frame_direct(d, p, n, pcm, info, 1);
 }
 
 void fill_info(mp3dec_frame_info_t *fi, const uint8_t *hdr, int frame_size)
@@ -402,6 +405,190 @@ int window_decode_frame(ExT<S> *dec, uint64_t end_offset, S *pcm, mp3dec_frame_i
     return f.samples;
 }
 
+
+/* ---- look-ahead for the plain frame loop ---------------------------------------------------------------------
+ * The README loop -- mp3dec_init, then mp3dec_decode_frame(dec, p, left, pcm, &info); p += info.frame_bytes -- costs
+ * one GPU round trip per frame when taken literally.  When a freshly initialised decoder is handed a buffer with
+ * many frames, they are decoded as one window (same machinery as the streaming API) and the following calls are
+ * answered from it, as long as each call continues exactly where the previous frame ended, with the same bytes and
+ * the same remaining length.  Anything else -- another buffer, a shorter length, a parse-only call, the end of the
+ * input -- first brings the caller's mp3dec_t up to date by replaying the last kPreroll frames from a private copy
+ * of the input through the one-frame path, then continues there.  MP3B_FRAME_LOOKAHEAD=0 switches the layer off. */
+struct FrameLook
+{
+    Window *w = nullptr;
+    std::vector<uint8_t> bytes;      /* private copy of the window's input */
+    const uint8_t *caller_base = nullptr;   /* caller address of bytes[0] */
+    uint64_t caller_end = 0;         /* bytes from caller_base to the end of the caller's buffer */
+    int float_output = 0;
+    uint64_t stamp = 0;
+    mp3dec_t saved;                  /* w == nullptr: the decoder state the window had reached when it was retired */
+    ~FrameLook() { delete w; }
+};
+
+std::mutex g_look_mu;
+std::unordered_map<const mp3dec_t *, FrameLook *> g_looks;
+uint64_t g_look_stamp = 0;
+constexpr size_t kMaxLooks = 16;      /* windows alive at once (~20 MB each) */
+constexpr size_t kMaxSaved = 4096;    /* retired windows: saved decoder states */
+constexpr int kMinLookBytes = 16384;
+
+bool lookahead_enabled()
+{
+    static const bool on = [] { const char *e = getenv("MP3B_FRAME_LOOKAHEAD"); return !(e && e[0] == '0'); }();
+    return on;
+}
+
+FrameLook *take_look(const mp3dec_t *dec)
+{
+    std::lock_guard<std::mutex> lock(g_look_mu);
+    auto it = g_looks.find(dec);
+    if (it == g_looks.end()) return nullptr;
+    FrameLook *l = it->second;
+    g_looks.erase(it);
+    return l;
+}
+
+void replay_into(mp3dec_t *dec, const FrameLook *l);
+
+void put_look(const mp3dec_t *dec, FrameLook *l)
+{
+    std::lock_guard<std::mutex> lock(g_look_mu);
+    l->stamp = ++g_look_stamp;
+    size_t live = 0;
+    for (auto &kv : g_looks) live += kv.second->w != nullptr;
+    if (live >= kMaxLooks)
+    {   /* too many decoders mid-stream: the one idle for longest keeps only its state (7 KB), not its window */
+        FrameLook *old = nullptr;
+        for (auto &kv : g_looks)
+            if (kv.second->w && (!old || kv.second->stamp < old->stamp)) old = kv.second;
+        if (old)
+        {
+            replay_into(&old->saved, old);
+            delete old->w;
+            old->w = nullptr;
+            std::vector<uint8_t>().swap(old->bytes);
+        }
+    }
+    if (g_looks.size() >= kMaxSaved)
+    {   /* abandoned long ago */
+        auto oldest = g_looks.begin();
+        for (auto it = g_looks.begin(); it != g_looks.end(); ++it)
+            if (it->second->stamp < oldest->second->stamp) oldest = it;
+        delete oldest->second;
+        g_looks.erase(oldest);
+    }
+    g_looks[dec] = l;
+}
+
+/* bring *dec to the state it has after the frames handed out so far: fresh decoder + the last kPreroll of them */
+void replay_into(mp3dec_t *dec, const FrameLook *l)
+{
+    const Window *w = l->w;
+    mp3dec_init(dec);
+    if (!w->next) return;
+    const size_t first = w->next > kPreroll ? w->next - kPreroll : 0;
+    static thread_local float scratch[MINIMP3_MAX_SAMPLES_PER_FRAME];
+    const uint64_t base = w->frames[0].off;
+    for (size_t k = first; k < w->next; k++)
+    {
+        mp3dec_frame_info_t fi;
+        memset(&fi, 0, sizeof(fi));
+        const uint64_t off = w->frames[k].off - base;
+        mp3dec_decode_frame_direct(dec, l->bytes.data() + off, (int)std::min<uint64_t>(l->bytes.size() - off, (uint64_t)INT_MAX),
+                                   scratch, &fi, l->float_output);
+    }
+}
+
+template <class S>
+FrameLook *start_look(const uint8_t *mp3, int mp3_bytes, const uint8_t *preroll, size_t preroll_bytes)
+{
+    /* window input = [frames to re-decode for the state] + [the caller's buffer]; only the extent of the frames
+     * that end up in the window is kept */
+    std::vector<uint8_t> in(preroll_bytes + (size_t)mp3_bytes);
+    if (preroll_bytes) memcpy(in.data(), preroll, preroll_bytes);
+    memcpy(in.data() + preroll_bytes, mp3, (size_t)mp3_bytes);
+    Window *w = build_window<S>(in.data(), 0, in.size(), window_frames() + kPreroll);
+    if (!w) return nullptr;
+    size_t k = 0;
+    while (k < w->frames.size() && w->frames[k].off < preroll_bytes) k++;
+    if (k >= w->frames.size() || w->frames[k].off != preroll_bytes) { delete w; return nullptr; }
+    w->next = k;
+    FrameLook *l = new FrameLook();
+    const WindowFrame &last = w->frames.back();
+    in.resize((size_t)(last.off + (uint64_t)last.info.frame_bytes));
+    l->bytes.swap(in);
+    l->w = w;
+    l->caller_base = mp3 - preroll_bytes;          /* address bytes[0] would have in the caller's buffer */
+    l->caller_end = preroll_bytes + (uint64_t)mp3_bytes;
+    l->float_output = sizeof(S) == 4;
+    return l;
+}
+
+/* hands out the next frame of the window the way mp3dec_decode_frame reports it */
+template <class S>
+int serve_frame(FrameLook *l, mp3dec_t *dec, const uint8_t *mp3, S *pcm, mp3dec_frame_info_t *info)
+{
+    Window *w = l->w;
+    const WindowFrame &f = w->frames[w->next++];
+    if (f.found)
+    {
+        *info = f.info;
+        memcpy(dec->header, mp3 + f.info.frame_offset, 4);
+    } else
+        info->frame_bytes = f.info.frame_bytes;      /* the other fields stay as the caller had them */
+    if (f.samples) memcpy(pcm, (const S *)w->pcm + f.pcm_pos, (size_t)f.samples*(size_t)f.info.channels*sizeof(S));
+    if (!dec->header[0]) dec->header[0] = 0xff;      /* "not freshly initialised": the state lives in the window */
+    put_look(dec, l);
+    return f.samples;
+}
+
+template <class S>
+int frame_lookahead_t(mp3dec_t *dec, const uint8_t *mp3, int mp3_bytes, S *pcm, mp3dec_frame_info_t *info)
+{
+    FrameLook *l = take_look(dec);
+    const bool fresh = dec->header[0] == 0;
+    if (l && fresh) { delete l; l = nullptr; }               /* mp3dec_init by the caller: whatever was cached is void */
+    if (l && !l->w)
+    {
+        /* this decoder's window was retired while it was idle: its state was saved, hand it back */
+        memcpy(dec, &l->saved, sizeof(mp3dec_t));
+        delete l;
+        return -1;
+    }
+    if (l)
+    {
+        Window *w = l->w;
+        const uint64_t pos = w->next < w->frames.size() ? w->frames[w->next].off
+                                                        : w->frames.back().off + (uint64_t)w->frames.back().info.frame_bytes;
+        const bool here = pcm && l->float_output == (sizeof(S) == 4) && mp3 == l->caller_base + pos &&
+                          (uint64_t)std::max(mp3_bytes, 0) == l->caller_end - pos;
+        if (here && w->next < w->frames.size() &&
+            !memcmp(mp3, l->bytes.data() + pos, (size_t)w->frames[w->next].info.frame_bytes))
+            return serve_frame<S>(l, dec, mp3, pcm, info);
+        if (here && w->next == w->frames.size() && mp3_bytes >= kMinLookBytes)
+        {
+            /* window used up, the caller goes on: next window, state from the last kPreroll frames */
+            const size_t back = std::min(kPreroll, w->frames.size());
+            const uint64_t restart = w->frames[w->frames.size() - back].off;
+            FrameLook *nl = start_look<S>(mp3, mp3_bytes, l->bytes.data() + restart, (size_t)(pos - restart));
+            if (nl)
+            {
+                delete l;
+                return serve_frame<S>(nl, dec, mp3, pcm, info);
+            }
+        }
+        /* the caller left the predicted path (or the input ends): make dec current, the direct path takes over */
+        replay_into(dec, l);
+        delete l;
+        return -1;
+    }
+    if (!fresh || !pcm || mp3_bytes < kMinLookBytes) return -1;
+    FrameLook *nl = start_look<S>(mp3, mp3_bytes, nullptr, 0);
+    if (!nl || nl->w->frames.size() - nl->w->next < 8) { delete nl; return -1; }
+    return serve_frame<S>(nl, dec, mp3, pcm, info);
+}
+
 template <class S>
 size_t ex_read_frame(ExT<S> *dec, S **buf, mp3dec_frame_info_t *frame_info, size_t max_samples)
 {
@@ -658,6 +845,14 @@ int load_buf_frames(mp3dec_t *dec, const uint8_t *buf, size_t buf_size, mp3dec_f
 }
 
 }  // namespace
+
+extern "C" __attribute__((visibility("hidden"))) int mp3dec_frame_lookahead(mp3dec_t *dec, const uint8_t *mp3, int mp3_bytes, void *pcm,
+                                                                            mp3dec_frame_info_t *info, int float_output)
+{
+    if (!lookahead_enabled() || !dec || !mp3 || !info) return -1;
+    return float_output ? frame_lookahead_t<float>(dec, mp3, mp3_bytes, (float *)pcm, info)
+                        : frame_lookahead_t<int16_t>(dec, mp3, mp3_bytes, (int16_t *)pcm, info);
+}
 
 extern "C" {
 

@@ -362,3 +362,49 @@ def test_device_side_info_matches_host_parse(name, m):
     p.close()
     assert len(desc) >= len(want) and len(want) > 0
     assert desc[:len(want)].tobytes() == want.tobytes()
+
+
+def _frame_loop(m, data, hop=None, rebuffer_at=None, chunk=None, parse_only_at=None):
+    """mp3dec_init + mp3dec_decode_frame loop with the ways a caller can leave the straight path: move the rest of the
+    stream to another buffer, feed at most `chunk` bytes per call, make one parse-only call (pcm = NULL)"""
+    L = m.load()
+    dec = m.Mp3Dec()
+    L.mp3dec_init(C.byref(dec))
+    info = m.FrameInfo()
+    buf = np.frombuffer(data, dtype=np.uint8).copy()
+    tmp = np.zeros(m.MINIMP3_MAX_SAMPLES_PER_FRAME, np.int16)
+    pos, out, n, calls = 0, [], len(data), 0
+    keep = [buf]
+    while True:
+        if rebuffer_at is not None and calls == rebuffer_at:
+            buf = np.concatenate([np.zeros(pos, np.uint8), np.frombuffer(data, dtype=np.uint8)[pos:]])   # same bytes, new address
+            keep.append(buf)
+        avail = n - pos if chunk is None else min(n - pos, chunk)
+        pcm_ptr = None if parse_only_at == calls else tmp.ctypes.data
+        samples = L.mp3dec_decode_frame(C.byref(dec), buf.ctypes.data + pos, avail, pcm_ptr, C.byref(info))
+        calls += 1
+        if samples and pcm_ptr:
+            out.append(tmp[:samples*info.channels].copy())
+        pos += info.frame_bytes
+        if not info.frame_bytes:
+            break
+    return np.concatenate(out) if out else np.zeros(0, np.int16)
+
+
+@pytest.mark.parametrize("name", ["l3-compl", "l3-he_mode", "l3-sin1k0db", "M2L3_bitrate_22_all", "l2-fl12"])
+def test_frame_loop_look_ahead_and_its_exits(name, m, ref, monkeypatch):
+    """the plain frame loop is answered from look-ahead windows; leaving the predicted path (new buffer, short reads,
+    tiny windows) replays the decoder state and goes on through the one-frame path: always the reference's stream"""
+    data = load_vector(name)
+    want, _ = ref.decode_frames(data)
+
+    def check(pcm):
+        assert len(pcm) == len(want) and np.abs(pcm.astype(np.int32) - want.astype(np.int32)).max() <= 1
+
+    check(_frame_loop(m, data))                                   # straight through one window
+    check(_frame_loop(m, data, rebuffer_at=37))                   # the stream moves to another buffer mid-way
+    check(_frame_loop(m, data, rebuffer_at=1))
+    check(_frame_loop(m, data, chunk=6000))                       # never enough bytes for a window: one-frame path
+    monkeypatch.setenv("MP3B_DEBUG_WINDOW_FRAMES", "9")           # many window boundaries
+    check(_frame_loop(m, data))
+    check(_frame_loop(m, data, rebuffer_at=23))
