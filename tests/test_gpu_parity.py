@@ -408,3 +408,31 @@ def test_frame_loop_look_ahead_and_its_exits(name, m, ref, monkeypatch):
     monkeypatch.setenv("MP3B_DEBUG_WINDOW_FRAMES", "9")           # many window boundaries
     check(_frame_loop(m, data))
     check(_frame_loop(m, data, rebuffer_at=23))
+
+
+def test_frame_loop_on_damaged_streams_call_by_call(m, ref):
+    """spliced / cut / duplicated streams through the frame loop (look-ahead windows engaged): every call reports what
+    the reference's call reports (samples, frame_bytes), sample counts match"""
+    rng = np.random.default_rng(777)
+    base = load_vector("l3-sin1k0db")
+    for t in range(12):
+        b = bytearray(base)
+        kind = t % 3
+        if kind == 0:
+            for _ in range(int(rng.integers(1, 6))):
+                p, n = int(rng.integers(0, len(b) - 200)), int(rng.integers(1, 200))
+                b[p:p + n] = rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+        elif kind == 1:
+            for _ in range(int(rng.integers(1, 4))):
+                p, n = int(rng.integers(0, len(b) - 500)), int(rng.integers(1, 500))
+                if rng.random() < 0.5:
+                    del b[p:p + n]
+                else:
+                    b[p:p] = b[p:p + n]
+        else:
+            b = b[int(rng.integers(1, 3000)):int(rng.integers(60000, len(b)))]
+        data = bytes(b)
+        want_pcm, want_frames = ref.decode_frames(data)
+        pcm, frames = m.decode_frames(data)
+        assert [(f["samples"], f["frame_bytes"]) for f in frames] == [(f.samples, f.frame_bytes) for f in want_frames], t
+        assert len(pcm) == len(want_pcm)
