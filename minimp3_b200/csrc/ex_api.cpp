@@ -505,9 +505,12 @@ FrameLook *start_look(const uint8_t *mp3, int mp3_bytes, const uint8_t *preroll,
 {
     /* window input = [frames to re-decode for the state] + [the caller's buffer]; only the extent of the frames
      * that end up in the window is kept */
-    std::vector<uint8_t> in(preroll_bytes + (size_t)mp3_bytes);
+    /* no frame is longer than 2881 bytes (MPEG-1 Layer II 384 kbit/s at 32 kHz; free format is capped at 2304): a
+     * view of that many bytes per frame holds every frame the window can take, the rest of a long buffer stays put */
+    const size_t view = std::min<size_t>((size_t)mp3_bytes, (window_frames() + kPreroll + 2)*2900);
+    std::vector<uint8_t> in(preroll_bytes + view);
     if (preroll_bytes) memcpy(in.data(), preroll, preroll_bytes);
-    memcpy(in.data() + preroll_bytes, mp3, (size_t)mp3_bytes);
+    memcpy(in.data() + preroll_bytes, mp3, view);
     Window *w = build_window<S>(in.data(), 0, in.size(), window_frames() + kPreroll);
     if (!w) return nullptr;
     size_t k = 0;

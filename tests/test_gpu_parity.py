@@ -436,3 +436,25 @@ def test_frame_loop_on_damaged_streams_call_by_call(m, ref):
         pcm, frames = m.decode_frames(data)
         assert [(f["samples"], f["frame_bytes"]) for f in frames] == [(f.samples, f.frame_bytes) for f in want_frames], t
         assert len(pcm) == len(want_pcm)
+
+
+def test_frame_loop_on_a_long_stream(m, ref):
+    """12 720 frames (> 3 default windows of 4096, input views shorter than the buffer): frame loop and streaming read"""
+    data = load_vector("l3-sin1k0db")*40
+    want, _ = ref.decode_frames(data)
+    pcm, frames = m.decode_frames(data)
+    assert len(pcm) == len(want) and np.abs(pcm.astype(np.int32) - want.astype(np.int32)).max() <= 1
+    L = m.load()
+    buf = np.frombuffer(data, dtype=np.uint8)
+    dec = m.Mp3DecEx()
+    assert L.mp3dec_ex_open_buf(C.byref(dec), buf.ctypes.data, len(buf), 1) == 0
+    out = np.zeros(len(want) + 4096, np.int16)
+    got = 0
+    while True:
+        n = L.mp3dec_ex_read(C.byref(dec), out.ctypes.data + 2*got, 100000)
+        got += n
+        if n != 100000:
+            break
+    L.mp3dec_ex_close(C.byref(dec))
+    want_lb = ref.load_buf(data)[1]
+    assert got == len(want_lb) and np.abs(out[:got].astype(np.int32) - want_lb.astype(np.int32)).max() <= 1
