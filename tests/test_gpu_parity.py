@@ -458,3 +458,24 @@ def test_frame_loop_on_a_long_stream(m, ref):
     L.mp3dec_ex_close(C.byref(dec))
     want_lb = ref.load_buf(data)[1]
     assert got == len(want_lb) and np.abs(out[:got].astype(np.int32) - want_lb.astype(np.int32)).max() <= 1
+
+
+def test_concurrent_frame_loops(m, ref):
+    """several decoders walked from different host threads at the same time (each with its own look-ahead window)"""
+    import threading
+    names = ["l3-compl", "l3-he_mode", "l3-sin1k0db", "M2L3_bitrate_22_all", "l2-fl12", "l3-si_huff", "l3-he_44khz", "l1-fl1"]
+    datas = [load_vector(n) for n in names]
+    results = [None]*len(names)
+
+    def work(i):
+        results[i] = m.decode_frames(datas[i])[0]
+
+    for rep in range(2):
+        threads = [threading.Thread(target=work, args=(i,)) for i in range(len(names))]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        for i, d in enumerate(datas):
+            want, _ = ref.decode_frames(d)
+            assert len(results[i]) == len(want) and np.abs(results[i].astype(np.int32) - want.astype(np.int32)).max() <= 1, names[i]
