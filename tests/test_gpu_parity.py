@@ -479,3 +479,35 @@ def test_concurrent_frame_loops(m, ref):
         for i, d in enumerate(datas):
             want, _ = ref.decode_frames(d)
             assert len(results[i]) == len(want) and np.abs(results[i].astype(np.int32) - want.astype(np.int32)).max() <= 1, names[i]
+
+
+def test_more_decoders_than_live_windows(m, ref):
+    """20 decoders advanced round-robin, a few frames at a time: more than the 16 windows kept alive, so windows are
+    retired to saved decoder states and decoding continues on the one-frame path -- every stream still exact"""
+    L = m.load()
+    data = load_vector("l3-he_mode")
+    want, _ = ref.decode_frames(data)
+    buf = np.frombuffer(data, dtype=np.uint8)
+    n_dec = 20
+    decs = [m.Mp3Dec() for _ in range(n_dec)]
+    for d in decs:
+        L.mp3dec_init(C.byref(d))
+    pos = [0]*n_dec
+    outs = [[] for _ in range(n_dec)]
+    done = [False]*n_dec
+    info = m.FrameInfo()
+    tmp = np.zeros(m.MINIMP3_MAX_SAMPLES_PER_FRAME, np.int16)
+    while not all(done):
+        for i in range(n_dec):
+            for _ in range(3):
+                if done[i]:
+                    break
+                s = L.mp3dec_decode_frame(C.byref(decs[i]), buf.ctypes.data + pos[i], len(data) - pos[i], tmp.ctypes.data, C.byref(info))
+                if s:
+                    outs[i].append(tmp[:s*info.channels].copy())
+                pos[i] += info.frame_bytes
+                if not info.frame_bytes:
+                    done[i] = True
+    for i in range(n_dec):
+        pcm = np.concatenate(outs[i])
+        assert len(pcm) == len(want) and np.abs(pcm.astype(np.int32) - want.astype(np.int32)).max() <= 1, i
