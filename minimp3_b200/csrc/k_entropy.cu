@@ -53,6 +53,7 @@ __device__ __forceinline__ GcDesc load_desc(const GcDesc *p)
     return d;
 }
 
+template <bool TAPS>
 __global__ void __launch_bounds__(kWarpsPerBlock*32, 2) k_l3_entropy(EntropyArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -132,10 +133,10 @@ __global__ void __launch_bounds__(kWarpsPerBlock*32, 2) k_l3_entropy(EntropyArgs
         {
             /* two steps = four lines = half a 32-byte sector */
             float4 v;
-            int q0, q1, q2, q3;
-            dec.step(T, v.x, v.y, q0, q1);
-            dec.step(T, v.z, v.w, q2, q3);
-            if (tq && (q0 | q1 | q2 | q3))
+            int q0 = 0, q1 = 0, q2 = 0, q3 = 0;
+            dec.template step<TAPS>(T, v.x, v.y, q0, q1);
+            dec.template step<TAPS>(T, v.z, v.w, q2, q3);
+            if (TAPS && tq && (q0 | q1 | q2 | q3))
             {
                 tq[2*iter] = (int16_t)q0; tq[2*iter + 1] = (int16_t)q1;
                 tq[2*iter + 2] = (int16_t)q2; tq[2*iter + 3] = (int16_t)q3;
@@ -169,7 +170,9 @@ cudaError_t launch_entropy(const DeviceTables &, const EntropyArgs &a, cudaStrea
 {
     if (!a.n_order) return cudaSuccess;
     const size_t smem = ((sizeof(SharedTables) + 15) & ~15) + sizeof(WarpScratch)*kWarpsPerBlock;
-    cudaError_t e = cudaFuncSetAttribute(k_l3_entropy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const bool taps = a.tap_q != nullptr;       /* the parity tests want the signed integers as well */
+    cudaError_t e = taps ? cudaFuncSetAttribute(k_l3_entropy<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                         : cudaFuncSetAttribute(k_l3_entropy<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
@@ -179,7 +182,8 @@ cudaError_t launch_entropy(const DeviceTables &, const EntropyArgs &a, cudaStrea
     const uint32_t max_blocks = (uint32_t)sms*2;
     if (blocks > max_blocks) blocks = max_blocks;
     if (cudaMemsetAsync(a.group_counter, 0, sizeof(uint32_t), s) != cudaSuccess) return cudaGetLastError();
-    k_l3_entropy<<<blocks, kWarpsPerBlock*32, smem, s>>>(a);
+    if (taps) k_l3_entropy<true><<<blocks, kWarpsPerBlock*32, smem, s>>>(a);
+    else k_l3_entropy<false><<<blocks, kWarpsPerBlock*32, smem, s>>>(a);
     return cudaGetLastError();
 }
 

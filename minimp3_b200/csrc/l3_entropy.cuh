@@ -294,6 +294,8 @@ struct GranuleDecoder
     /* next two lines; q0/q1 receive the signed quantised values.  Big-value pairs and count1 half-quads share
      * one code path (a count1 line is a value of magnitude 0 or 1: one * pow43(1) == one exactly), so lanes in
      * different regions of their granules do not serialise. */
+    /* WANT_Q = false (production): the signed integers q0 / q1 are only needed by the parity taps */
+    template <bool WANT_Q = true>
     MP3_HD void step(const EntropyTables &T, float &v0, float &v1, int &q0, int &q1)
     {
         v0 = v1 = 0.f;
@@ -383,8 +385,11 @@ struct GranuleDecoder
             /* a zero value gives one * 0 = +0 and reads no sign */
             v0 = flip_sign(MP3_FMUL(one, l3_pow43(x, T.pow43)), neg_x);
             v1 = flip_sign(MP3_FMUL(one, l3_pow43(y, T.pow43)), neg_y);
-            q0 = neg_x ? -x : x;
-            q1 = neg_y ? -y : y;
+            if (WANT_Q)
+            {
+                q0 = neg_x ? -x : x;
+                q1 = neg_y ? -y : y;
+            }
         }
         if (mode == EMODE_BIG) { if (--big_left == 0) mode = EMODE_C1A; }
         else mode = (mode == EMODE_C1A) ? EMODE_C1B : EMODE_C1A;
