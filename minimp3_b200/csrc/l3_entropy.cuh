@@ -29,15 +29,15 @@ struct EntropyTables
 /* MSB-first bit reader over big-endian bytes, fed by aligned 32-bit loads.  The 64-bit window is kept as two
  * 32-bit halves (funnel shifts instead of 64-bit shifts) and two more words are fetched ahead of need so the
  * global-load latency overlaps with the decoding of the bits already in the window. */
-/* m with its sign bit toggled when neg is 1 */
-MP3_HD float flip_sign(float m, uint32_t neg)
+/* m (>= +0) with the sign bit `sign` (0 or 0x80000000) put on */
+MP3_HD float flip_sign(float m, uint32_t sign)
 {
 #if defined(__CUDA_ARCH__)
-    return __uint_as_float(__float_as_uint(m) ^ (neg << 31));
+    return __uint_as_float(__float_as_uint(m) | sign);
 #else
     union { float f; uint32_t u; } c;
     c.f = m;
-    c.u ^= neg << 31;
+    c.u |= sign;
     return c.f;
 #endif
 }
@@ -225,7 +225,7 @@ struct GranuleDecoder
     int iscf_st;
     float gain, one;
     int scf_shift, limit;
-    int mode, big_left, band_left, band_idx, ireg, reg_left, pending, extent, line;
+    int mode, big_left, band_left, band_idx, ireg, reg_left, pending, extent;
     uint32_t tinfo;
     uint8_t table_select[3], region_count[3];
     bool count1_b;
@@ -285,7 +285,7 @@ struct GranuleDecoder
         reg_left = region_count[0] + 1;
         tinfo = T.tabinfo[table_select[0]];
         one = 0.f;
-        pending = 0; extent = 0; line = 0;
+        pending = 0; extent = 0;
         count1_b = (d.flags0 & GCF_COUNT1_TABLE) != 0;
     }
 
@@ -305,8 +305,6 @@ struct GranuleDecoder
         __builtin_assume(__isShared(T.lut)); __builtin_assume(__isShared(T.pow43)); __builtin_assume(__isShared(T.tabinfo));
         __builtin_assume(__isShared(sfbw)); __builtin_assume(__isShared(iscf));
 #endif
-        const int this_line = line;
-        line += 2;
         if (mode == EMODE_DONE) return;
         if (band_left == 0)
         {
@@ -376,11 +374,11 @@ struct GranuleDecoder
             const int n2 = y == 15 ? linbits : 0, s2 = y != 0;
             x += (int)((t >> 1) >> (31 - n1));
             const uint32_t t1 = t << n1;
-            const uint32_t neg_x = (t1 >> 31) & (uint32_t)s1;
+            const uint32_t neg_x = t1 & (0u - (uint32_t)s1) & 0x80000000u;     /* sign bit in place */
             const uint32_t t2 = t1 << s1;
             y += (int)((t2 >> 1) >> (31 - n2));
             const uint32_t t3 = t2 << n2;
-            const uint32_t neg_y = (t3 >> 31) & (uint32_t)s2;
+            const uint32_t neg_y = t3 & (0u - (uint32_t)s2) & 0x80000000u;
             br.skip(n1 + s1 + n2 + s2);
             /* a zero value gives one * 0 = +0 and reads no sign */
             v0 = flip_sign(MP3_FMUL(one, l3_pow43(x, T.pow43)), neg_x);
@@ -394,7 +392,7 @@ struct GranuleDecoder
         if (mode == EMODE_BIG) { if (--big_left == 0) mode = EMODE_C1A; }
         else mode = (mode == EMODE_C1A) ? EMODE_C1B : EMODE_C1A;
         band_left--;
-        extent = this_line + 2;
+        extent += 2;    /* every step before the last one gets here */
     }
 };
 
