@@ -45,9 +45,9 @@ constexpr int kSlots = (GT + 2)*2;          /* granule-channel slots incl. two h
 constexpr int kXPitch = 18;                 /* rows sit in shared memory exactly as in HBM (bulk copies) */
 constexpr int kXSlot = 576;
 constexpr int kRows = 15 + 18*GT;           /* time slots per channel: 15 history + tile */
-constexpr int kYPitch = 33;
+constexpr int kYPitch = 34;                 /* even: a DCT thread moves its row as 8-byte words, 16 threads cover all banks */
 constexpr int kXFloats = kSlots*kXSlot;     /* 11520 */
-constexpr int kYFloats = 2*kRows*kYPitch;   /* 10494, aliases XS */
+constexpr int kYFloats = 2*kRows*kYPitch;   /* 10812, aliases XS */
 constexpr int kTFloats = kSlots*288;
 static_assert(sizeof(TileRec) == 256 && MP3B_TILE_SLOTS == kSlots, "tile record layout");
 static_assert(kYFloats <= kXFloats, "Y must fit in the X region");
@@ -680,11 +680,17 @@ k_l3_transform(TransformArgs a, const uint16_t *__restrict__ reorder_inv, const 
             const int slot = (row < 15 ? 1 : 2 + (((row - 15)*3641) >> 16))*nch + ch;
             const int nj = max(S.meta[slot].act, S.meta[slot - nch].act);
             float v[32];
+            float2 *y2 = reinterpret_cast<float2 *>(y);
 #pragma unroll
-            for (int k = 0; k < 32; k++) v[k] = k < nj ? y[k] : 0.f;
+            for (int k = 0; k < 32; k += 2)
+            {
+                const float2 q = y2[k >> 1];
+                v[k] = k < nj ? q.x : 0.f;
+                v[k + 1] = k + 1 < nj ? q.y : 0.f;
+            }
             dct2_32_paired(v);
 #pragma unroll
-            for (int k = 0; k < 32; k++) y[k] = v[k];
+            for (int k = 0; k < 32; k += 2) y2[k >> 1] = make_float2(v[k], v[k + 1]);
         }
     }
     __syncthreads();
