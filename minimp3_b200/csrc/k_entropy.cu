@@ -115,6 +115,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock*32, 2) k_l3_entropy(EntropyArgs
             if (want_ist)
             {
                 uint8_t *o = a.ist_pos + (size_t)gc*40;
+#pragma unroll 1
                 for (int k = 0; k < 40; k++) o[k] = k < n_ist ? ist_local[k] : (uint8_t)0;
             }
         }

@@ -193,19 +193,51 @@ MP3_HD int read_scalefactors(BitRd &br, const ScfLayout &L, int scfsi, bool lsf,
                              int st, uint8_t *ist_out)
 {
     int idx = 0;
+    /* kept rolled: run once per granule, the unrolled form was 3000 instructions of straight-line code that
+     * every warp had to pull through the instruction cache */
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
     for (int p = 0; p < 4 && L.count[p]; p++, scfsi *= 2)
     {
         const int cnt = L.count[p];
         const int bits = L.size[p];
         const bool copy = (scfsi & 8) != 0;
         const int max_scf = lsf ? (1 << bits) - 1 : -1;
-        for (int k = 0; k < cnt; k++)
+        if (!copy && bits)
         {
-            int s = 0, ist = 0;
-            if (copy) { s = prev ? prev[(idx + k)*st] : 0; ist = s; }
-            else if (bits) { s = (int)br.get(bits); ist = (s == max_scf) ? 255 : s; }
-            dst[(idx + k)*st] = (uint8_t)s;
-            if (ist_out) ist_out[idx + k] = (uint8_t)ist;
+            /* up to six fields (<= 5 bits each) per refill of the window instead of one get() per field */
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+            for (int k = 0; k < cnt; )
+            {
+                br.refill();
+                uint32_t win = br.hi;
+                const int n = cnt - k < 6 ? cnt - k : 6;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+                for (int i = 0; i < n; i++, k++)
+                {
+                    const int s = (int)(win >> (32 - bits));
+                    win <<= bits;
+                    dst[(idx + k)*st] = (uint8_t)s;
+                    if (ist_out) ist_out[idx + k] = (uint8_t)((s == max_scf) ? 255 : s);
+                }
+                br.skip(n*bits);
+            }
+        } else
+        {
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+            for (int k = 0; k < cnt; k++)
+            {
+                const int s = (copy && prev) ? prev[(idx + k)*st] : 0;
+                dst[(idx + k)*st] = (uint8_t)s;
+                if (ist_out) ist_out[idx + k] = (uint8_t)s;
+            }
         }
         idx += cnt;
     }
