@@ -44,21 +44,21 @@ MP3_HD float flip_sign(float m, uint32_t sign)
 
 struct BitRd
 {
-    const uint32_t *w;
-    uint64_t n_words, widx;
+    const uint32_t *wp;     /* next word to fetch */
+    const uint32_t *wend;   /* end of the buffer (host harness only) */
     uint32_t hi, lo;        /* window, MSB-aligned: `avail` valid bits from bit 31 of hi downwards */
     uint32_t next, next2;   /* two words of lookahead; next2 still in memory byte order */
     int avail;
     int pos;                /* bits consumed since init */
 
-    /* word i as stored (big-endian bit order not applied yet).  The device buffer carries 64 bytes of slack
+    /* a word as stored (big-endian bit order not applied yet).  The device buffer carries 64 bytes of slack
      * behind the last payload byte (capi.cu), the host harness is bounds-checked. */
-    MP3_HD uint32_t raw(uint64_t i) const
+    MP3_HD uint32_t raw(const uint32_t *p) const
     {
 #if defined(__CUDA_ARCH__)
-        return __ldg(w + i);
+        return __ldg(p);
 #else
-        return i >= n_words ? 0u : w[i];
+        return p >= wend ? 0u : *p;
 #endif
     }
     static MP3_HD uint32_t be(uint32_t v)
@@ -80,30 +80,32 @@ struct BitRd
     }
     MP3_HD void init(const uint32_t *words, uint64_t nw, uint64_t bit_off)
     {
-        w = words; n_words = nw;
-        widx = bit_off >> 5;
+        wend = words + nw;
+        wp = words + (bit_off >> 5);
         const int sh = (int)(bit_off & 31);
-        const uint32_t w0 = be(raw(widx)), w1 = be(raw(widx + 1));
+        const uint32_t w0 = be(raw(wp)), w1 = be(raw(wp + 1));
         hi = shl_hi(w0, w1, sh);
         lo = w1 << sh;
         avail = 64 - sh;
-        next = be(raw(widx + 2));
-        next2 = raw(widx + 3);
-        widx += 4;
+        next = be(raw(wp + 2));
+        next2 = raw(wp + 3);
+        wp += 4;
         pos = 0;
     }
+    /* Tops the window up to more than 32 valid bits.  Written without a branch: in a warp of 32 granules some
+     * lane needs the refill at almost every call, so a divergent region (and its reconvergence stall) would be
+     * paid every time anyway. */
     MP3_HD void refill()
     {
-        if (avail <= 32)
-        {
-            /* lo holds no valid bits any more: append `next` right below the avail valid bits of hi */
-            const int sh = 32 - avail;            /* 0..31 */
-            hi |= shl_hi(0u, next, sh);
-            lo = next << sh;
-            avail += 32;
-            next = be(next2);          /* the byte swap waits here, one refill after the load was issued */
-            next2 = raw(widx++);
-        }
+        const bool need = avail <= 32;          /* lo holds no valid bits any more */
+        const int sh = (32 - avail) & 31;       /* need: 0..31, append `next` right below the valid bits of hi */
+        const uint32_t nx = need ? next : 0u;
+        hi |= shl_hi(0u, nx, sh);
+        lo = need ? next << sh : lo;
+        avail += need ? 32 : 0;
+        next = need ? be(next2) : next;         /* the byte swap waits here, one refill after the load was issued */
+        if (need) next2 = raw(wp);
+        wp += need ? 1 : 0;
     }
     MP3_HD uint32_t peek(int n) const { return n ? hi >> (32 - n) : 0u; }
     MP3_HD void skip(int n)
