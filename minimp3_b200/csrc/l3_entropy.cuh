@@ -400,12 +400,13 @@ struct GranuleDecoder
             y = pending & 1;
         }
         /* escapes and signs of both values (minimp3.h:807-826) from one snapshot of the window, without
-         * branches: at least 32 bits are in, the four fields take 2*(13 + 1) at most */
-        br.refill();
+         * branches.  The refill at the top left more than 32 bits and a code takes 19 at most, so the two sign
+         * bits are always there; only escapes (up to 2*13 more bits, rare) need the window topped up again. */
         {
-            const uint32_t t = br.hi;
             const int n1 = x == 15 ? linbits : 0, s1 = x != 0;
             const int n2 = y == 15 ? linbits : 0, s2 = y != 0;
+            if (n1 | n2) br.refill();
+            const uint32_t t = br.hi;
             x += (int)((t >> 1) >> (31 - n1));
             const uint32_t t1 = t << n1;
             const uint32_t neg_x = t1 & (0u - (uint32_t)s1) & 0x80000000u;     /* sign bit in place */
