@@ -225,6 +225,9 @@ void mp3dec_batch_plan_destroy(mp3dec_batch_plan_t *plan);
  * 5 ist_pos uint8[n_gc][40].  Taps must be enabled before run. */
 int mp3dec_batch_plan_enable_taps(mp3dec_batch_plan_t *plan);
 int mp3dec_batch_plan_read_tap(mp3dec_batch_plan_t *plan, int which, void *dst, size_t dst_bytes);
+/* Test tap: |x|^(4/3) for x = 0 .. n-1 (n <= 8207) exactly as the entropy kernel's requantiser evaluates it
+ * (L3_pow_43, minimp3.h:716-740), computed on the current device.  0 or MP3D_E_MEMORY / MP3D_E_PARAM. */
+int mp3dec_b200_pow43_device(float *dst, int n);
 
 /* Multi-GPU sharding helper: assigns streams to n_shards by greedy longest-processing-time on input
  * bytes; shard_of[i] receives the shard of stream i.  No data-path collective exists: shards are

@@ -59,7 +59,7 @@ EXPORTS = ["mp3dec_init", "mp3dec_decode_frame", "mp3dec_decode_frame_f32", "mp3
            "mp3dec_load_buf", "mp3dec_load_buf_f32", "mp3dec_decode_batch_cuda", "mp3dec_batch_plan_create",
            "mp3dec_batch_plan_run", "mp3dec_batch_plan_run_stage", "mp3dec_batch_plan_sync", "mp3dec_batch_plan_fetch", "mp3dec_batch_plan_stats",
            "mp3dec_batch_plan_device_pcm", "mp3dec_batch_plan_destroy", "mp3dec_batch_plan_enable_taps",
-           "mp3dec_batch_plan_read_tap", "mp3dec_batch_shard", "mp3dec_b200_version",
+           "mp3dec_batch_plan_read_tap", "mp3dec_b200_pow43_device", "mp3dec_batch_shard", "mp3dec_b200_version",
            "mp3dec_detect_cb", "mp3dec_load_cb", "mp3dec_iterate_buf", "mp3dec_iterate_cb", "mp3dec_ex_open_buf",
            "mp3dec_ex_open_cb", "mp3dec_ex_close", "mp3dec_ex_seek", "mp3dec_ex_read_frame", "mp3dec_ex_read",
            "mp3dec_detect", "mp3dec_load", "mp3dec_iterate", "mp3dec_ex_open"]
@@ -125,6 +125,8 @@ def load():
     L.mp3dec_batch_plan_destroy.argtypes = [vp]
     L.mp3dec_batch_plan_destroy.restype = None
     L.mp3dec_batch_plan_read_tap.argtypes = [vp, C.c_int, vp, C.c_size_t]
+    L.mp3dec_b200_pow43_device.argtypes = [vp, C.c_int]
+    L.mp3dec_b200_pow43_device.restype = C.c_int
     L.mp3dec_batch_shard.argtypes = [C.POINTER(C.c_size_t), C.c_int, C.c_int, C.POINTER(C.c_int)]
     L.mp3dec_batch_shard.restype = None
     L.mp3dec_b200_version.restype = C.c_char_p

@@ -17,25 +17,22 @@
 #include <cuda_runtime.h>
 
 #include "kernels.h"
-#include "l3_entropy.cuh"
 #define MP3T_QUAL static __device__ const
 #include "mp3_tables.h"
 
 namespace mp3b {
-
 namespace {
 
 constexpr int kWarpsPerBlock = 16;
 constexpr int kC1Base = MP3T_HUFF_LUT_SIZE;          /* count1 table A (64 entries) then B (16) */
+constexpr int kSfbShort = 8*23, kSfbMixed = 8*23 + 8*40;
 
 struct SharedTables
 {
     uint16_t lut[(MP3T_HUFF_LUT_SIZE + 80 + 7) & ~7];
     float pow43[148];
     uint32_t tabinfo[32];
-    uint8_t sfb_long[8*23];
-    uint8_t sfb_short[8*40];
-    uint8_t sfb_mixed[8*40];
+    uint8_t sfb[8*23 + 8*40 + 8*40];    /* long, short, mixed band widths, one row per sample rate */
 };
 
 struct WarpScratch
@@ -43,6 +40,29 @@ struct WarpScratch
     uint8_t prev[40*32];    /* the previous granule's scalefactors during set-up (scfsi) */
     uint8_t iscf[40*32];
 };
+
+/* the tables: static shared memory, named directly by the decoder's accessors (see l3_entropy.cuh) */
+__shared__ SharedTables g_tabs;
+/* the per-warp scalefactor scratch: dynamic shared memory */
+extern __shared__ __align__(16) unsigned char g_scratch[];
+
+}  // namespace
+}  // namespace mp3b
+
+#if defined(__CUDA_ARCH__)
+#define MP3B_ENT_LUT(T, i) (g_tabs.lut[i])
+#define MP3B_ENT_POW43(T) (g_tabs.pow43)
+#define MP3B_ENT_TABINFO(T, i) (g_tabs.tabinfo[i])
+#define MP3B_ENT_SFBW(dec, i) (g_tabs.sfb[(dec).sfbw_off + (i)])
+#define MP3B_ENT_ISCF(dec, b) (g_scratch[(dec).iscf_off + (b)*32])
+#define MP3B_ENT_SET_SFBW(dec, T, kind, row) \
+    ((dec).sfbw_off = (kind) == 0 ? (row)*23 : (kind) == 1 ? kSfbMixed + (row)*40 : kSfbShort + (row)*40)
+#endif
+#include "l3_entropy.cuh"
+
+namespace mp3b {
+
+namespace {
 
 __device__ __forceinline__ GcDesc load_desc(const GcDesc *p)
 {
@@ -56,9 +76,8 @@ __device__ __forceinline__ GcDesc load_desc(const GcDesc *p)
 template <bool TAPS>
 __global__ void __launch_bounds__(kWarpsPerBlock*32, 2) k_l3_entropy(EntropyArgs a)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    SharedTables &S = *reinterpret_cast<SharedTables *>(smem_raw);
-    WarpScratch *scratch = reinterpret_cast<WarpScratch *>(smem_raw + ((sizeof(SharedTables) + 15) & ~15));
+    SharedTables &S = g_tabs;
+    WarpScratch *scratch = reinterpret_cast<WarpScratch *>(g_scratch);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
@@ -68,15 +87,16 @@ __global__ void __launch_bounds__(kWarpsPerBlock*32, 2) k_l3_entropy(EntropyArgs
     if (tid < 32) S.tabinfo[tid] = (uint32_t)MP3T_HUFF_BASE[tid] | ((uint32_t)MP3T_HUFF_ROOTW[tid] << 16) | ((uint32_t)MP3T_HUFF_LINBITS[tid] << 20);
     if (tid < 64) S.lut[kC1Base + tid] = (uint16_t)(((MP3T_COUNT1A[tid] >> 4) << 8) | (MP3T_COUNT1A[tid] & 15));
     if (tid < 16) S.lut[kC1Base + 64 + tid] = (uint16_t)((4 << 8) | (~tid & 15));
-    for (int i = tid; i < 8*23; i += blockDim.x) S.sfb_long[i] = MP3T_SFB_LONG[i];
-    for (int i = tid; i < 8*40; i += blockDim.x) { S.sfb_short[i] = MP3T_SFB_SHORT[i]; S.sfb_mixed[i] = MP3T_SFB_MIXED[i]; }
+    for (int i = tid; i < 8*23; i += blockDim.x) S.sfb[i] = MP3T_SFB_LONG[i];
+    for (int i = tid; i < 8*40; i += blockDim.x) { S.sfb[kSfbShort + i] = MP3T_SFB_SHORT[i]; S.sfb[kSfbMixed + i] = MP3T_SFB_MIXED[i]; }
     __syncthreads();
 
+    /* the decoder reaches the tables through the MP3B_ENT_* accessors above; the pointers only serve the host build */
     EntropyTables T;
     T.lut = S.lut; T.pow43 = S.pow43; T.tabinfo = S.tabinfo;
     T.c1info[0] = (uint32_t)kC1Base | (6u << 16);
     T.c1info[1] = (uint32_t)(kC1Base + 64) | (4u << 16);
-    T.sfb_long = S.sfb_long; T.sfb_short = S.sfb_short; T.sfb_mixed = S.sfb_mixed;
+    T.sfb_long = S.sfb; T.sfb_short = S.sfb + kSfbShort; T.sfb_mixed = S.sfb + kSfbMixed;
 
     WarpScratch &W = scratch[warp];
     const uint32_t n_groups = (a.n_order + 31)/32;
@@ -111,7 +131,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock*32, 2) k_l3_entropy(EntropyArgs
             const bool use_d0 = valid && (d.flags1 & GCF1_GR1) && d.scfsi;
             if (use_d0) d0 = load_desc(a.gcs + (gc - ((d.flags1 & GCF1_STEREO) ? 2 : 1)));
             dec.init(d, use_d0 ? &d0 : nullptr, a.md_words, a.md_n_words, T, W.iscf + lane, W.prev + lane, 32,
-                     want_ist ? ist_local : nullptr, &n_ist);
+                     want_ist ? ist_local : nullptr, &n_ist,
+                     (uint32_t)(warp*sizeof(WarpScratch) + offsetof(WarpScratch, iscf) + lane));
             if (want_ist)
             {
                 uint8_t *o = a.ist_pos + (size_t)gc*40;
@@ -170,7 +191,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock*32, 2) k_l3_entropy(EntropyArgs
 cudaError_t launch_entropy(const DeviceTables &, const EntropyArgs &a, cudaStream_t s)
 {
     if (!a.n_order) return cudaSuccess;
-    const size_t smem = ((sizeof(SharedTables) + 15) & ~15) + sizeof(WarpScratch)*kWarpsPerBlock;
+    const size_t smem = sizeof(WarpScratch)*kWarpsPerBlock;     /* the tables are static shared memory */
     const bool taps = a.tap_q != nullptr;       /* the parity tests want the signed integers as well */
     cudaError_t e = taps ? cudaFuncSetAttribute(k_l3_entropy<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
                          : cudaFuncSetAttribute(k_l3_entropy<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -189,3 +210,24 @@ cudaError_t launch_entropy(const DeviceTables &, const EntropyArgs &a, cudaStrea
 }
 
 }  // namespace mp3b
+
+/* ---- test tap (include/minimp3_b200.h): the requantiser's |x|^(4/3) evaluated on the device ---- */
+namespace {
+__global__ void k_pow43_tap(float *out, int n)
+{
+    const int x = blockIdx.x*blockDim.x + threadIdx.x;
+    if (x < n) out[x] = mp3b::l3_pow43(x, MP3T_POW43);
+}
+}  // namespace
+
+extern "C" int mp3dec_b200_pow43_device(float *dst, int n)
+{
+    if (!dst || n < 0 || n > 8207) return -1;     /* MP3D_E_PARAM */
+    if (!n) return 0;
+    float *d = nullptr;
+    if (cudaMalloc(&d, (size_t)n*sizeof(float)) != cudaSuccess) return -2;    /* MP3D_E_MEMORY */
+    k_pow43_tap<<<(n + 255)/256, 256>>>(d, n);
+    const cudaError_t e = cudaMemcpy(dst, d, (size_t)n*sizeof(float), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    return e == cudaSuccess ? 0 : -2;
+}

@@ -16,7 +16,23 @@
 
 namespace mp3b {
 
-/* pointers to the decode tables (shared memory on the device, plain arrays on the host) */
+/*
+ * Table access.  By default through the pointers below.  The entropy kernel keeps the tables in a file-scope
+ * __shared__ struct and defines these accessors (before including this header) to name that struct directly:
+ * a pointer that has been through a struct member is a generic address to the compiler, and every use of one
+ * costs it the shared-window base again (S2R + LEA) -- a dozen extra instructions per decoded line pair.
+ */
+#ifndef MP3B_ENT_LUT
+#define MP3B_ENT_LUT(T, i) ((T).lut[i])
+#define MP3B_ENT_POW43(T) ((T).pow43)
+#define MP3B_ENT_TABINFO(T, i) ((T).tabinfo[i])
+#define MP3B_ENT_SFBW(dec, i) ((dec).sfbw[i])
+#define MP3B_ENT_ISCF(dec, b) ((dec).iscf[(b)*(dec).iscf_st])
+#define MP3B_ENT_SET_SFBW(dec, T, kind, row) \
+    ((dec).sfbw = (kind) == 0 ? (T).sfb_long + (row)*23 : (kind) == 1 ? (T).sfb_mixed + (row)*40 : (T).sfb_short + (row)*40)
+#endif
+
+/* pointers to the decode tables (plain arrays on the host) */
 struct EntropyTables
 {
     const uint16_t *lut;        /* MP3T_HUFF_LUT */
@@ -257,18 +273,20 @@ struct GranuleDecoder
     const uint8_t *sfbw;      /* band widths of this granule's partition */
     const uint8_t *iscf;      /* final integer scalefactors, stride iscf_st */
     int iscf_st;
+    uint32_t sfbw_off, iscf_off;   /* the same two as offsets, for accessors that address shared memory by name */
     float gain, one;
     int scf_shift, limit;
     int mode, big_left, band_left, band_idx, ireg, reg_left, pending, extent;
     uint32_t tinfo;
     uint8_t table_select[3], region_count[3];
-    bool count1_b;
+    uint32_t c1info;          /* T.c1info[] entry of this granule's count1 table */
 
     /* scalefactors + set-up.  iscf_buf / prev_buf: 40 bytes each at stride st.  d0: descriptor of granule 0
      * of the same frame/channel when this is granule 1 with scfsi != 0 (else nullptr).
      * ist_out: optional [40] intensity positions. */
     MP3_HD void init(const GcDesc &d, const GcDesc *d0, const uint32_t *words, uint64_t n_words, const EntropyTables &T,
-                     uint8_t *iscf_buf, uint8_t *prev_buf, int st, uint8_t *ist_out, int *n_ist)
+                     uint8_t *iscf_buf, uint8_t *prev_buf, int st, uint8_t *ist_out, int *n_ist,
+                     uint32_t iscf_buf_off = 0)
     {
         const bool mpeg1 = (d.flags1 & GCF1_MPEG1) != 0;
         const uint8_t *prev = nullptr;
@@ -304,12 +322,12 @@ struct GranuleDecoder
         }
         iscf = iscf_buf;
         iscf_st = st;
+        iscf_off = iscf_buf_off;
         /* global gain (minimp3.h:708-709): BITS_DEQUANTIZER_OUT = -1, MAX_SCFI = 44 */
         const int gain_exp = (int)d.global_gain - 4 - 210 - ((d.flags0 & GCF_MS_STEREO) ? 2 : 0);
         gain = l3_ldexp_q2(2048.0f, 44 - gain_exp);
 
-        sfbw = d.n_short_sfb ? (d.n_long_sfb ? T.sfb_mixed + d.sr_idx*40 : T.sfb_short + d.sr_idx*40)
-                             : T.sfb_long + d.sr_idx*23;
+        MP3B_ENT_SET_SFBW(*this, T, d.n_short_sfb ? (d.n_long_sfb ? 1 : 2) : 0, d.sr_idx);
         limit = d.part_23_length;
         mode = d.big_values ? EMODE_BIG : EMODE_C1A;
         big_left = d.big_values;
@@ -317,13 +335,13 @@ struct GranuleDecoder
         ireg = 0;
         for (int i = 0; i < 3; i++) { table_select[i] = d.table_select[i]; region_count[i] = d.region_count[i]; }
         reg_left = region_count[0] + 1;
-        tinfo = T.tabinfo[table_select[0]];
+        tinfo = MP3B_ENT_TABINFO(T, table_select[0]);
         one = 0.f;
         pending = 0; extent = 0;
-        count1_b = (d.flags0 & GCF_COUNT1_TABLE) != 0;
+        c1info = (d.flags0 & GCF_COUNT1_TABLE) ? T.c1info[1] : T.c1info[0];
     }
 
-    MP3_HD float band_scale(int b) const { return l3_ldexp_q2(gain, (int)iscf[b*iscf_st] << scf_shift); }
+    MP3_HD float band_scale(int b) const { return l3_ldexp_q2(gain, (int)MP3B_ENT_ISCF(*this, b) << scf_shift); }
 
     /* next two lines; q0/q1 receive the signed quantised values.  Big-value pairs and count1 half-quads share
      * one code path (a count1 line is a value of magnitude 0 or 1: one * pow43(1) == one exactly), so lanes in
@@ -334,16 +352,11 @@ struct GranuleDecoder
     {
         v0 = v1 = 0.f;
         q0 = q1 = 0;
-#if defined(__CUDA_ARCH__)
-        /* the tables and the scalefactor scratch live in shared memory on the device: lets the compiler use LDS */
-        __builtin_assume(__isShared(T.lut)); __builtin_assume(__isShared(T.pow43)); __builtin_assume(__isShared(T.tabinfo));
-        __builtin_assume(__isShared(sfbw)); __builtin_assume(__isShared(iscf));
-#endif
         if (mode == EMODE_DONE) return;
         if (band_left == 0)
         {
             /* next scalefactor band (minimp3.h:788-790, 865); region / code-book switch only while in big values */
-            const int wd = sfbw[band_idx];
+            const int wd = MP3B_ENT_SFBW(*this, band_idx);
             if (!wd) { mode = EMODE_DONE; return; }
             band_left = wd >> 1;
             one = band_scale(band_idx);
@@ -355,7 +368,7 @@ struct GranuleDecoder
                     ireg++;
                     const int ts = ireg == 1 ? table_select[1] : table_select[2];
                     const int rc = ireg == 1 ? region_count[1] : region_count[2];
-                    tinfo = T.tabinfo[ts];
+                    tinfo = MP3B_ENT_TABINFO(T, ts);
                     reg_left = rc + 1;
                 }
                 reg_left--;
@@ -365,19 +378,19 @@ struct GranuleDecoder
         if (mode != EMODE_C1B)
         {
             const bool big = mode == EMODE_BIG;
-            const uint32_t info = big ? tinfo : T.c1info[count1_b ? 1 : 0];
+            const uint32_t info = big ? tinfo : c1info;
             const int base = (int)(info & 0xFFFF), rootw = (int)((info >> 16) & 15);
             int e = 0;
             br.refill();
             if (rootw)
             {
-                e = T.lut[base + br.peek(rootw)];
+                e = MP3B_ENT_LUT(T, base + br.peek(rootw));
                 int wcur = rootw;
                 while (e & 0x8000)
                 {
                     br.skip(wcur);
                     wcur = (e >> 11) & 15;
-                    e = T.lut[base + (e & 0x7FF) + br.peek(wcur)];
+                    e = MP3B_ENT_LUT(T, base + (e & 0x7FF) + br.peek(wcur));
                 }
                 br.skip(e >> 8);
             }
@@ -416,8 +429,8 @@ struct GranuleDecoder
             const uint32_t neg_y = t3 & (0u - (uint32_t)s2) & 0x80000000u;
             br.skip(n1 + s1 + n2 + s2);
             /* a zero value gives one * 0 = +0 and reads no sign */
-            v0 = flip_sign(MP3_FMUL(one, l3_pow43(x, T.pow43)), neg_x);
-            v1 = flip_sign(MP3_FMUL(one, l3_pow43(y, T.pow43)), neg_y);
+            v0 = flip_sign(MP3_FMUL(one, l3_pow43(x, MP3B_ENT_POW43(T))), neg_x);
+            v1 = flip_sign(MP3_FMUL(one, l3_pow43(y, MP3B_ENT_POW43(T))), neg_y);
             if (WANT_Q)
             {
                 q0 = neg_x ? -x : x;

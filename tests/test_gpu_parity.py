@@ -291,6 +291,19 @@ def test_mixed_layer_corpus(m, ref):
         assert np.abs(o["pcm"].astype(np.int32) - want.astype(np.int32)).max() <= 1
 
 
+def test_device_pow43_is_bit_exact_over_the_whole_range(m, ref):
+    # L3_pow_43 (minimp3.h:716-740) on the device, every magnitude a 13-bit escape can produce; the device
+    # divides without the compiler's slow-path call (l3_div_small), so all 8207 quotients are checked
+    n = 8207
+    got = np.zeros(n, np.float32)
+    assert m.load().mp3dec_b200_pow43_device(got.ctypes.data, n) == 0
+    ref.lib.ref_const_pow43.restype = C.c_float
+    ref.lib.ref_const_pow43.argtypes = [C.c_int]
+    want = np.array([ref.lib.ref_const_pow43(x) for x in range(n)], np.float32)
+    bad = np.where(got.view(np.uint32) != want.view(np.uint32))[0]
+    assert len(bad) == 0, bad[:10]
+
+
 def test_f32_to_s16(m, ref_f32):
     rng = np.random.default_rng(3)
     x = np.concatenate([rng.uniform(-1.2, 1.2, 10007), np.array([0.5/32768, -0.5/32768, 1.5/32768, -1.5/32768, 1.0, -1.0])]).astype(np.float32)
