@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(kFramesPerBlock*12) k_l12_dequant(Layer12Args 
         l12_read_scale_info(d.hdr, d.kbps, br, &F.sci, true);
         F.group = d.n_blocks == 1 ? 1 : 3;
         F.sub_bits = l12_subblock_bits(F.sci, F.group);
-        F.sample_bit_off = d.bit_off + (uint64_t)br.pos;
+        F.sample_bit_off = d.bit_off + (uint64_t)br.bits_consumed();
     }
     __syncthreads();
 

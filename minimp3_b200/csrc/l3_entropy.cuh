@@ -62,10 +62,10 @@ struct BitRd
 {
     const uint32_t *wp;     /* next word to fetch */
     const uint32_t *wend;   /* end of the buffer (host harness only) */
-    uint32_t hi, lo;        /* window, MSB-aligned: `avail` valid bits from bit 31 of hi downwards */
-    uint32_t next, next2;   /* two words of lookahead; next2 still in memory byte order */
-    int avail;
-    int pos;                /* bits consumed since init */
+    uint32_t hi, lo;        /* two consecutive words of the stream, big-endian applied */
+    uint32_t next, next2;   /* the two words behind them; next2 still in memory byte order */
+    int off;                /* cursor: bit offset into hi:lo, < 64; < 32 after normalize() */
+    int base;               /* bits consumed up to the first bit of hi */
 
     /* a word as stored (big-endian bit order not applied yet).  The device buffer carries 64 bytes of slack
      * behind the last payload byte (capi.cu), the host harness is bounds-checked. */
@@ -98,43 +98,38 @@ struct BitRd
     {
         wend = words + nw;
         wp = words + (bit_off >> 5);
-        const int sh = (int)(bit_off & 31);
-        const uint32_t w0 = be(raw(wp)), w1 = be(raw(wp + 1));
-        hi = shl_hi(w0, w1, sh);
-        lo = w1 << sh;
-        avail = 64 - sh;
+        hi = be(raw(wp));
+        lo = be(raw(wp + 1));
         next = be(raw(wp + 2));
         next2 = raw(wp + 3);
         wp += 4;
-        pos = 0;
+        off = (int)(bit_off & 31);
+        base = -off;
     }
-    /* Tops the window up to more than 32 valid bits.  Written without a branch: in a warp of 32 granules some
-     * lane needs the refill at almost every call, so a divergent region (and its reconvergence stall) would be
-     * paid every time anyway. */
-    MP3_HD void refill()
+    /* Brings the cursor back into the first word (needs off < 64).  The words only move, nothing is shifted: the
+     * cursor is applied by top() / top2() when bits are looked at, and consuming bits is one addition.  Written
+     * without a branch: in a warp of 32 granules some lane crosses a word at almost every call. */
+    MP3_HD void normalize()
     {
-        const bool need = avail <= 32;          /* lo holds no valid bits any more */
-        const int sh = (32 - avail) & 31;       /* need: 0..31, append `next` right below the valid bits of hi */
-        const uint32_t nx = need ? next : 0u;
-        hi |= shl_hi(0u, nx, sh);
-        lo = need ? next << sh : lo;
-        avail += need ? 32 : 0;
-        next = need ? be(next2) : next;         /* the byte swap waits here, one refill after the load was issued */
-        if (need) next2 = raw(wp);
-        wp += need ? 1 : 0;
+        const bool adv = off >= 32;
+        hi = adv ? lo : hi;
+        lo = adv ? next : lo;
+        next = adv ? be(next2) : next;          /* the byte swap waits here, one word after the load was issued */
+        if (adv) next2 = raw(wp);
+        wp += adv ? 1 : 0;
+        off -= adv ? 32 : 0;
+        base += adv ? 32 : 0;
     }
-    MP3_HD uint32_t peek(int n) const { return n ? hi >> (32 - n) : 0u; }
-    MP3_HD void skip(int n)
-    {
-        hi = shl_hi(hi, lo, n);
-        lo <<= n;
-        avail -= n;
-        pos += n;
-    }
+    /* the 32 bits at the cursor, and the 32 behind them (cursor < 32) */
+    MP3_HD uint32_t top() const { return shl_hi(hi, lo, off); }
+    MP3_HD uint32_t top2() const { return shl_hi(lo, next, off); }
+    MP3_HD void skip(int n) { off += n; }
+    MP3_HD int bits_consumed() const { return base + off; }
+    /* 0 <= n <= 32 */
     MP3_HD uint32_t get(int n)
     {
-        refill();
-        const uint32_t v = peek(n);
+        normalize();
+        const uint32_t v = n ? top() >> (32 - n) : 0u;
         skip(n);
         return v;
     }
@@ -230,8 +225,8 @@ MP3_HD int read_scalefactors(BitRd &br, const ScfLayout &L, int scfsi, bool lsf,
 #endif
             for (int k = 0; k < cnt; )
             {
-                br.refill();
-                uint32_t win = br.hi;
+                br.normalize();
+                uint32_t win = br.top();
                 const int n = cnt - k < 6 ? cnt - k : 6;
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
@@ -374,6 +369,11 @@ struct GranuleDecoder
                 reg_left--;
             }
         }
+        /* one look at the stream per step: t0 = the 32 bits at the cursor; the code (19 bits at most) is walked
+         * inside t0 with a local count c, and the cursor moves once, at the end */
+        br.normalize();
+        const uint32_t t0 = br.top();
+        int c = 0;
         int x, y, linbits = 0;
         if (mode != EMODE_C1B)
         {
@@ -381,18 +381,17 @@ struct GranuleDecoder
             const uint32_t info = big ? tinfo : c1info;
             const int base = (int)(info & 0xFFFF), rootw = (int)((info >> 16) & 15);
             int e = 0;
-            br.refill();
             if (rootw)
             {
-                e = MP3B_ENT_LUT(T, base + br.peek(rootw));
+                e = MP3B_ENT_LUT(T, base + (t0 >> (32 - rootw)));
                 int wcur = rootw;
                 while (e & 0x8000)
                 {
-                    br.skip(wcur);
-                    wcur = (e >> 11) & 15;
-                    e = MP3B_ENT_LUT(T, base + (e & 0x7FF) + br.peek(wcur));
+                    c += wcur;
+                    wcur = (e >> 11) & 15;      /* 1..8 */
+                    e = MP3B_ENT_LUT(T, base + (e & 0x7FF) + ((t0 << c) >> (32 - wcur)));
                 }
-                br.skip(e >> 8);
+                c += e >> 8;
             }
             if (big)
             {
@@ -402,7 +401,7 @@ struct GranuleDecoder
             } else
             {
                 /* count1 quad: stop when its code ends past the granule's bit budget (minimp3.h:852-864) */
-                if (br.pos > limit) { mode = EMODE_DONE; return; }
+                if (br.bits_consumed() + c > limit) { mode = EMODE_DONE; return; }
                 x = (e >> 3) & 1;
                 y = (e >> 2) & 1;
                 pending = e & 3;
@@ -412,14 +411,12 @@ struct GranuleDecoder
             x = (pending >> 1) & 1;
             y = pending & 1;
         }
-        /* escapes and signs of both values (minimp3.h:807-826) from one snapshot of the window, without
-         * branches.  The refill at the top left more than 32 bits and a code takes 19 at most, so the two sign
-         * bits are always there; only escapes (up to 2*13 more bits, rare) need the window topped up again. */
+        /* escapes and signs of both values (minimp3.h:807-826) without branches, from the 32 bits behind the
+         * code: the reader holds 96 bits from the start of the cursor's word, a step takes 19 + 2*(13 + 1) at most */
         {
             const int n1 = x == 15 ? linbits : 0, s1 = x != 0;
             const int n2 = y == 15 ? linbits : 0, s2 = y != 0;
-            if (n1 | n2) br.refill();
-            const uint32_t t = br.hi;
+            const uint32_t t = BitRd::shl_hi(t0, br.top2(), c);
             x += (int)((t >> 1) >> (31 - n1));
             const uint32_t t1 = t << n1;
             const uint32_t neg_x = t1 & (0u - (uint32_t)s1) & 0x80000000u;     /* sign bit in place */
@@ -427,7 +424,10 @@ struct GranuleDecoder
             y += (int)((t2 >> 1) >> (31 - n2));
             const uint32_t t3 = t2 << n2;
             const uint32_t neg_y = t3 & (0u - (uint32_t)s2) & 0x80000000u;
-            br.skip(n1 + s1 + n2 + s2);
+            br.skip(c + n1 + s1 + n2 + s2);
+            /* only a step with escapes can leave the cursor beyond the second word: take one word off now so that
+             * the next call's normalize() finds it below 64 */
+            if (n1 | n2) br.normalize();
             /* a zero value gives one * 0 = +0 and reads no sign */
             v0 = flip_sign(MP3_FMUL(one, l3_pow43(x, MP3B_ENT_POW43(T))), neg_x);
             v1 = flip_sign(MP3_FMUL(one, l3_pow43(y, MP3B_ENT_POW43(T))), neg_y);
