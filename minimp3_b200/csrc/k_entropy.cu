@@ -53,10 +53,8 @@ extern __shared__ __align__(16) unsigned char g_scratch[];
 #define MP3B_ENT_LUT(T, i) (g_tabs.lut[i])
 #define MP3B_ENT_POW43(T) (g_tabs.pow43)
 #define MP3B_ENT_TABINFO(T, i) (g_tabs.tabinfo[i])
-#define MP3B_ENT_SFBW(dec, i) (g_tabs.sfb[(dec).sfbw_off + (i)])
-#define MP3B_ENT_ISCF(dec, b) (g_scratch[(dec).iscf_off + (b)*32])
-#define MP3B_ENT_SET_SFBW(dec, T, kind, row) \
-    ((dec).sfbw_off = (kind) == 0 ? (row)*23 : (kind) == 1 ? kSfbMixed + (row)*40 : kSfbShort + (row)*40)
+#define MP3B_ENT_SFB(T, kind, row) \
+    (g_tabs.sfb + ((kind) == 0 ? (row)*23 : (kind) == 1 ? kSfbMixed + (row)*40 : kSfbShort + (row)*40))
 #endif
 #include "l3_entropy.cuh"
 
@@ -131,8 +129,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock*32, 2) k_l3_entropy(EntropyArgs
             const bool use_d0 = valid && (d.flags1 & GCF1_GR1) && d.scfsi;
             if (use_d0) d0 = load_desc(a.gcs + (gc - ((d.flags1 & GCF1_STEREO) ? 2 : 1)));
             dec.init(d, use_d0 ? &d0 : nullptr, a.md_words, a.md_n_words, T, W.iscf + lane, W.prev + lane, 32,
-                     want_ist ? ist_local : nullptr, &n_ist,
-                     (uint32_t)(warp*sizeof(WarpScratch) + offsetof(WarpScratch, iscf) + lane));
+                     want_ist ? ist_local : nullptr, &n_ist);
             if (want_ist)
             {
                 uint8_t *o = a.ist_pos + (size_t)gc*40;

@@ -26,10 +26,8 @@ namespace mp3b {
 #define MP3B_ENT_LUT(T, i) ((T).lut[i])
 #define MP3B_ENT_POW43(T) ((T).pow43)
 #define MP3B_ENT_TABINFO(T, i) ((T).tabinfo[i])
-#define MP3B_ENT_SFBW(dec, i) ((dec).sfbw[i])
-#define MP3B_ENT_ISCF(dec, b) ((dec).iscf[(b)*(dec).iscf_st])
-#define MP3B_ENT_SET_SFBW(dec, T, kind, row) \
-    ((dec).sfbw = (kind) == 0 ? (T).sfb_long + (row)*23 : (kind) == 1 ? (T).sfb_mixed + (row)*40 : (T).sfb_short + (row)*40)
+#define MP3B_ENT_SFB(T, kind, row) \
+    ((kind) == 0 ? (T).sfb_long + (row)*23 : (kind) == 1 ? (T).sfb_mixed + (row)*40 : (T).sfb_short + (row)*40)
 #endif
 
 /* pointers to the decode tables (plain arrays on the host) */
@@ -268,10 +266,10 @@ struct GranuleDecoder
     const uint8_t *sfbw;      /* band widths of this granule's partition */
     const uint8_t *iscf;      /* final integer scalefactors, stride iscf_st */
     int iscf_st;
-    uint32_t sfbw_off, iscf_off;   /* the same two as offsets, for accessors that address shared memory by name */
+    const uint8_t *sfbw_run, *iscf_run;   /* the next band's entries: per-lane pointers that only ever advance */
     float gain, one;
     int scf_shift, limit;
-    int mode, big_left, band_left, band_idx, ireg, reg_left, pending, extent;
+    int mode, big_left, band_left, ireg, reg_left, pending, extent;
     uint32_t tinfo;
     uint8_t table_select[3], region_count[3];
     uint32_t c1info;          /* T.c1info[] entry of this granule's count1 table */
@@ -280,8 +278,7 @@ struct GranuleDecoder
      * of the same frame/channel when this is granule 1 with scfsi != 0 (else nullptr).
      * ist_out: optional [40] intensity positions. */
     MP3_HD void init(const GcDesc &d, const GcDesc *d0, const uint32_t *words, uint64_t n_words, const EntropyTables &T,
-                     uint8_t *iscf_buf, uint8_t *prev_buf, int st, uint8_t *ist_out, int *n_ist,
-                     uint32_t iscf_buf_off = 0)
+                     uint8_t *iscf_buf, uint8_t *prev_buf, int st, uint8_t *ist_out, int *n_ist)
     {
         const bool mpeg1 = (d.flags1 & GCF1_MPEG1) != 0;
         const uint8_t *prev = nullptr;
@@ -317,16 +314,17 @@ struct GranuleDecoder
         }
         iscf = iscf_buf;
         iscf_st = st;
-        iscf_off = iscf_buf_off;
+        iscf_run = iscf_buf;
         /* global gain (minimp3.h:708-709): BITS_DEQUANTIZER_OUT = -1, MAX_SCFI = 44 */
         const int gain_exp = (int)d.global_gain - 4 - 210 - ((d.flags0 & GCF_MS_STEREO) ? 2 : 0);
         gain = l3_ldexp_q2(2048.0f, 44 - gain_exp);
 
-        MP3B_ENT_SET_SFBW(*this, T, d.n_short_sfb ? (d.n_long_sfb ? 1 : 2) : 0, d.sr_idx);
+        sfbw = MP3B_ENT_SFB(T, d.n_short_sfb ? (d.n_long_sfb ? 1 : 2) : 0, d.sr_idx);
+        sfbw_run = sfbw;
         limit = d.part_23_length;
         mode = d.big_values ? EMODE_BIG : EMODE_C1A;
         big_left = d.big_values;
-        band_left = 0; band_idx = 0;
+        band_left = 0;
         ireg = 0;
         for (int i = 0; i < 3; i++) { table_select[i] = d.table_select[i]; region_count[i] = d.region_count[i]; }
         reg_left = region_count[0] + 1;
@@ -336,7 +334,7 @@ struct GranuleDecoder
         c1info = (d.flags0 & GCF_COUNT1_TABLE) ? T.c1info[1] : T.c1info[0];
     }
 
-    MP3_HD float band_scale(int b) const { return l3_ldexp_q2(gain, (int)MP3B_ENT_ISCF(*this, b) << scf_shift); }
+    MP3_HD float band_scale(int b) const { return l3_ldexp_q2(gain, (int)iscf[b*iscf_st] << scf_shift); }
 
     /* next two lines; q0/q1 receive the signed quantised values.  Big-value pairs and count1 half-quads share
      * one code path (a count1 line is a value of magnitude 0 or 1: one * pow43(1) == one exactly), so lanes in
@@ -351,11 +349,16 @@ struct GranuleDecoder
         if (band_left == 0)
         {
             /* next scalefactor band (minimp3.h:788-790, 865); region / code-book switch only while in big values */
-            const int wd = MP3B_ENT_SFBW(*this, band_idx);
+#if defined(__CUDA_ARCH__)
+            /* both run through shared memory on the device; as per-lane pointers in registers they cost one LDS
+             * each (an index into a named table would have its base rebuilt at every use) */
+            __builtin_assume(__isShared(sfbw_run)); __builtin_assume(__isShared(iscf_run));
+#endif
+            const int wd = *sfbw_run++;
             if (!wd) { mode = EMODE_DONE; return; }
             band_left = wd >> 1;
-            one = band_scale(band_idx);
-            band_idx++;
+            one = l3_ldexp_q2(gain, (int)*iscf_run << scf_shift);
+            iscf_run += iscf_st;
             if (mode == EMODE_BIG)
             {
                 if (reg_left == 0)
