@@ -222,7 +222,8 @@ void mp3dec_batch_plan_destroy(mp3dec_batch_plan_t *plan);
 /* Test taps (parity tests): device-side intermediates of the last mp3dec_batch_plan_run(), copied to host.
  * which: 0 quantised lines int16[n_gc][576], 1 scalefactors float[n_gc][40], 2 requantised spectra
  * float[n_gc][576] (after MS, zero beyond nzl), 3 subband samples float[n_gc][576], 4 GcDesc records,
- * 5 ist_pos uint8[n_gc][40].  Taps must be enabled before run. */
+ * 5 ist_pos uint8[n_gc][40], 8 the entropy kernel's lane order uint32[n_order] (readable without enabling taps).
+ * Taps must be enabled before run. */
 int mp3dec_batch_plan_enable_taps(mp3dec_batch_plan_t *plan);
 int mp3dec_batch_plan_read_tap(mp3dec_batch_plan_t *plan, int which, void *dst, size_t dst_bytes);
 /* Test tap: |x|^(4/3) for x = 0 .. n-1 (n <= 8207) exactly as the entropy kernel's requantiser evaluates it

@@ -239,6 +239,13 @@ class BatchPlan:
         shapes = {0: ((n, 576), np.int16), 1: ((n, 40), np.float32), 2: ((n, 576), np.float32), 3: ((n, 576), np.float32),
                   4: ((n, 32), np.uint8), 5: ((n, 40), np.uint8), 6: ((n,), np.uint16),
                   7: ((int(self.stats["n_tiles"]), 16), np.int64)}
+        if which == 8:
+            # lane order of the entropy kernel: one entry per real Layer III granule-channel (<= n), rest stays ~0
+            a = np.full(n, 0xFFFFFFFF, np.uint32)
+            r = self.L.mp3dec_batch_plan_read_tap(self.handle, which, a.ctypes.data, a.nbytes)
+            if r:
+                raise RuntimeError("read_tap(8) failed: %d" % r)
+            return a[a != 0xFFFFFFFF]
         shape, dt = shapes[which]
         a = np.zeros(shape, dt)
         r = self.L.mp3dec_batch_plan_read_tap(self.handle, which, a.ctypes.data, a.nbytes)

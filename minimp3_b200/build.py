@@ -17,7 +17,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libminimp3_b200.so")
 HARNESS = os.path.join(ROOT, "tests", "_build", "libmp3b_cpu_harness.so")
 
-CU_SOURCES = ["k_entropy.cu", "k_stereo.cu", "k_transform.cu", "k_layer12.cu", "k_sideinfo.cu", "capi.cu"]
+CU_SOURCES = ["k_entropy.cu", "k_stereo.cu", "k_transform.cu", "k_layer12.cu", "k_sideinfo.cu", "k_order.cu", "capi.cu"]
 CPP_SOURCES = ["host_parse.cpp", "ex_api.cpp"]
 HEADERS = ["l3_types.h", "l3_math.cuh", "l3_entropy.cuh", "l3_sideinfo.cuh", "l12_decode.cuh", "l3_tables_build.h", "kernels.h", "host_parse.h", "mp3_tables.h",
            os.path.join("..", "..", "include", "minimp3_b200.h")]

@@ -170,14 +170,14 @@ struct PinBuf
 /* all device + pinned memory of one in-flight batch; recycled between calls */
 struct BufferSet
 {
-    PinBuf h_md, h_gcs, h_frames, h_tiles, h_ist, h_order, h_pcm, h_l12, h_tiles12;
-    DevBuf d_md, d_gcs, d_frames, d_tiles, d_tile_recs, d_tile_jobs, d_counter, d_istlist, d_order, d_xr, d_nzl, d_istpos, d_pcm, d_l12, d_tiles12, d_sub12;
+    PinBuf h_md, h_gcs, h_frames, h_tiles, h_ist, h_order, h_gcbase, h_pcm, h_l12, h_tiles12;
+    DevBuf d_md, d_gcs, d_frames, d_tiles, d_tile_recs, d_tile_jobs, d_counter, d_istlist, d_order, d_order_sorted, d_order_scratch, d_gcbase, d_xr, d_nzl, d_istpos, d_pcm, d_l12, d_tiles12, d_sub12;
     DevBuf d_tap_q, d_tap_scf, d_tap_sub, d_phase_clk;
     void release()
     {
-        h_md.release(); h_gcs.release(); h_frames.release(); h_tiles.release(); h_ist.release(); h_order.release(); h_pcm.release(); h_l12.release(); h_tiles12.release();
+        h_md.release(); h_gcs.release(); h_frames.release(); h_tiles.release(); h_ist.release(); h_order.release(); h_gcbase.release(); h_pcm.release(); h_l12.release(); h_tiles12.release();
         d_l12.release(); d_tiles12.release(); d_sub12.release();
-        d_md.release(); d_gcs.release(); d_frames.release(); d_tiles.release(); d_tile_recs.release(); d_tile_jobs.release(); d_counter.release(); d_istlist.release(); d_order.release(); d_xr.release(); d_nzl.release();
+        d_md.release(); d_gcs.release(); d_frames.release(); d_tiles.release(); d_tile_recs.release(); d_tile_jobs.release(); d_counter.release(); d_istlist.release(); d_order.release(); d_order_sorted.release(); d_order_scratch.release(); d_gcbase.release(); d_xr.release(); d_nzl.release();
         d_istpos.release(); d_pcm.release(); d_tap_q.release(); d_tap_scf.release(); d_tap_sub.release(); d_phase_clk.release();
     }
 };
@@ -251,6 +251,9 @@ size_t round_up(size_t v, size_t a) { return (v + a - 1)/a*a; }
 
 }  // namespace
 
+/* fewer granule-channels or streams than this: the per-stream order of the host walker is used as it is */
+static const uint64_t kMinOrderSort = 8192;
+
 struct mp3dec_batch_plan
 {
     DeviceCtx *ctx = nullptr;
@@ -265,6 +268,7 @@ struct mp3dec_batch_plan
     size_t sample_size = 2;
     bool taps = false;
     cudaEvent_t ev_kernels = nullptr, ev_d2h = nullptr, ev_h2d = nullptr;
+    bool order_sorted = false;     /* the entropy kernel reads d_order_sorted (order across streams, k_order.cu) */
     bool d2h_started = false;
     mp3dec_batch_stats_t stats{};
 };
@@ -432,7 +436,7 @@ static mp3dec_batch_plan_t *plan_create_impl(const mp3dec_batch_stream_t *stream
         /* descriptor vectors are no longer needed on the host */
         std::vector<GcDesc>().swap(sp.gcs);
         std::vector<FrameRec>().swap(sp.frame_recs);
-        std::vector<uint16_t>().swap(sp.gc_len);
+        std::vector<uint32_t>().swap(sp.gc_key);
         std::vector<TileDesc>().swap(sp.tiles);
         std::vector<GranuleRef>().swap(sp.granules);
         std::vector<uint32_t>().swap(sp.istereo_gcs);
@@ -440,10 +444,23 @@ static mp3dec_batch_plan_t *plan_create_impl(const mp3dec_batch_stream_t *stream
     const double t1 = now_ms();
 
     /* ---- device buffers + H2D ---- */
+    const bool sort_order = frs && orders >= kMinOrderSort && n_streams >= 2;
+    const size_t order_scratch = sort_order ? order_sort_scratch_bytes((uint32_t)orders) : 0;
+    uint32_t max_slots = 0;
+    if (sort_order)
+    {
+        if (!B.h_gcbase.ensure(((size_t)n_streams + 1)*4 + 64)) { *err = MP3D_E_MEMORY; mp3dec_batch_plan_destroy(P); return nullptr; }
+        uint32_t *gb = (uint32_t *)B.h_gcbase.p;
+        for (int i = 0; i <= n_streams; i++) gb[i] = (uint32_t)P->gc_base[i];
+        for (int i = 0; i < n_streams; i++) max_slots = std::max(max_slots, gb[i + 1] - gb[i]);
+    }
     ok = B.d_md.ensure(P->md_bytes) && B.d_gcs.ensure((size_t)gcs*sizeof(GcDesc) + 64) && B.d_frames.ensure((size_t)frs*sizeof(FrameRec) + 64) &&
          B.d_tiles.ensure((size_t)tiles*sizeof(TileDesc) + 64) && B.d_tile_recs.ensure((size_t)tiles*sizeof(TileRec) + 256) && B.d_tile_jobs.ensure((size_t)tiles*MP3B_TILE_JOBS*2 + 256) && B.d_counter.ensure(256) &&
          B.d_istlist.ensure((size_t)ists*4 + 64) &&
-         B.d_order.ensure((size_t)orders*4 + 64) && B.d_l12.ensure((size_t)l12s*sizeof(L12FrameDesc) + 64) &&
+         B.d_order.ensure((size_t)orders*4 + 64) &&
+         (!sort_order || (B.d_order_sorted.ensure((size_t)orders*4 + 64) && B.d_order_scratch.ensure(order_scratch) &&
+                          B.d_gcbase.ensure(((size_t)n_streams + 1)*4 + 64))) &&
+         B.d_l12.ensure((size_t)l12s*sizeof(L12FrameDesc) + 64) &&
          B.d_tiles12.ensure((size_t)tiles12*sizeof(TileDesc) + 64) && B.d_sub12.ensure((size_t)blks*384*sizeof(float) + 64) &&
          B.d_xr.ensure((size_t)gcs*576*sizeof(float) + 64) && B.d_nzl.ensure((size_t)gcs*2 + 64) &&
          B.d_istpos.ensure((size_t)gcs*40 + 64) && B.d_pcm.ensure((size_t)samples*P->sample_size + 64);
@@ -458,6 +475,7 @@ static mp3dec_batch_plan_t *plan_create_impl(const mp3dec_batch_stream_t *stream
     if (tiles) cudaMemcpyAsync(B.d_tiles.p, B.h_tiles.p, (size_t)tiles*sizeof(TileDesc), cudaMemcpyHostToDevice, up);
     if (ists) cudaMemcpyAsync(B.d_istlist.p, B.h_ist.p, (size_t)ists*4, cudaMemcpyHostToDevice, up);
     if (orders) cudaMemcpyAsync(B.d_order.p, B.h_order.p, (size_t)orders*4, cudaMemcpyHostToDevice, up);
+    if (sort_order) cudaMemcpyAsync(B.d_gcbase.p, B.h_gcbase.p, ((size_t)n_streams + 1)*4, cudaMemcpyHostToDevice, up);
     if (l12s) cudaMemcpyAsync(B.d_l12.p, B.h_l12.p, (size_t)l12s*sizeof(L12FrameDesc), cudaMemcpyHostToDevice, up);
     if (tiles12) cudaMemcpyAsync(B.d_tiles12.p, B.h_tiles12.p, (size_t)tiles12*sizeof(TileDesc), cudaMemcpyHostToDevice, up);
     if (up != P->stream)
@@ -472,6 +490,20 @@ static mp3dec_batch_plan_t *plan_create_impl(const mp3dec_batch_stream_t *stream
         *err = MP3D_E_CUDA;
         mp3dec_batch_plan_destroy(P);
         return nullptr;
+    }
+    /* the walker ordered every stream's granule-channels by size; with enough of them the GPU redoes it across the
+     * streams of a window, which is what fills the entropy kernel's warps evenly when streams are alike */
+    if (sort_order)
+    {
+        if (launch_order_sort((const GcDesc *)B.d_gcs.p, (const uint32_t *)B.d_order.p, (uint32_t)orders, (uint32_t *)B.d_order_sorted.p,
+                              (const uint32_t *)B.d_gcbase.p, (uint32_t)n_streams, max_slots, B.d_order_scratch.p, order_scratch,
+                              P->stream) != cudaSuccess)
+        {
+            *err = MP3D_E_CUDA;
+            mp3dec_batch_plan_destroy(P);
+            return nullptr;
+        }
+        P->order_sorted = true;
     }
     float h2d = 0.f;
     if (!async)
@@ -545,7 +577,7 @@ static int plan_run_stages(mp3dec_batch_plan_t *P, int stage_mask)
     ea.md_n_words = P->md_bytes/4;
     ea.gcs = (const GcDesc *)B.d_gcs.p;
     ea.n_gc = (uint32_t)P->n_gc;
-    ea.order = (const uint32_t *)B.d_order.p;
+    ea.order = (const uint32_t *)(P->order_sorted ? B.d_order_sorted.p : B.d_order.p);
     ea.n_order = (uint32_t)P->n_order;
     ea.group_counter = (uint32_t *)B.d_counter.p;
     ea.xr = (float *)B.d_xr.p;
@@ -642,6 +674,7 @@ int mp3dec_batch_plan_read_tap(mp3dec_batch_plan_t *P, int which, void *dst, siz
     case 5: src = B.d_istpos.p; bytes = n*40; break;
     case 6: src = B.d_nzl.p; bytes = n*2; break;
     case 7: src = B.d_phase_clk.p; bytes = (size_t)P->n_tiles*128; break;
+    case 8: src = P->order_sorted ? B.d_order_sorted.p : B.d_order.p; bytes = (size_t)P->n_order*4; break;
     default: return MP3D_E_PARAM;
     }
     if ((which == 0 || which == 1 || which == 3 || which == 7) && !P->taps) return MP3D_E_PARAM;

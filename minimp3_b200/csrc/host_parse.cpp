@@ -405,16 +405,16 @@ static void build_order(StreamPlan *plan)
 {
     uint32_t count[257];
     memset(count, 0, sizeof(count));
-    if (!plan->gc_len.empty() || plan->gcs.empty())
+    if (!plan->gc_key.empty() || plan->gcs.empty())
     {
-        /* device_side_info: lengths were kept per descriptor slot, 0xFFFF marks the padding slots */
-        const size_t n = plan->gc_len.size();
+        /* device_side_info: sizes were kept per descriptor slot, ~0 marks the padding slots */
+        const size_t n = plan->gc_key.size();
         for (size_t i = 0; i < n; i++)
-            if (plan->gc_len[i] != 0xFFFF) count[(plan->gc_len[i] >> 4) + 1]++;
+            if (plan->gc_key[i] != 0xFFFFFFFFu) count[((plan->gc_key[i] & 0xFFFF) >> 4) + 1]++;
         for (int b = 0; b < 256; b++) count[b + 1] += count[b];
         plan->order.resize(count[256]);
         for (size_t i = 0; i < n; i++)
-            if (plan->gc_len[i] != 0xFFFF) plan->order[count[plan->gc_len[i] >> 4]++] = (uint32_t)i;
+            if (plan->gc_key[i] != 0xFFFFFFFFu) plan->order[count[(plan->gc_key[i] & 0xFFFF) >> 4]++] = (uint32_t)i;
         return;
     }
     const size_t n = plan->gcs.size();
@@ -485,7 +485,7 @@ void walk_stream(const uint8_t *buf, size_t size, uint8_t *md_dst, uint64_t md_b
     {
         /* one allocation per array for the common constant-bit-rate case instead of log2(n) regrowths */
         const size_t guess = size/(size_t)std::max(first.frame_bytes, 96) + 8;
-        if (opt.device_side_info) { plan->frame_recs.reserve(guess); plan->gc_len.reserve(guess*4); }
+        if (opt.device_side_info) { plan->frame_recs.reserve(guess); plan->gc_key.reserve(guess*4); }
         else plan->gcs.reserve(guess*4);
         plan->granules.reserve(guess*3);
     }
@@ -531,7 +531,7 @@ void walk_stream(const uint8_t *buf, size_t size, uint8_t *md_dst, uint64_t md_b
                     {
                         /* keep stereo pairs on even indices (MS / intensity partners are gc ^ 1) */
                         padded = true;
-                        if (opt.device_side_info) plan->gc_len.push_back(0xFFFF);
+                        if (opt.device_side_info) plan->gc_key.push_back(0xFFFFFFFFu);
                         else
                         {
                             GcDesc pad;
@@ -553,7 +553,7 @@ void walk_stream(const uint8_t *buf, size_t size, uint8_t *md_dst, uint64_t md_b
                     for (int ch = 0; ch < fp.nch; ch++)
                     {
                         const GranuleSide &g = fp.side[igr*fp.nch + ch];
-                        if (opt.device_side_info) plan->gc_len.push_back(g.part_23_length);
+                        if (opt.device_side_info) plan->gc_key.push_back((uint32_t)g.big_values << 16 | g.part_23_length);
                         else
                         {
                             GcDesc d;

@@ -94,7 +94,7 @@ struct StreamPlan
     /* device work */
     std::vector<GcDesc> gcs;               /* host-side descriptors (single-frame API, CPU harness) ... */
     std::vector<FrameRec> frame_recs;      /* ... or, with WalkOptions.device_side_info, the frames k_l3_side_info turns into them */
-    std::vector<uint16_t> gc_len;          /* device_side_info: part_23_length per descriptor slot, 0xFFFF = padding slot */
+    std::vector<uint32_t> gc_key;          /* device_side_info: big_values << 16 | part_23_length per descriptor slot, ~0 = padding slot */
     uint32_t n_gc = 0;                     /* descriptor slots of the stream (= gcs.size() in host mode) */
     std::vector<GranuleRef> granules;
     std::vector<TileDesc> tiles;

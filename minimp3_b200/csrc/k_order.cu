@@ -1,0 +1,112 @@
+/*
+ * k_order.cu -- lane order of the entropy kernel across the streams of a batch.
+ *
+ * The entropy kernel decodes 32 granule-channels per warp in lock step (one lane each), so a warp takes as long as
+ * its longest lane.  The host walker orders every stream's granule-channels by size on its own (build_order in
+ * host_parse.cpp).  Here the streams of a window of 32 consecutive streams are merged: inside a window the
+ * granule-channels are sorted by (big_values, part_23_length / 8) -- the two side-info fields L3_huffman's loops
+ * run on (minimp3.h:742-877; read by L3_read_side_info, minimp3.h:484-607) -- and, among equals, laid out position
+ * by position (slot k of every stream of the window next to each other).  Streams that are alike -- same material,
+ * same encoder settings; at best copies of each other, as in BASELINE.json's batch -- then fill whole warps with
+ * lanes of equal length (lane efficiency 0.81 -> 0.99 on that batch).  A window of unrelated streams loses a few
+ * per cent against the per-stream order: the two fields predict the line count poorly across sample rates and block
+ * types.  The window is small because the lanes of a warp should read their bitstreams from neighbouring memory:
+ * with 32 random streams of a 1024-stream batch per warp the kernel takes twice as long (one bitstream load then
+ * touches 32 pages instead of three).
+ *
+ * One kernel builds a 64-bit key per granule-channel, a stable radix sort (CUB, part of the CUDA toolkit; a
+ * preparation step like the H2D copies, once per plan) orders the list by it.
+ */
+#include <cuda_runtime.h>
+
+#include <cub/device/device_radix_sort.cuh>
+
+#include "kernels.h"
+
+namespace mp3b {
+
+namespace {
+
+constexpr int kWindowShift = 5;                   /* 32 streams per window */
+
+struct KeyLayout
+{
+    int pos_bits;       /* slot index inside the stream */
+    int total_bits;
+};
+
+/* key, most significant first: window | big_values (9, descending) | part_23_length / 8 (9, descending) | slot |
+ * stream inside the window (5) */
+__global__ void __launch_bounds__(256) k_order_keys(const GcDesc *__restrict__ gcs, const uint32_t *__restrict__ order_in, uint32_t n,
+                                                    const uint32_t *__restrict__ gc_base, uint32_t n_streams, int pos_bits,
+                                                    unsigned long long *__restrict__ keys)
+{
+    const uint32_t i = blockIdx.x*blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t gc = __ldg(order_in + i);
+    /* stream of this granule-channel: last s with gc_base[s] <= gc */
+    uint32_t lo = 0, hi = n_streams;
+    while (hi - lo > 1)
+    {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(gc_base + mid) <= gc) lo = mid; else hi = mid;
+    }
+    const uint32_t slot = gc - __ldg(gc_base + lo);
+    const uint32_t w = __ldg(reinterpret_cast<const uint32_t *>(gcs + gc) + 2);      /* part_23_length | big_values << 16 */
+    const uint32_t len8 = min((w & 0xffffu) >> 3, 511u), big = min(w >> 16, 511u);
+    unsigned long long k = lo >> kWindowShift;
+    /* longest first: the entropy kernel's warps claim their groups in list order, so the groups claimed last --
+     * the tail that decides when the kernel ends -- are the short ones */
+    k = k << 9 | (511u - big);
+    k = k << 9 | (511u - len8);
+    k = k << pos_bits | slot;
+    k = k << kWindowShift | (lo & ((1u << kWindowShift) - 1));
+    keys[i] = k;
+}
+
+int bits_for(uint64_t max_value)
+{
+    int b = 1;
+    while (b < 63 && (max_value >> b)) b++;
+    return b;
+}
+
+KeyLayout key_layout(uint32_t n_streams, uint32_t max_slots)
+{
+    KeyLayout L;
+    L.pos_bits = bits_for(max_slots ? max_slots - 1 : 0);
+    L.total_bits = bits_for((n_streams - 1) >> kWindowShift) + 9 + 9 + L.pos_bits + kWindowShift;
+    return L;
+}
+
+}  // namespace
+
+size_t order_sort_scratch_bytes(uint32_t n)
+{
+    size_t temp = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, temp, (const unsigned long long *)nullptr, (unsigned long long *)nullptr,
+                                    (const uint32_t *)nullptr, (uint32_t *)nullptr, (int)n);
+    /* two key arrays in front of CUB's own scratch */
+    return 2*((size_t)n*sizeof(unsigned long long) + 256) + temp + 256;
+}
+
+cudaError_t launch_order_sort(const GcDesc *gcs, const uint32_t *order_in, uint32_t n, uint32_t *order_out,
+                              const uint32_t *gc_base, uint32_t n_streams, uint32_t max_slots,
+                              void *scratch, size_t scratch_bytes, cudaStream_t s)
+{
+    if (!n || !n_streams) return cudaSuccess;
+    const KeyLayout L = key_layout(n_streams, max_slots);
+    if (L.total_bits > 64) return cudaErrorInvalidValue;
+    const size_t key_bytes = ((size_t)n*sizeof(unsigned long long) + 255) & ~(size_t)255;
+    unsigned long long *keys_in = (unsigned long long *)scratch;
+    unsigned long long *keys_out = (unsigned long long *)((char *)scratch + key_bytes);
+    void *temp = (char *)scratch + 2*key_bytes;
+    if (scratch_bytes < 2*key_bytes) return cudaErrorInvalidValue;
+    size_t temp_bytes = scratch_bytes - 2*key_bytes;
+    k_order_keys<<<(n + 255)/256, 256, 0, s>>>(gcs, order_in, n, gc_base, n_streams, L.pos_bits, keys_in);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    return cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys_in, keys_out, order_in, order_out, (int)n, 0, L.total_bits, s);
+}
+
+}  // namespace mp3b

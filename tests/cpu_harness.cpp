@@ -97,7 +97,7 @@ int h_walk_frame_recs(const uint8_t *buf, size_t size, int raw, int allow, GcDes
     scalars[7] = plan.avg_bitrate_kbps; scalars[8] = (int64_t)plan.main_data_bytes; scalars[9] = plan.frames;
     scalars[10] = plan.frames_decoded; scalars[11] = (int64_t)plan.n_gc; scalars[12] = (int64_t)plan.tiles.size();
     scalars[13] = (int64_t)plan.granules.size(); scalars[14] = (int64_t)plan.istereo_gcs.size();
-    if (!plan.gcs.empty() || plan.gc_len.size() != plan.n_gc) return -1;
+    if (!plan.gcs.empty() || plan.gc_key.size() != plan.n_gc) return -1;
     for (const FrameRec &fr : plan.frame_recs)
     {
         GcDesc d[4];

@@ -291,6 +291,34 @@ def test_mixed_layer_corpus(m, ref):
         assert np.abs(o["pcm"].astype(np.int32) - want.astype(np.int32)).max() <= 1
 
 
+def test_regrouped_lane_order_lists_every_granule_channel_once(m):
+    # capi.cu regroup_lane_order: streams of a window of 32 are merged position by position and sorted by
+    # (big_values, part_23_length / 8); every real granule-channel must still be listed exactly once, and copies of
+    # one stream must end up in whole warps of the same granule-channel
+    data = [load_vector("l3-sin1k0db")]*64 + [load_vector("l3-compl"), load_vector("l3-he_mode"), load_vector("l1-fl1")]*3
+    plan = m.BatchPlan(data, device=0)
+    try:
+        plan.run()
+        plan.sync()
+        order = plan.read_tap(8).astype(np.int64)
+        assert len(np.unique(order)) == len(order)
+        n_real = {}
+        for d in set(data):
+            one = m.BatchPlan([d], device=0)
+            one.run()
+            one.sync()
+            n_real[d] = (len(one.read_tap(8)), int(one.stats["n_granule_channels"]))
+            one.close()
+        assert len(order) == sum(n_real[d][0] for d in data)
+        # first window: 32 copies of one stream -> lanes 32 k .. 32 k + 31 hold slot j of streams 0..31
+        per = n_real[data[0]][1]
+        first = order[:32*n_real[data[0]][0]].reshape(-1, 32)
+        assert np.all(first % per == first[:, :1] % per)
+        assert np.all(np.sort(first // per, axis=1) == np.arange(32))
+    finally:
+        plan.close()
+
+
 def test_device_pow43_is_bit_exact_over_the_whole_range(m, ref):
     # L3_pow_43 (minimp3.h:716-740) on the device, every magnitude a 13-bit escape can produce; the device
     # divides without the compiler's slow-path call (l3_div_small), so all 8207 quotients are checked
