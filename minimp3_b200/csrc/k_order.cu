@@ -31,14 +31,15 @@ constexpr int kWindowShift = 5;                   /* 32 streams per window */
 
 struct KeyLayout
 {
-    int pos_bits;       /* slot index inside the stream */
+    int pos_bits;       /* slot index inside the stream ... */
+    int pos_shift;      /* ... without its lowest bits when the key would not fit into 64 (never below ~10^9 slots) */
     int total_bits;
 };
 
 /* key, most significant first: window | big_values (9, descending) | part_23_length / 8 (9, descending) | slot |
  * stream inside the window (5) */
 __global__ void __launch_bounds__(256) k_order_keys(const GcDesc *__restrict__ gcs, const uint32_t *__restrict__ order_in, uint32_t n,
-                                                    const uint32_t *__restrict__ gc_base, uint32_t n_streams, int pos_bits,
+                                                    const uint32_t *__restrict__ gc_base, uint32_t n_streams, int pos_bits, int pos_shift,
                                                     unsigned long long *__restrict__ keys)
 {
     const uint32_t i = blockIdx.x*blockDim.x + threadIdx.x;
@@ -59,7 +60,7 @@ __global__ void __launch_bounds__(256) k_order_keys(const GcDesc *__restrict__ g
      * the tail that decides when the kernel ends -- are the short ones */
     k = k << 9 | (511u - big);
     k = k << 9 | (511u - len8);
-    k = k << pos_bits | slot;
+    k = k << pos_bits | (slot >> pos_shift);
     k = k << kWindowShift | (lo & ((1u << kWindowShift) - 1));
     keys[i] = k;
 }
@@ -75,7 +76,14 @@ KeyLayout key_layout(uint32_t n_streams, uint32_t max_slots)
 {
     KeyLayout L;
     L.pos_bits = bits_for(max_slots ? max_slots - 1 : 0);
-    L.total_bits = bits_for((n_streams - 1) >> kWindowShift) + 9 + 9 + L.pos_bits + kWindowShift;
+    L.pos_shift = 0;
+    const int fixed_bits = bits_for((n_streams - 1) >> kWindowShift) + 9 + 9 + kWindowShift;
+    if (fixed_bits + L.pos_bits > 64)
+    {
+        L.pos_shift = fixed_bits + L.pos_bits - 64;
+        L.pos_bits -= L.pos_shift;
+    }
+    L.total_bits = fixed_bits + L.pos_bits;
     return L;
 }
 
@@ -96,14 +104,13 @@ cudaError_t launch_order_sort(const GcDesc *gcs, const uint32_t *order_in, uint3
 {
     if (!n || !n_streams) return cudaSuccess;
     const KeyLayout L = key_layout(n_streams, max_slots);
-    if (L.total_bits > 64) return cudaErrorInvalidValue;
     const size_t key_bytes = ((size_t)n*sizeof(unsigned long long) + 255) & ~(size_t)255;
     unsigned long long *keys_in = (unsigned long long *)scratch;
     unsigned long long *keys_out = (unsigned long long *)((char *)scratch + key_bytes);
     void *temp = (char *)scratch + 2*key_bytes;
     if (scratch_bytes < 2*key_bytes) return cudaErrorInvalidValue;
     size_t temp_bytes = scratch_bytes - 2*key_bytes;
-    k_order_keys<<<(n + 255)/256, 256, 0, s>>>(gcs, order_in, n, gc_base, n_streams, L.pos_bits, keys_in);
+    k_order_keys<<<(n + 255)/256, 256, 0, s>>>(gcs, order_in, n, gc_base, n_streams, L.pos_bits, L.pos_shift, keys_in);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     return cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys_in, keys_out, order_in, order_out, (int)n, 0, L.total_bits, s);
