@@ -168,8 +168,9 @@ __global__ void __launch_bounds__(kWarpsPerBlock*32, kBlocksPerSm) k_l3_entropy(
                 /* every other round: the 32-byte sector leaves as a whole */
                 if (valid && 2*iter < my_end)
                 {
-                    *reinterpret_cast<float4 *>(row + 2*iter - 4) = held;
-                    *reinterpret_cast<float4 *>(row + 2*iter) = v;
+                    /* streaming stores: 0.5 GB of spectra pass through, the 135 MB of bitstream should keep the L2 */
+                    __stcs(reinterpret_cast<float4 *>(row + 2*iter - 4), held);
+                    __stcs(reinterpret_cast<float4 *>(row + 2*iter), v);
                 }
             } else
                 held = v;
