@@ -24,7 +24,7 @@ namespace mp3b {
 namespace {
 
 constexpr int kWarpsPerBlock = 16;
-constexpr int kBlocksPerSm = 2;      /* 12 x 3 (36 warps per SM fit since the kernel is down to 54 registers): +1.5 % on dense streams, -1 % on config 2 */
+constexpr int kBlocksPerSm = 2;      /* 12 x 3 (36 warps per SM fit at 54 registers) measured twice: within +-5 % either way depending on the stream, slower on config 2 */
 constexpr int kC1Base = MP3T_HUFF_LUT_SIZE;          /* count1 table A (64 entries) then B (16) */
 constexpr int kSfbShort = 8*23, kSfbMixed = 8*23 + 8*40;
 
