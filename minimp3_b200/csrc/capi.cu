@@ -445,7 +445,7 @@ static mp3dec_batch_plan_t *plan_create_impl(const mp3dec_batch_stream_t *stream
 
     /* ---- device buffers + H2D ---- */
     const bool sort_order = frs && orders >= kMinOrderSort && n_streams >= 2;
-    const size_t order_scratch = sort_order ? order_sort_scratch_bytes((uint32_t)orders) : 0;
+    const size_t order_scratch = sort_order ? order_sort_scratch_bytes((uint32_t)orders, (uint32_t)n_streams) : 0;
     uint32_t max_slots = 0;
     if (sort_order)
     {

@@ -8,16 +8,20 @@
  * run on (minimp3.h:742-877; read by L3_read_side_info, minimp3.h:484-607) -- and, among equals, laid out position
  * by position (slot k of every stream of the window next to each other).  Streams that are alike -- same material,
  * same encoder settings; at best copies of each other, as in BASELINE.json's batch -- then fill whole warps with
- * lanes of equal length (lane efficiency 0.81 -> 0.99 on that batch).  A window of unrelated streams loses a few
- * per cent against the per-stream order: the two fields predict the line count poorly across sample rates and block
- * types.  The window is small because the lanes of a warp should read their bitstreams from neighbouring memory:
- * with 32 random streams of a 1024-stream batch per warp the kernel takes twice as long (one bitstream load then
- * touches 32 pages instead of three).
+ * lanes of equal length (lane efficiency 0.81 -> 0.99 on that batch).  A window of unrelated streams would lose a
+ * few per cent against the per-stream order (the two fields predict the line count poorly across sample rates and
+ * block types, and one stream per warp is the friendlier memory pattern), so a window is only merged when its
+ * streams are alike: k_order_alike counts, per window, the slots whose two fields equal those of the same slot of
+ * the window's first stream; below half, the window keeps the walker's order (stream, part_23_length / 16, slot).
+ * The window is small because the lanes of a warp should read their bitstreams from neighbouring memory: with 32
+ * random streams of a 1024-stream batch per warp the kernel takes twice as long (one bitstream load then touches
+ * 32 pages instead of three).
  *
- * One kernel builds a 64-bit key per granule-channel, a stable radix sort (CUB, part of the CUDA toolkit; a
+ * Two small kernels build a 64-bit key per granule-channel, a stable radix sort (CUB, part of the CUDA toolkit; a
  * preparation step like the H2D copies, once per plan) orders the list by it.
  */
 #include <cuda_runtime.h>
+#include <stdlib.h>
 
 #include <cub/device/device_radix_sort.cuh>
 
@@ -36,32 +40,97 @@ struct KeyLayout
     int total_bits;
 };
 
-/* key, most significant first: window | big_values (9, descending) | part_23_length / 8 (9, descending) | slot |
- * stream inside the window (5) */
-__global__ void __launch_bounds__(256) k_order_keys(const GcDesc *__restrict__ gcs, const uint32_t *__restrict__ order_in, uint32_t n,
-                                                    const uint32_t *__restrict__ gc_base, uint32_t n_streams, int pos_bits, int pos_shift,
-                                                    unsigned long long *__restrict__ keys)
+/* stream of a granule-channel: last s with gc_base[s] <= gc */
+__device__ __forceinline__ uint32_t stream_of(const uint32_t *__restrict__ gc_base, uint32_t n_streams, uint32_t gc)
 {
-    const uint32_t i = blockIdx.x*blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const uint32_t gc = __ldg(order_in + i);
-    /* stream of this granule-channel: last s with gc_base[s] <= gc */
     uint32_t lo = 0, hi = n_streams;
     while (hi - lo > 1)
     {
         const uint32_t mid = (lo + hi) >> 1;
         if (__ldg(gc_base + mid) <= gc) lo = mid; else hi = mid;
     }
+    return lo;
+}
+
+/* part_23_length | big_values << 16 of a descriptor */
+__device__ __forceinline__ uint32_t size_word(const GcDesc *__restrict__ gcs, uint32_t gc)
+{
+    return __ldg(reinterpret_cast<const uint32_t *>(gcs + gc) + 2);
+}
+
+/* stat[2 w] += slots of window w (outside its first stream) whose size fields equal the first stream's at the same
+ * slot, stat[2 w + 1] += slots compared */
+__global__ void __launch_bounds__(256) k_order_alike(const GcDesc *__restrict__ gcs, const uint32_t *__restrict__ order_in, uint32_t n,
+                                                     const uint32_t *__restrict__ gc_base, uint32_t n_streams, uint32_t *__restrict__ stat)
+{
+    const uint32_t i = blockIdx.x*blockDim.x + threadIdx.x;
+    uint32_t win = 0xFFFFFFFFu;
+    bool counted = false, same = false;
+    if (i < n)
+    {
+        const uint32_t gc = __ldg(order_in + i);
+        const uint32_t s = stream_of(gc_base, n_streams, gc), s0 = s & ~((1u << kWindowShift) - 1);
+        win = s >> kWindowShift;
+        if (s != s0)
+        {
+            counted = true;
+            const uint32_t slot = gc - __ldg(gc_base + s), first = __ldg(gc_base + s0);
+            if (slot < __ldg(gc_base + s0 + 1) - first)
+            {
+                const uint32_t a = size_word(gcs, gc), b = size_word(gcs, first + slot);
+                same = (a >> 16) == (b >> 16) && ((a & 0xffffu) >> 3) == ((b & 0xffffu) >> 3);
+            }
+        }
+    }
+    /* the list arrives stream by stream: a warp almost always sits inside one window and adds once */
+    const uint32_t win0 = __shfl_sync(0xffffffffu, win, 0);
+    if (__all_sync(0xffffffffu, win == win0))
+    {
+        const uint32_t n_same = __popc(__ballot_sync(0xffffffffu, same)), n_counted = __popc(__ballot_sync(0xffffffffu, counted));
+        if ((threadIdx.x & 31) == 0 && win0 != 0xFFFFFFFFu && n_counted)
+        {
+            atomicAdd(stat + 2*win0, n_same);
+            atomicAdd(stat + 2*win0 + 1, n_counted);
+        }
+    } else if (counted)
+    {
+        if (same) atomicAdd(stat + 2*win, 1u);
+        atomicAdd(stat + 2*win + 1, 1u);
+    }
+}
+
+/* key, most significant first, of a window whose streams are alike:
+ *     window | big_values (9, descending) | part_23_length / 8 (9, descending) | slot | stream inside the window (5)
+ * and of any other window (the walker's per-stream order):
+ *     window | stream inside the window (5) part_23_length / 16 (8) 0 (5) | slot | 0 (5) */
+__global__ void __launch_bounds__(256) k_order_keys(const GcDesc *__restrict__ gcs, const uint32_t *__restrict__ order_in, uint32_t n,
+                                                    const uint32_t *__restrict__ gc_base, uint32_t n_streams, int pos_bits, int pos_shift,
+                                                    const uint32_t *__restrict__ stat, int force, unsigned long long *__restrict__ keys)
+{
+    const uint32_t i = blockIdx.x*blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t gc = __ldg(order_in + i);
+    const uint32_t lo = stream_of(gc_base, n_streams, gc);
     const uint32_t slot = gc - __ldg(gc_base + lo);
-    const uint32_t w = __ldg(reinterpret_cast<const uint32_t *>(gcs + gc) + 2);      /* part_23_length | big_values << 16 */
-    const uint32_t len8 = min((w & 0xffffu) >> 3, 511u), big = min(w >> 16, 511u);
-    unsigned long long k = lo >> kWindowShift;
-    /* longest first: the entropy kernel's warps claim their groups in list order, so the groups claimed last --
-     * the tail that decides when the kernel ends -- are the short ones */
-    k = k << 9 | (511u - big);
-    k = k << 9 | (511u - len8);
-    k = k << pos_bits | (slot >> pos_shift);
-    k = k << kWindowShift | (lo & ((1u << kWindowShift) - 1));
+    const uint32_t w = size_word(gcs, gc);
+    const uint32_t win = lo >> kWindowShift, in_win = lo & ((1u << kWindowShift) - 1);
+    const bool alike = force >= 0 ? force != 0 : 2u*__ldg(stat + 2*win) >= __ldg(stat + 2*win + 1) && __ldg(stat + 2*win + 1) != 0;
+    unsigned long long k = win;
+    if (alike)
+    {
+        /* longest first: the entropy kernel's warps claim their groups in list order, so the groups claimed last --
+         * the tail that decides when the kernel ends -- are the short ones */
+        const uint32_t len8 = min((w & 0xffffu) >> 3, 511u), big = min(w >> 16, 511u);
+        k = k << 9 | (511u - big);
+        k = k << 9 | (511u - len8);
+        k = k << pos_bits | (slot >> pos_shift);
+        k = k << kWindowShift | in_win;
+    } else
+    {
+        k = k << 18 | (in_win << 13 | min((w & 0xffffu) >> 4, 255u) << 5);
+        k = k << pos_bits | (slot >> pos_shift);
+        k = k << kWindowShift;
+    }
     keys[i] = k;
 }
 
@@ -89,13 +158,13 @@ KeyLayout key_layout(uint32_t n_streams, uint32_t max_slots)
 
 }  // namespace
 
-size_t order_sort_scratch_bytes(uint32_t n)
+size_t order_sort_scratch_bytes(uint32_t n, uint32_t n_streams)
 {
     size_t temp = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, temp, (const unsigned long long *)nullptr, (unsigned long long *)nullptr,
                                     (const uint32_t *)nullptr, (uint32_t *)nullptr, (int)n);
-    /* two key arrays in front of CUB's own scratch */
-    return 2*((size_t)n*sizeof(unsigned long long) + 256) + temp + 256;
+    /* two key arrays and the per-window counters in front of CUB's own scratch */
+    return 2*((size_t)n*sizeof(unsigned long long) + 256) + ((((size_t)n_streams >> kWindowShift) + 1)*8 + 256) + temp + 256;
 }
 
 cudaError_t launch_order_sort(const GcDesc *gcs, const uint32_t *order_in, uint32_t n, uint32_t *order_out,
@@ -105,13 +174,20 @@ cudaError_t launch_order_sort(const GcDesc *gcs, const uint32_t *order_in, uint3
     if (!n || !n_streams) return cudaSuccess;
     const KeyLayout L = key_layout(n_streams, max_slots);
     const size_t key_bytes = ((size_t)n*sizeof(unsigned long long) + 255) & ~(size_t)255;
+    const size_t stat_bytes = ((((size_t)n_streams >> kWindowShift) + 1)*8 + 255) & ~(size_t)255;
     unsigned long long *keys_in = (unsigned long long *)scratch;
     unsigned long long *keys_out = (unsigned long long *)((char *)scratch + key_bytes);
-    void *temp = (char *)scratch + 2*key_bytes;
-    if (scratch_bytes < 2*key_bytes) return cudaErrorInvalidValue;
-    size_t temp_bytes = scratch_bytes - 2*key_bytes;
-    k_order_keys<<<(n + 255)/256, 256, 0, s>>>(gcs, order_in, n, gc_base, n_streams, L.pos_bits, L.pos_shift, keys_in);
-    cudaError_t e = cudaGetLastError();
+    uint32_t *stat = (uint32_t *)((char *)scratch + 2*key_bytes);
+    void *temp = (char *)scratch + 2*key_bytes + stat_bytes;
+    if (scratch_bytes < 2*key_bytes + stat_bytes) return cudaErrorInvalidValue;
+    size_t temp_bytes = scratch_bytes - 2*key_bytes - stat_bytes;
+    /* MP3B_DEBUG_ORDER_ALIKE=0 / 1: treat every window as unrelated / alike (experiments) */
+    static const int force = [] { const char *p = getenv("MP3B_DEBUG_ORDER_ALIKE"); return p ? atoi(p) : -1; }();
+    cudaError_t e = cudaMemsetAsync(stat, 0, stat_bytes, s);
+    if (e != cudaSuccess) return e;
+    if (force < 0) k_order_alike<<<(n + 255)/256, 256, 0, s>>>(gcs, order_in, n, gc_base, n_streams, stat);
+    k_order_keys<<<(n + 255)/256, 256, 0, s>>>(gcs, order_in, n, gc_base, n_streams, L.pos_bits, L.pos_shift, stat, force, keys_in);
+    e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     return cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys_in, keys_out, order_in, order_out, (int)n, 0, L.total_bits, s);
 }

@@ -93,9 +93,10 @@ cudaError_t launch_intensity_stereo(const DeviceTables &t, const StereoArgs &a, 
 /* Layer III side info of n_frames frames -> their GcDesc records (k_sideinfo.cu) */
 cudaError_t launch_side_info(const FrameRec *frames, uint32_t n_frames, GcDesc *gcs, cudaStream_t s);
 /* Lane order of the entropy kernel across the streams of a batch (k_order.cu): order_in[0..n) -> order_out, sorted
- * inside windows of 32 streams by (big_values, part_23_length / 8), equal keys position by position.  gc_base[i]:
+ * inside windows of 32 streams by (big_values, part_23_length / 8), equal keys position by position -- where the
+ * streams of a window are alike; other windows keep the walker's per-stream order.  gc_base[i]:
  * first descriptor slot of stream i (n_streams + 1 entries), max_slots: most slots any stream has. */
-size_t order_sort_scratch_bytes(uint32_t n);
+size_t order_sort_scratch_bytes(uint32_t n, uint32_t n_streams);
 cudaError_t launch_order_sort(const GcDesc *gcs, const uint32_t *order_in, uint32_t n, uint32_t *order_out,
                               const uint32_t *gc_base, uint32_t n_streams, uint32_t max_slots,
                               void *scratch, size_t scratch_bytes, cudaStream_t s);
