@@ -16,8 +16,6 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     for _ in range(3):
         plan.run_stage(0)
     torch.cuda.synchronize()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record(torch.cuda.current_stream())
     plan.sync()
     import time
     t0 = time.perf_counter()
