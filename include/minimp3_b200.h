@@ -186,6 +186,9 @@ typedef struct
     int host_threads;                 /* 0: all online cores */
     int output;                       /* MP3D_BATCH_OUT_* */
     void *cuda_stream;                /* cudaStream_t to run on, NULL: library-owned stream */
+    int n_devices;                    /* 0 / 1: `device` alone.  2..8: mp3dec_decode_batch_cuda shards the streams over */
+    int devices[8];                   /* devices[0 .. n_devices-1] (greedy LPT on input bytes, no collective); */
+                                      /* `device` is ignored then.  Plans (mp3dec_batch_plan_*) are single-device. */
 } mp3dec_batch_opts_t;
 
 /* Decodes n_streams independent buffers; per-stream result and return code (infos_out[i], rets_out[i],
@@ -193,6 +196,18 @@ typedef struct
  * MP3D_E_MEMORY / MP3D_E_CUDA if the batch as a whole could not run. */
 int mp3dec_decode_batch_cuda(const mp3dec_batch_stream_t *streams, int n_streams, mp3dec_file_info_t *infos_out,
                              int *rets_out, const mp3dec_batch_opts_t *opts);
+
+/* Where the time of the calling thread's last mp3dec_decode_batch_cuda() went (measurement aid). */
+typedef struct
+{
+    double total_ms;             /* whole call */
+    double host_parse_ms;        /* host stage (frame walk + staging copies), summed over the chunks of the call */
+    double issue_ms;             /* until the last chunk's kernels and read-back were queued */
+    double finish_ms;            /* waiting for the read-backs + output hand-over (malloc copies) */
+    uint64_t h2d_bytes, d2h_bytes;
+    int n_chunks, n_devices;
+} mp3dec_batch_call_stats_t;
+void mp3dec_batch_last_call_stats(mp3dec_batch_call_stats_t *out);
 
 /* Split form of the batch call, for callers that keep inputs resident (and for measurement):
  * plan = host parse + H2D; run = kernels only (asynchronous on the stream); fetch = D2H + infos. */
@@ -206,12 +221,14 @@ typedef struct
     uint64_t h2d_bytes;          /* bytes copied host to device by plan creation */
     int kernels_per_run;         /* kernel launches one mp3dec_batch_plan_run() issues */
     double host_parse_ms, h2d_ms;
+    int kernels_prep;            /* own kernels of the plan's GPU preparation (side-info parse, lane-order keys) */
 } mp3dec_batch_stats_t;
 
 mp3dec_batch_plan_t *mp3dec_batch_plan_create(const mp3dec_batch_stream_t *streams, int n_streams,
                                               const mp3dec_batch_opts_t *opts, int *err);
 int mp3dec_batch_plan_run(mp3dec_batch_plan_t *plan);
-/* measurement aid: one stage only (0 entropy, 1 intensity stereo, 2 transform) */
+/* measurement aid: one stage only (0 entropy, 1 intensity stereo, 2 transform, 3 Layer I/II, 4 the plan's GPU
+ * preparation: side-info parse + lane order, which plan creation already ran once) */
 int mp3dec_batch_plan_run_stage(mp3dec_batch_plan_t *plan, int stage);
 int mp3dec_batch_plan_sync(mp3dec_batch_plan_t *plan);
 int mp3dec_batch_plan_fetch(mp3dec_batch_plan_t *plan, mp3dec_file_info_t *infos_out, int *rets_out);
@@ -230,9 +247,9 @@ int mp3dec_batch_plan_read_tap(mp3dec_batch_plan_t *plan, int which, void *dst, 
  * (L3_pow_43, minimp3.h:716-740), computed on the current device.  0 or MP3D_E_MEMORY / MP3D_E_PARAM. */
 int mp3dec_b200_pow43_device(float *dst, int n);
 
-/* Multi-GPU sharding helper: assigns streams to n_shards by greedy longest-processing-time on input
- * bytes; shard_of[i] receives the shard of stream i.  No data-path collective exists: shards are
- * decoded independently, one process (or plan) per GPU. */
+/* Multi-GPU sharding helper (what opts.devices uses inside the batch call): assigns streams to n_shards by
+ * greedy longest-processing-time on input bytes; shard_of[i] receives the shard of stream i.  No data-path
+ * collective exists: shards are decoded independently. */
 void mp3dec_batch_shard(const size_t *sizes, int n_streams, int n_shards, int *shard_of);
 
 const char *mp3dec_b200_version(void);

@@ -45,14 +45,21 @@ class BatchStream(C.Structure):
 class BatchOpts(C.Structure):
     _fields_ = [("device", C.c_int), ("float_output", C.c_int), ("raw_frames", C.c_int),
                 ("allow_mono_stereo_transition", C.c_int), ("host_threads", C.c_int), ("output", C.c_int),
-                ("cuda_stream", C.c_void_p)]
+                ("cuda_stream", C.c_void_p), ("n_devices", C.c_int), ("devices", C.c_int*8)]
 
 
 class BatchStats(C.Structure):
     _fields_ = [("input_bytes", C.c_uint64), ("samples", C.c_uint64), ("n_granule_channels", C.c_uint64),
                 ("n_tiles", C.c_uint64), ("n_istereo_granules", C.c_uint64), ("n_frames", C.c_uint64),
                 ("h2d_bytes", C.c_uint64),
-                ("kernels_per_run", C.c_int), ("host_parse_ms", C.c_double), ("h2d_ms", C.c_double)]
+                ("kernels_per_run", C.c_int), ("host_parse_ms", C.c_double), ("h2d_ms", C.c_double),
+                ("kernels_prep", C.c_int)]
+
+
+class BatchCallStats(C.Structure):
+    _fields_ = [("total_ms", C.c_double), ("host_parse_ms", C.c_double), ("issue_ms", C.c_double),
+                ("finish_ms", C.c_double), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
+                ("n_chunks", C.c_int), ("n_devices", C.c_int)]
 
 
 EXPORTS = ["mp3dec_init", "mp3dec_decode_frame", "mp3dec_decode_frame_f32", "mp3dec_f32_to_s16", "mp3dec_detect_buf",
@@ -62,7 +69,7 @@ EXPORTS = ["mp3dec_init", "mp3dec_decode_frame", "mp3dec_decode_frame_f32", "mp3
            "mp3dec_batch_plan_read_tap", "mp3dec_b200_pow43_device", "mp3dec_batch_shard", "mp3dec_b200_version",
            "mp3dec_detect_cb", "mp3dec_load_cb", "mp3dec_iterate_buf", "mp3dec_iterate_cb", "mp3dec_ex_open_buf",
            "mp3dec_ex_open_cb", "mp3dec_ex_close", "mp3dec_ex_seek", "mp3dec_ex_read_frame", "mp3dec_ex_read",
-           "mp3dec_detect", "mp3dec_load", "mp3dec_iterate", "mp3dec_ex_open"]
+           "mp3dec_detect", "mp3dec_load", "mp3dec_iterate", "mp3dec_ex_open", "mp3dec_batch_last_call_stats"]
 
 
 class MapInfo(C.Structure):
@@ -120,6 +127,8 @@ def load():
     L.mp3dec_batch_plan_fetch.argtypes = [vp, C.POINTER(FileInfo), C.POINTER(C.c_int)]
     L.mp3dec_batch_plan_stats.argtypes = [vp, C.POINTER(BatchStats)]
     L.mp3dec_batch_plan_stats.restype = None
+    L.mp3dec_batch_last_call_stats.argtypes = [C.POINTER(BatchCallStats)]
+    L.mp3dec_batch_last_call_stats.restype = None
     L.mp3dec_batch_plan_device_pcm.argtypes = [vp]
     L.mp3dec_batch_plan_device_pcm.restype = vp
     L.mp3dec_batch_plan_destroy.argtypes = [vp]
@@ -152,9 +161,14 @@ def _as_u8(data):
 
 
 def _opts(device=0, float_output=False, raw_frames=False, allow_mono_stereo=False, host_threads=0, output=OUT_PINNED,
-          cuda_stream=None):
-    return BatchOpts(int(device), int(bool(float_output)), int(bool(raw_frames)), int(bool(allow_mono_stereo)),
-                     int(host_threads), int(output), C.c_void_p(cuda_stream) if cuda_stream else None)
+          cuda_stream=None, devices=None):
+    o = BatchOpts(int(device), int(bool(float_output)), int(bool(raw_frames)), int(bool(allow_mono_stereo)),
+                  int(host_threads), int(output), C.c_void_p(cuda_stream) if cuda_stream else None)
+    if devices:
+        o.n_devices = len(devices)
+        for i, d in enumerate(devices[:8]):
+            o.devices[i] = int(d)
+    return o
 
 
 def shard_streams(sizes, n_shards):
@@ -286,6 +300,20 @@ class _Batch:
         if err:
             raise RuntimeError("mp3dec_decode_batch_cuda failed: %d" % err)
         return sum(self.infos[i].samples for i in range(self.n))
+
+    def call_stats(self):
+        """where the time of the last call() on this thread went (mp3dec_batch_last_call_stats)"""
+        cs = BatchCallStats()
+        self.L.mp3dec_batch_last_call_stats(C.byref(cs))
+        return {f[0]: getattr(cs, f[0]) for f in BatchCallStats._fields_}
+
+    def free_outputs(self):
+        """MP3D_BATCH_OUT_MALLOC: hand the per-stream buffers back (the caller owns them)"""
+        if self.opts.output == OUT_MALLOC:
+            for i in range(self.n):
+                if self.infos[i].buffer:
+                    self.L.free(self.infos[i].buffer)
+                    self.infos[i].buffer = None
 
     def results(self, copy=True):
         dt = np.float32 if self.float_output else np.int16

@@ -36,10 +36,29 @@ double now_ms()
 class HostPool
 {
 public:
+    /* the pool of the calling thread: the process-wide one (all cores), or, inside a multi-device call, the
+     * device thread's share of the cores (set_current) so that the devices' host stages run side by side */
     static HostPool &get()
     {
-        static HostPool p;
+        if (current_) return *current_;
+        static HostPool p((int)std::thread::hardware_concurrency());
         return p;
+    }
+    static void set_current(HostPool *p) { current_ = p; }
+    explicit HostPool(int n)
+    {
+        if (n <= 0) n = 1;
+        for (int t = 0; t < n - 1; t++) workers_.emplace_back([this, t] { loop(t); });
+    }
+    ~HostPool()
+    {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            stop_ = true;
+            generation_++;
+        }
+        cv_.notify_all();
+        for (auto &w : workers_) w.join();
     }
     /* runs f(i) for i in [0, n) on up to `threads` workers (0 = all) plus the calling thread */
     void run(int n, int threads, const std::function<void(int)> &f)
@@ -72,22 +91,7 @@ public:
     }
 
 private:
-    HostPool()
-    {
-        int n = (int)std::thread::hardware_concurrency();
-        if (n <= 0) n = 1;
-        for (int t = 0; t < n - 1; t++) workers_.emplace_back([this, t] { loop(t); });
-    }
-    ~HostPool()
-    {
-        {
-            std::lock_guard<std::mutex> lk(mu_);
-            stop_ = true;
-            generation_++;
-        }
-        cv_.notify_all();
-        for (auto &w : workers_) w.join();
-    }
+    static thread_local HostPool *current_;
     void loop(int id)
     {
         uint64_t seen = 0;
@@ -126,6 +130,8 @@ private:
     uint64_t generation_ = 0;
     bool stop_ = false;
 };
+
+thread_local HostPool *HostPool::current_ = nullptr;
 
 template <class F>
 void parallel_for(int n, int threads, F f)
@@ -269,6 +275,10 @@ struct mp3dec_batch_plan
     bool taps = false;
     cudaEvent_t ev_kernels = nullptr, ev_d2h = nullptr, ev_h2d = nullptr;
     bool order_sorted = false;     /* the entropy kernel reads d_order_sorted (order across streams, k_order.cu) */
+    bool sort_order = false;
+    size_t order_scratch = 0;
+    uint32_t max_slots = 0;
+    uint64_t n_frame_recs = 0;
     bool d2h_started = false;
     mp3dec_batch_stats_t stats{};
 };
@@ -296,6 +306,27 @@ void mp3dec_batch_shard(const size_t *sizes, int n_streams, int n_shards, int *s
 
 static mp3dec_batch_plan_t *plan_create_impl(const mp3dec_batch_stream_t *streams, int n_streams,
                                              const mp3dec_batch_opts_t *opts_in, int *err, bool async);
+
+/* GPU preparation of a plan, behind the H2D copies: side info -> descriptors (k_l3_side_info) and the lane order of
+ * the entropy kernel across streams (k_order.cu).  Runs once at plan creation; stage 4 of
+ * mp3dec_batch_plan_run_stage repeats it so that a measurement can include every kernel of the job. */
+static int plan_prep(mp3dec_batch_plan_t *P)
+{
+    BufferSet &B = *P->bufs;
+    if (P->n_frame_recs && launch_side_info((const FrameRec *)B.d_frames.p, (uint32_t)P->n_frame_recs, (GcDesc *)B.d_gcs.p, P->stream) != cudaSuccess)
+        return MP3D_E_CUDA;
+    /* the walker ordered every stream's granule-channels by size; with enough of them the GPU redoes it across the
+     * streams of a window, which is what fills the entropy kernel's warps evenly when streams are alike */
+    if (P->sort_order)
+    {
+        if (launch_order_sort((const GcDesc *)B.d_gcs.p, (const uint32_t *)B.d_order.p, (uint32_t)P->n_order, (uint32_t *)B.d_order_sorted.p,
+                              (const uint32_t *)B.d_gcbase.p, (uint32_t)P->n_streams, P->max_slots, B.d_order_scratch.p, P->order_scratch,
+                              P->stream) != cudaSuccess)
+            return MP3D_E_CUDA;
+        P->order_sorted = true;
+    }
+    return 0;
+}
 
 mp3dec_batch_plan_t *mp3dec_batch_plan_create(const mp3dec_batch_stream_t *streams, int n_streams,
                                               const mp3dec_batch_opts_t *opts_in, int *err)
@@ -484,26 +515,12 @@ static mp3dec_batch_plan_t *plan_create_impl(const mp3dec_batch_stream_t *stream
         cudaEventRecord(P->ev_h2d, up);
         cudaStreamWaitEvent(P->stream, P->ev_h2d, 0);
     }
-    /* side info -> descriptors, once per plan (they stay resident for every run of the plan) */
-    if (frs && launch_side_info((const FrameRec *)B.d_frames.p, (uint32_t)frs, (GcDesc *)B.d_gcs.p, P->stream) != cudaSuccess)
+    P->sort_order = sort_order; P->order_scratch = order_scratch; P->max_slots = max_slots; P->n_frame_recs = frs;
+    if (plan_prep(P) != 0)
     {
         *err = MP3D_E_CUDA;
         mp3dec_batch_plan_destroy(P);
         return nullptr;
-    }
-    /* the walker ordered every stream's granule-channels by size; with enough of them the GPU redoes it across the
-     * streams of a window, which is what fills the entropy kernel's warps evenly when streams are alike */
-    if (sort_order)
-    {
-        if (launch_order_sort((const GcDesc *)B.d_gcs.p, (const uint32_t *)B.d_order.p, (uint32_t)orders, (uint32_t *)B.d_order_sorted.p,
-                              (const uint32_t *)B.d_gcbase.p, (uint32_t)n_streams, max_slots, B.d_order_scratch.p, order_scratch,
-                              P->stream) != cudaSuccess)
-        {
-            *err = MP3D_E_CUDA;
-            mp3dec_batch_plan_destroy(P);
-            return nullptr;
-        }
-        P->order_sorted = true;
     }
     float h2d = 0.f;
     if (!async)
@@ -530,6 +547,7 @@ static mp3dec_batch_plan_t *plan_create_impl(const mp3dec_batch_stream_t *stream
     P->stats.h2d_bytes = P->md_bytes + frs*sizeof(FrameRec) + tiles*sizeof(TileDesc) + ists*4 + orders*4 +
                          l12s*sizeof(L12FrameDesc) + tiles12*sizeof(TileDesc);
     P->stats.kernels_per_run = (orders ? 1 : 0) + (ists ? 1 : 0) + (tiles ? 2 : 0) + (l12s ? 1 : 0) + (tiles12 ? 1 : 0);
+    P->stats.kernels_prep = (frs ? 1 : 0) + (sort_order ? 2 : 0);    /* own kernels; the radix sort behind them is CUB's */
     P->stats.host_parse_ms = t1 - t0;
     P->stats.h2d_ms = h2d;
     return P;
@@ -552,10 +570,17 @@ static int plan_run_stages(mp3dec_batch_plan_t *P, int stage_mask);
 
 int mp3dec_batch_plan_run(mp3dec_batch_plan_t *P) { return plan_run_stages(P, 15); }
 
-/* measurement aid: launch a single stage (0 entropy, 1 intensity stereo, 2 transform) on the plan's stream */
+/* measurement aid: launch a single stage (0 entropy, 1 intensity stereo, 2 transform, 3 Layer I/II, 4 the plan's GPU
+ * preparation: side-info parse + lane order) on the plan's stream */
 int mp3dec_batch_plan_run_stage(mp3dec_batch_plan_t *P, int stage)
 {
-    if (stage < 0 || stage > 3) return MP3D_E_PARAM;
+    if (stage < 0 || stage > 4) return MP3D_E_PARAM;
+    if (stage == 4)
+    {
+        if (!P) return MP3D_E_PARAM;
+        cudaSetDevice(P->ctx->device);
+        return plan_prep(P);
+    }
     return plan_run_stages(P, 1 << stage);
 }
 
@@ -772,11 +797,91 @@ void mp3dec_batch_plan_destroy(mp3dec_batch_plan_t *P)
 /* Whole batch in one call.  Large batches are cut into chunks of streams and pipelined: while chunk c is being
  * decoded and its PCM travels back over PCIe (second stream), the host threads already walk chunk c+1 and its
  * bitstream goes up.  Per-stream results are independent of the chunking. */
+static thread_local mp3dec_batch_call_stats_t t_call_stats;
+
+void mp3dec_batch_last_call_stats(mp3dec_batch_call_stats_t *out)
+{
+    if (out) *out = t_call_stats;
+}
+
+/* opts->n_devices > 1: the streams are split over the listed GPUs by greedy LPT on input bytes (mp3dec_batch_shard)
+ * and every shard goes through the single-device call on its own host thread with its share of the host cores;
+ * results land in the caller's arrays at the streams' own indices.  No data-path collective: streams are
+ * independent. */
+static int decode_batch_multi(const mp3dec_batch_stream_t *streams, int n_streams, mp3dec_file_info_t *infos_out,
+                              int *rets_out, const mp3dec_batch_opts_t *opts)
+{
+    const int nd = std::min(opts->n_devices, 8);
+    const double call_t0 = now_ms();
+    for (int d = 0; d < nd; d++)
+        if (!get_ctx(opts->devices[d])) return MP3D_E_CUDA;
+    std::vector<size_t> sizes(n_streams);
+    for (int i = 0; i < n_streams; i++) sizes[i] = streams[i].size;
+    std::vector<int> shard_of(n_streams);
+    mp3dec_batch_shard(sizes.data(), n_streams, nd, shard_of.data());
+    std::vector<std::vector<int>> ids(nd);
+    for (int i = 0; i < n_streams; i++) ids[shard_of[i]].push_back(i);
+    /* one pool per device slot, each with an equal share of the cores; created on first use, kept */
+    static std::mutex pools_mu;
+    static std::vector<HostPool *> pools[9];
+    int cores = opts->host_threads > 0 ? opts->host_threads : (int)std::thread::hardware_concurrency();
+    if (cores < nd) cores = nd;
+    {
+        std::lock_guard<std::mutex> lk(pools_mu);
+        while ((int)pools[nd].size() < nd) pools[nd].push_back(new HostPool(std::max(1, cores/nd)));
+    }
+    std::vector<int> errs(nd, 0);
+    std::vector<mp3dec_batch_call_stats_t> stats(nd);
+    std::vector<std::thread> th;
+    for (int d = 0; d < nd; d++)
+        th.emplace_back([&, d] {
+            HostPool::set_current(pools[nd][d]);
+            const int n = (int)ids[d].size();
+            std::vector<mp3dec_batch_stream_t> sub(n);
+            std::vector<mp3dec_file_info_t> infos(infos_out ? n : 0);
+            std::vector<int> rets(n, 0);
+            for (int k = 0; k < n; k++) sub[k] = streams[ids[d][k]];
+            mp3dec_batch_opts_t o = *opts;
+            o.n_devices = 0;
+            o.device = opts->devices[d];
+            o.host_threads = 0;
+            errs[d] = n ? mp3dec_decode_batch_cuda(sub.data(), n, infos_out ? infos.data() : nullptr, rets.data(), &o) : 0;
+            mp3dec_batch_last_call_stats(&stats[d]);
+            if (!n) memset(&stats[d], 0, sizeof(stats[d]));
+            for (int k = 0; k < n; k++)
+            {
+                if (infos_out) infos_out[ids[d][k]] = infos[k];
+                if (rets_out) rets_out[ids[d][k]] = rets[k];
+            }
+            HostPool::set_current(nullptr);
+        });
+    for (auto &t : th) t.join();
+    mp3dec_batch_call_stats_t &cs = t_call_stats;
+    memset(&cs, 0, sizeof(cs));
+    int err = 0;
+    for (int d = 0; d < nd; d++)
+    {
+        if (errs[d] && !err) err = errs[d];
+        cs.host_parse_ms = std::max(cs.host_parse_ms, stats[d].host_parse_ms);
+        cs.issue_ms = std::max(cs.issue_ms, stats[d].issue_ms);
+        cs.finish_ms = std::max(cs.finish_ms, stats[d].finish_ms);
+        cs.h2d_bytes += stats[d].h2d_bytes; cs.d2h_bytes += stats[d].d2h_bytes;
+        cs.n_chunks += stats[d].n_chunks;
+    }
+    cs.n_devices = nd;
+    cs.total_ms = now_ms() - call_t0;
+    return err;
+}
+
 int mp3dec_decode_batch_cuda(const mp3dec_batch_stream_t *streams, int n_streams, mp3dec_file_info_t *infos_out,
                              int *rets_out, const mp3dec_batch_opts_t *opts)
 {
     if (!streams || n_streams < 0) return MP3D_E_PARAM;
+    if (opts && opts->n_devices > 1 && !opts->cuda_stream) return decode_batch_multi(streams, n_streams, infos_out, rets_out, opts);
     int err = 0;
+    const double call_t0 = now_ms();
+    mp3dec_batch_call_stats_t &cs = t_call_stats;
+    memset(&cs, 0, sizeof(cs));
     const bool user_stream = opts && opts->cuda_stream;
     int n_chunks = 1;
     if (!user_stream && n_streams >= 64)
@@ -791,9 +896,16 @@ int mp3dec_decode_batch_cuda(const mp3dec_batch_stream_t *streams, int n_streams
     {
         mp3dec_batch_plan_t *P = mp3dec_batch_plan_create(streams, n_streams, opts, &err);
         if (!P) return err;
+        cs.n_chunks = 1; cs.n_devices = 1;
+        cs.host_parse_ms = P->stats.host_parse_ms;
+        cs.h2d_bytes = P->stats.h2d_bytes;
+        cs.d2h_bytes = (P->opts.output == MP3D_BATCH_OUT_DEVICE) ? 0 : P->n_samples*P->sample_size;
         err = mp3dec_batch_plan_run(P);
+        cs.issue_ms = now_ms() - call_t0;
         if (!err) err = mp3dec_batch_plan_fetch(P, infos_out, rets_out);
         mp3dec_batch_plan_destroy(P);
+        cs.total_ms = now_ms() - call_t0;
+        cs.finish_ms = cs.total_ms - cs.issue_ms;
         return err;
     }
     std::vector<mp3dec_batch_plan_t *> plans(n_chunks, nullptr);
@@ -818,6 +930,9 @@ int mp3dec_decode_batch_cuda(const mp3dec_batch_stream_t *streams, int n_streams
         const double a0 = now_ms();
         plans[c] = plan_create_impl(streams + first[c], first[c + 1] - first[c], opts, &err, true);
         if (!plans[c]) break;
+        cs.host_parse_ms += plans[c]->stats.host_parse_ms;
+        cs.h2d_bytes += plans[c]->stats.h2d_bytes;
+        if (plans[c]->opts.output != MP3D_BATCH_OUT_DEVICE) cs.d2h_bytes += plans[c]->n_samples*plans[c]->sample_size;
         const double a1 = now_ms();
         err = mp3dec_batch_plan_run(plans[c]);
         const double a2 = now_ms();
@@ -844,6 +959,8 @@ int mp3dec_decode_batch_cuda(const mp3dec_batch_stream_t *streams, int n_streams
             mp3dec_batch_plan_destroy(plans[c]);
         }
     if (dbg_timing) fprintf(stderr, "issue %.3f ms, finish %.3f ms, destroy %.3f ms\n", tt1 - tt0, tt2 - tt1, now_ms() - tt2);
+    cs.n_chunks = n_chunks; cs.n_devices = 1;
+    cs.issue_ms = tt1 - call_t0; cs.finish_ms = tt2 - tt1; cs.total_ms = now_ms() - call_t0;
     return err;
 }
 
