@@ -209,7 +209,9 @@ def main():
     # rank r decodes streams r*S .. r*S + S - 1 of the cycle: independent streams, shards need no collective
     streams, names = corpus.build_streams(args.config, args.streams, first=rank*args.streams)
     stream = torch.cuda.Stream()
-    plan = m.BatchPlan(streams, device=local_rank, raw_frames=False, output=m.OUT_PINNED, cuda_stream=stream.cuda_stream)
+    # load_buf semantics per stream (tags, VBR-tag trimming); mono/stereo transitions allowed as in the reference's own test build
+    plan = m.BatchPlan(streams, device=local_rank, raw_frames=False, allow_mono_stereo=True, output=m.OUT_PINNED,
+                       cuda_stream=stream.cuda_stream)
     st = plan.stats
     samples_per_step = int(st["samples"])
 
@@ -308,7 +310,7 @@ def main():
             devs = list(range(n_dev))
             for key, output in (("e2e", m.OUT_PINNED), ("scope_ii", m.OUT_DEVICE), ("e2e_malloc", m.OUT_MALLOC)):
                 batch = m._Batch(all_streams, device=local_rank, devices=devs if n_dev > 1 else None, raw_frames=False,
-                                 output=output, host_threads=0)
+                                 allow_mono_stereo=True, output=output, host_threads=0)
                 ms_call, cs = timed_calls(batch, total_samples)
                 results[key] = (ms_call, cs)
                 del batch
