@@ -173,9 +173,12 @@ typedef struct
 } mp3dec_batch_stream_t;
 
 #define MP3D_BATCH_OUT_MALLOC 0   /* infos[i].buffer = malloc()ed host copy, caller free()s (drop-in) */
-#define MP3D_BATCH_OUT_PINNED 1   /* infos[i].buffer points into a pinned slab owned by the library, valid
-                                     until the next batch call on the same device */
+#define MP3D_BATCH_OUT_PINNED 1   /* infos[i].buffer points into a pinned slab owned by the library */
 #define MP3D_BATCH_OUT_DEVICE 2   /* infos[i].buffer is a device pointer into the library's PCM buffer */
+/* Lifetime of PINNED / DEVICE outputs of mp3dec_decode_batch_cuda: until the caller's next PINNED / DEVICE call on the
+ * same device, or mp3dec_batch_release_outputs(device).  Nothing else the library does (malloc-output batch calls,
+ * mp3dec_load_buf, the frame and streaming APIs, other threads' calls in malloc mode) touches them.  Outputs of a
+ * plan (mp3dec_batch_plan_fetch) live until mp3dec_batch_plan_destroy. */
 
 typedef struct
 {
@@ -196,6 +199,8 @@ typedef struct
  * MP3D_E_MEMORY / MP3D_E_CUDA if the batch as a whole could not run. */
 int mp3dec_decode_batch_cuda(const mp3dec_batch_stream_t *streams, int n_streams, mp3dec_file_info_t *infos_out,
                              int *rets_out, const mp3dec_batch_opts_t *opts);
+
+void mp3dec_batch_release_outputs(int device);
 
 /* Where the time of the calling thread's last mp3dec_decode_batch_cuda() went (measurement aid). */
 typedef struct

@@ -69,7 +69,7 @@ EXPORTS = ["mp3dec_init", "mp3dec_decode_frame", "mp3dec_decode_frame_f32", "mp3
            "mp3dec_batch_plan_read_tap", "mp3dec_b200_pow43_device", "mp3dec_batch_shard", "mp3dec_b200_version",
            "mp3dec_detect_cb", "mp3dec_load_cb", "mp3dec_iterate_buf", "mp3dec_iterate_cb", "mp3dec_ex_open_buf",
            "mp3dec_ex_open_cb", "mp3dec_ex_close", "mp3dec_ex_seek", "mp3dec_ex_read_frame", "mp3dec_ex_read",
-           "mp3dec_detect", "mp3dec_load", "mp3dec_iterate", "mp3dec_ex_open", "mp3dec_batch_last_call_stats"]
+           "mp3dec_detect", "mp3dec_load", "mp3dec_iterate", "mp3dec_ex_open", "mp3dec_batch_last_call_stats", "mp3dec_batch_release_outputs"]
 
 
 class MapInfo(C.Structure):
@@ -127,6 +127,8 @@ def load():
     L.mp3dec_batch_plan_fetch.argtypes = [vp, C.POINTER(FileInfo), C.POINTER(C.c_int)]
     L.mp3dec_batch_plan_stats.argtypes = [vp, C.POINTER(BatchStats)]
     L.mp3dec_batch_plan_stats.restype = None
+    L.mp3dec_batch_release_outputs.argtypes = [C.c_int]
+    L.mp3dec_batch_release_outputs.restype = None
     L.mp3dec_batch_last_call_stats.argtypes = [C.POINTER(BatchCallStats)]
     L.mp3dec_batch_last_call_stats.restype = None
     L.mp3dec_batch_plan_device_pcm.argtypes = [vp]

@@ -198,6 +198,10 @@ struct DeviceCtx
     cudaStream_t stream_h2d = nullptr;  /* chunk-pipelined calls: inputs of chunk c+1 go up while chunk c computes */
     std::mutex mu;
     std::vector<BufferSet *> free_sets;
+    /* sets whose PCM (pinned slab / device buffer) was handed to the caller by a MP3D_BATCH_OUT_PINNED / _DEVICE
+     * call: nobody reuses them -- not the library's internal batch calls either -- until the NEXT call of that kind
+     * on this device (or mp3dec_batch_release_outputs) */
+    std::vector<BufferSet *> exported_sets;
     /* single-frame API scratch */
     BufferSet frame_set;
     DevBuf d_state_in, d_state_out;
@@ -253,6 +257,16 @@ void release_set(DeviceCtx *c, BufferSet *s)
     else { s->release(); delete s; }
 }
 
+void release_exported(DeviceCtx *c)
+{
+    std::vector<BufferSet *> sets;
+    {
+        std::lock_guard<std::mutex> lock(c->mu);
+        sets.swap(c->exported_sets);
+    }
+    for (BufferSet *s : sets) release_set(c, s);
+}
+
 size_t round_up(size_t v, size_t a) { return (v + a - 1)/a*a; }
 
 }  // namespace
@@ -274,6 +288,7 @@ struct mp3dec_batch_plan
     size_t sample_size = 2;
     bool taps = false;
     cudaEvent_t ev_kernels = nullptr, ev_d2h = nullptr, ev_h2d = nullptr;
+    bool export_on_destroy = false; /* one-call entry point with pinned / device output: the caller holds pointers into bufs */
     bool order_sorted = false;     /* the entropy kernel reads d_order_sorted (order across streams, k_order.cu) */
     bool sort_order = false;
     size_t order_scratch = 0;
@@ -561,7 +576,7 @@ int mp3dec_batch_plan_enable_taps(mp3dec_batch_plan_t *P)
     const size_t n = (size_t)P->n_gc;
     if (!B.d_tap_q.ensure(n*576*2 + 64) || !B.d_tap_scf.ensure(n*40*4 + 64) || !B.d_tap_sub.ensure(n*576*4 + 64) ||
         !B.d_phase_clk.ensure((size_t)P->n_tiles*128 + 64)) return MP3D_E_MEMORY;
-    cudaMemset(B.d_phase_clk.p, 0, (size_t)P->n_tiles*128);
+    cudaMemsetAsync(B.d_phase_clk.p, 0, (size_t)P->n_tiles*128, P->stream);
     P->taps = true;
     return 0;
 }
@@ -790,7 +805,15 @@ void mp3dec_batch_plan_destroy(mp3dec_batch_plan_t *P)
     if (P->ev_kernels) cudaEventDestroy(P->ev_kernels);
     if (P->ev_d2h) cudaEventDestroy(P->ev_d2h);
     if (P->ev_h2d) cudaEventDestroy(P->ev_h2d);
-    if (P->bufs) release_set(P->ctx, P->bufs);
+    if (P->bufs)
+    {
+        if (P->export_on_destroy)
+        {
+            std::lock_guard<std::mutex> lock(P->ctx->mu);
+            P->ctx->exported_sets.push_back(P->bufs);
+        } else
+            release_set(P->ctx, P->bufs);
+    }
     delete P;
 }
 
@@ -802,6 +825,12 @@ static thread_local mp3dec_batch_call_stats_t t_call_stats;
 void mp3dec_batch_last_call_stats(mp3dec_batch_call_stats_t *out)
 {
     if (out) *out = t_call_stats;
+}
+
+void mp3dec_batch_release_outputs(int device)
+{
+    DeviceCtx *c = get_ctx(device);
+    if (c) release_exported(c);
 }
 
 /* opts->n_devices > 1: the streams are split over the listed GPUs by greedy LPT on input bytes (mp3dec_batch_shard)
@@ -883,6 +912,13 @@ int mp3dec_decode_batch_cuda(const mp3dec_batch_stream_t *streams, int n_streams
     mp3dec_batch_call_stats_t &cs = t_call_stats;
     memset(&cs, 0, sizeof(cs));
     const bool user_stream = opts && opts->cuda_stream;
+    const bool exports = opts && opts->output != MP3D_BATCH_OUT_MALLOC;
+    if (exports)
+    {
+        /* the pointers of the previous pinned / device-output call on this device end here */
+        DeviceCtx *c = get_ctx(opts->device);
+        if (c) release_exported(c);
+    }
     int n_chunks = 1;
     if (!user_stream && n_streams >= 64)
     {
@@ -896,6 +932,7 @@ int mp3dec_decode_batch_cuda(const mp3dec_batch_stream_t *streams, int n_streams
     {
         mp3dec_batch_plan_t *P = mp3dec_batch_plan_create(streams, n_streams, opts, &err);
         if (!P) return err;
+        P->export_on_destroy = exports;
         cs.n_chunks = 1; cs.n_devices = 1;
         cs.host_parse_ms = P->stats.host_parse_ms;
         cs.h2d_bytes = P->stats.h2d_bytes;
@@ -930,6 +967,7 @@ int mp3dec_decode_batch_cuda(const mp3dec_batch_stream_t *streams, int n_streams
         const double a0 = now_ms();
         plans[c] = plan_create_impl(streams + first[c], first[c + 1] - first[c], opts, &err, true);
         if (!plans[c]) break;
+        plans[c]->export_on_destroy = exports;
         cs.host_parse_ms += plans[c]->stats.host_parse_ms;
         cs.h2d_bytes += plans[c]->stats.h2d_bytes;
         if (plans[c]->opts.output != MP3D_BATCH_OUT_DEVICE) cs.d2h_bytes += plans[c]->n_samples*plans[c]->sample_size;
@@ -1013,8 +1051,9 @@ static int decode_frame_impl(mp3dec_t *dec, const uint8_t *mp3, int mp3_bytes, v
     SyncState st;
     memcpy(st.header, dec->header, 4);
     st.free_format_bytes = dec->free_format_bytes;
-    st.reserv = dec->reserv;
-    const int reserv_before = dec->reserv;
+    /* the reference keeps 0 <= reserv <= 511; anything else is a caller's uninitialised or foreign struct */
+    const int reserv_before = std::min(std::max(dec->reserv, 0), 511);
+    st.reserv = reserv_before;
     FrameParse fp;
     fp.info = FrameInfo{ info->frame_bytes, info->frame_offset, info->channels, info->hz, info->layer, info->bitrate_kbps };
     parse_frame(&st, mp3, mp3_bytes, &fp, pcm == nullptr);
@@ -1095,7 +1134,7 @@ static int decode_frame_impl(mp3dec_t *dec, const uint8_t *mp3, int mp3_bytes, v
     const int reserv_old = fp.reset ? 0 : reserv_before;
     const int mdb = fp.main_data_begin;
     const int bytes_have = std::min(reserv_old, mdb);
-    uint8_t maindata[511 + 2304 + 64];
+    uint8_t maindata[511 + 2304 + 64 + 16];      /* copied in 16-byte units below */
     memset(maindata, 0, sizeof(maindata));
     memcpy(maindata, dec->reserv_buf + std::max(0, reserv_old - mdb), (size_t)bytes_have);
     memcpy(maindata + bytes_have, fp.payload, (size_t)fp.payload_bytes);
@@ -1121,7 +1160,7 @@ static int decode_frame_impl(mp3dec_t *dec, const uint8_t *mp3, int mp3_bytes, v
                   B.d_pcm.ensure(2304*4) && B.h_pcm.ensure(2304*4) && ctx->d_state_in.ensure(1536*4) &&
                   ctx->d_state_out.ensure(1536*4) && ctx->h_state.ensure(2*1536*4);
         if (!ok) return 0;
-        if (B.d_md.cap != md_cap_before) cudaMemset(B.d_md.p, 0, B.d_md.cap);   /* fresh allocation: defined guard bytes */
+        if (B.d_md.cap != md_cap_before) cudaMemsetAsync(B.d_md.p, 0, B.d_md.cap, ctx->stream);   /* fresh allocation: defined guard bytes (same stream as the copies) */
         uint8_t *h = (uint8_t *)B.h_md.p;
         memcpy(h, maindata, md_bytes);
         GcDesc gcs[4];

@@ -3,9 +3,11 @@
  * APIs (every PCM sample comes out of the CUDA kernels: look-ahead windows through mp3dec_decode_batch_cuda, single
  * frames through mp3dec_decode_frame).
  *
- * Host control logic restated from /root/reference/minimp3_ex.h: mp3dec_iterate_buf (:527-564),
- * mp3dec_load_index (:641-698), mp3dec_ex_open_buf (:700-717), mp3dec_ex_seek incl. the bit-reservoir pre-roll
- * (:743-893), mp3dec_ex_read_frame / mp3dec_ex_read (:895-1013), the stdio flavours (:1199-1434).
+ * Behaviour follows /root/reference/minimp3_ex.h -- mp3dec_iterate_buf (:527-564), mp3dec_load_index (:641-698),
+ * mp3dec_ex_open_buf (:700-717), mp3dec_ex_seek incl. the bit-reservoir pre-roll (:743-893), mp3dec_ex_read_frame /
+ * mp3dec_ex_read (:895-1013), the stdio flavours (:1199-1434) -- written here around this library's own pieces: one
+ * frame walk (walk_frames) under both the iterate call and the index builder, an index pass that asks the parser's
+ * decoder-state emulation (not the decoder) which frames produce output, look-ahead windows under the reads.
  * The *_cb flavours read the whole stream through the caller's callbacks into memory first and then run the
  * buffer flavours (same results; I/O happens up front instead of lazily).
  */
@@ -68,76 +70,162 @@ void fill_info(mp3dec_frame_info_t *fi, const uint8_t *hdr, int frame_size)
     fi->frame_bytes = frame_size;
 }
 
-/* index builder callback (minimp3_ex.h:641-698) */
-template <class S>
-int load_index(void *user_data, const uint8_t *frame, int frame_size, int free_format_bytes, size_t buf_size,
-               uint64_t offset, mp3dec_frame_info_t *info)
+/* ---- frame walk shared by mp3dec_iterate_buf and the index builder ------------------------------------------
+ * Tags are skipped, then every frame the sync search finds (minimp3_ex.h:527-564 defines which) is handed to
+ * visit(frame, frame_size, free_format_bytes, bytes_left, offset, info); a non-zero return ends the walk and is
+ * returned. */
+template <class Visit>
+int walk_frames(const uint8_t *buf, size_t size, Visit &&visit)
 {
-    ExT<S> *dec = (ExT<S> *)user_data;
-    if (!dec->index.frames && !dec->start_offset)
-    {   /* first frame: a VBR tag makes the full scan unnecessary */
-        uint32_t frames;
-        int delay, padding;
-        dec->info = *info;
-        dec->start_offset = dec->offset = offset;
-        dec->end_offset = offset + buf_size;
-        dec->free_format_bytes = free_format_bytes;
-        if (3 == dec->info.layer)
-        {
-            int ret = check_vbrtag(frame, frame_size, &frames, &delay, &padding);
-            if (ret) dec->start_offset = dec->offset = offset + frame_size;
-            if (ret > 0)
-            {
-                padding *= info->channels;
-                dec->start_delay = dec->to_skip = delay*info->channels;
-                dec->samples = (uint64_t)hdr_frame_samples(frame)*info->channels*(uint64_t)frames;
-                if (dec->samples >= (uint64_t)dec->start_delay) dec->samples -= dec->start_delay;
-                if (padding > 0 && dec->samples >= (uint64_t)padding) dec->samples -= padding;
-                dec->detected_samples = dec->samples;
-                dec->vbr_tag_found = 1;
-                return MP3D_E_USER;
-            } else if (ret < 0)
-                return 0;
-        }
-    }
-    if (dec->flags & MP3D_DO_NOT_SCAN) return MP3D_E_USER;
-    if (dec->index.num_frames + 1 > dec->index.capacity)
+    const uint8_t *const origin = buf;
+    skip_id3(&buf, &size);
+    mp3dec_frame_info_t fi;
+    memset(&fi, 0, sizeof(fi));
+    while (size)
     {
-        dec->index.capacity = dec->index.capacity ? dec->index.capacity*2 : 4096;
-        mp3dec_frame_t *grown = (mp3dec_frame_t *)realloc((void *)dec->index.frames, sizeof(mp3dec_frame_t)*dec->index.capacity);
-        if (!grown) return MP3D_E_MEMORY;
-        dec->index.frames = grown;
+        int free_format_bytes = 0, frame_size = 0;
+        const int junk = find_frame(buf, (int)std::min(size, (size_t)INT_MAX), &free_format_bytes, &frame_size);
+        buf += junk;
+        size -= (size_t)junk;
+        if (!frame_size)
+        {
+            if (junk) continue;      /* the search window (INT_MAX bytes) ended without a frame: go on behind it */
+            break;
+        }
+        fill_info(&fi, buf, frame_size);
+        const int r = visit(buf, frame_size, free_format_bytes, size, (uint64_t)(buf - origin), &fi);
+        if (r) return r;
+        buf += frame_size;
+        size -= (size_t)frame_size;
     }
-    mp3dec_frame_t *e = &dec->index.frames[dec->index.num_frames++];
-    e->offset = offset;
-    e->sample = dec->samples;
-    if (!dec->buffer_samples && dec->index.num_frames < 256)
-    {   /* cut files: the first frames may be undecodable until the reservoir fills */
-        dec->buffer_samples = decode_frame(&dec->mp3d, frame, (int)std::min(buf_size, (size_t)INT_MAX), dec->buffer, info);
-        dec->samples += (uint64_t)dec->buffer_samples*info->channels;
-    } else
-        dec->samples += (uint64_t)hdr_frame_samples(frame)*info->channels;
     return 0;
 }
 
-size_t idx_search(mp3dec_index_t *idx, uint64_t position)   /* minimp3_ex.h:720-740 */
+/* Length and encoder delay from a Xing/Info tag (minimp3_ex.h:655-676): samples the stream delivers after the
+ * decoder delay at the front and the padding at the end are cut. */
+struct TagLength
 {
-    size_t end = idx->num_frames, start = 0, index = 0;
-    while (start <= end)
+    uint64_t samples;
+    int delay;          /* channel-inclusive samples to drop at the start */
+};
+
+TagLength length_from_tag(const uint8_t *frame, int channels, uint32_t n_frames, int delay, int padding)
+{
+    TagLength t;
+    t.delay = delay*channels;
+    t.samples = (uint64_t)hdr_frame_samples(frame)*(uint64_t)channels*(uint64_t)n_frames;
+    if (t.samples >= (uint64_t)t.delay) t.samples -= (uint64_t)t.delay;
+    const int64_t pad = (int64_t)padding*channels;
+    if (pad > 0 && t.samples >= (uint64_t)pad) t.samples -= (uint64_t)pad;
+    return t;
+}
+
+/* ---- stream index (mp3dec_load_index, minimp3_ex.h:641-698) -------------------------------------------------
+ * One pass over the frames of buf: the first frame fixes the stream parameters and may carry a VBR tag (which ends
+ * the pass: the length is known); every other frame becomes an index entry (offset, samples delivered before it).
+ * How many samples a frame delivers: the reference decodes frames until the first one that produces output (a cut
+ * file starts with frames whose bit reservoir is missing) and counts whole frames from then on.  Whether a frame
+ * produces output is a property of the bitstream alone, so the parser's decoder-state emulation (parse_frame)
+ * answers it here without touching the GPU. */
+template <class S>
+class IndexPass
+{
+public:
+    explicit IndexPass(ExT<S> *d) : dec_(d) {}
+
+    int frame(const uint8_t *hdr, int frame_size, int free_format_bytes, size_t bytes_left, uint64_t offset,
+              const mp3dec_frame_info_t *info)
     {
-        size_t mid = (start + end)/2;
-        if (idx->frames[mid].sample >= position)
+        ExT<S> &d = *dec_;
+        if (!have_params_ && !d.index.frames && !d.start_offset)
         {
-            if (idx->frames[mid].sample == position) return mid;
-            end = mid - 1;
-        } else
-        {
-            index = mid;
-            start = mid + 1;
-            if (start == idx->num_frames) break;
+            have_params_ = true;
+            d.info = *info;
+            d.start_offset = d.offset = offset;
+            d.end_offset = offset + bytes_left;
+            d.free_format_bytes = free_format_bytes;
+            if (info->layer == 3)
+            {
+                uint32_t n_frames = 0;
+                int delay = 0, padding = 0;
+                const int tag = check_vbrtag(hdr, frame_size, &n_frames, &delay, &padding);
+                if (tag) d.start_offset = d.offset = offset + (uint64_t)frame_size;     /* the tag frame holds no audio */
+                if (tag > 0)
+                {
+                    const TagLength t = length_from_tag(hdr, info->channels, n_frames, delay, padding);
+                    d.start_delay = d.to_skip = t.delay;
+                    d.samples = d.detected_samples = t.samples;
+                    d.vbr_tag_found = 1;
+                    return MP3D_E_USER;
+                }
+                if (tag < 0) return 0;       /* tag without a frame count: skipped, the scan goes on */
+            }
         }
+        if (d.flags & MP3D_DO_NOT_SCAN) return MP3D_E_USER;
+        mp3dec_frame_t e;
+        e.offset = offset;
+        e.sample = d.samples;
+        entries_.push_back(e);
+        uint64_t produced = (uint64_t)hdr_frame_samples(hdr);
+        if (!counting_whole_frames_ && entries_.size() < 256)
+        {
+            FrameParse fp;
+            memset(&fp.info, 0, sizeof(fp.info));
+            parse_frame(&probe_, hdr, (int)std::min(bytes_left, (size_t)INT_MAX), &fp);
+            produced = (uint64_t)fp.samples;
+            counting_whole_frames_ = fp.samples != 0;
+        } else
+            counting_whole_frames_ = true;
+        d.samples += produced*(uint64_t)info->channels;
+        return 0;
     }
-    return index;
+
+    /* hands the entries to the public index (malloc()ed: mp3dec_ex_close frees it) */
+    int finish(uint64_t offset_bias)
+    {
+        ExT<S> &d = *dec_;
+        if (entries_.empty()) return 0;
+        mp3dec_frame_t *out = (mp3dec_frame_t *)malloc(entries_.size()*sizeof(mp3dec_frame_t));
+        if (!out) return MP3D_E_MEMORY;
+        for (size_t k = 0; k < entries_.size(); k++)
+        {
+            out[k] = entries_[k];
+            out[k].offset += offset_bias;
+        }
+        free(d.index.frames);
+        d.index.frames = out;
+        d.index.num_frames = d.index.capacity = entries_.size();
+        return 0;
+    }
+
+private:
+    ExT<S> *dec_;
+    std::vector<mp3dec_frame_t> entries_;
+    SyncState probe_;                      /* decoder-state emulation for the "does it produce output" question */
+    bool have_params_ = false;
+    bool counting_whole_frames_ = false;
+};
+
+template <class S>
+int scan_stream(ExT<S> *dec, const uint8_t *buf, size_t size, uint64_t offset_bias)
+{
+    IndexPass<S> pass(dec);
+    const int r = walk_frames(buf, size, [&](const uint8_t *f, int fs, int ffb, size_t left, uint64_t off, mp3dec_frame_info_t *fi) {
+        return pass.frame(f, fs, ffb, left, off, fi);
+    });
+    if (r && r != MP3D_E_USER) return r;
+    return pass.finish(offset_bias);
+}
+
+/* index entry decoding has to start from for `position`: the entry holding it -- the last one that starts before
+ * it, or the one starting exactly there (minimp3_ex.h:720-740) */
+size_t entry_for_sample(const mp3dec_index_t &idx, uint64_t position)
+{
+    const mp3dec_frame_t *first = idx.frames, *last = idx.frames + idx.num_frames;
+    const mp3dec_frame_t *it = std::lower_bound(first, last, position,
+                                                [](const mp3dec_frame_t &f, uint64_t pos) { return f.sample < pos; });
+    if (it != last && it->sample == position) return (size_t)(it - first);
+    return it == first ? 0 : (size_t)(it - first) - 1;
 }
 
 void drop_window(const void *owner);
@@ -151,93 +239,96 @@ int ex_open_buf(ExT<S> *dec, const uint8_t *buf, size_t buf_size, int flags)
     dec->file.buffer = buf;
     dec->file.size = buf_size;
     dec->flags = flags;
-    mp3dec_init(&dec->mp3d);
-    int ret = mp3dec_iterate_buf(dec->file.buffer, dec->file.size, load_index<S>, dec);
-    if (ret && MP3D_E_USER != ret) return ret;
+    const int ret = scan_stream(dec, buf, buf_size, 0);
+    if (ret) return ret;
     mp3dec_init(&dec->mp3d);
     dec->buffer_samples = 0;
     dec->indexes_built = !(dec->vbr_tag_found || (flags & MP3D_DO_NOT_SCAN));
-    dec->flags &= (~MP3D_DO_NOT_SCAN);
+    dec->flags &= ~MP3D_DO_NOT_SCAN;
     return 0;
 }
 
+/* payload bytes (what follows header, CRC and side info) of the Layer III frame at hdr, or -1 if its side info is
+ * not valid: what the frame adds to the bit reservoir */
+int l3_payload_bytes(const uint8_t *hdr, int free_format_bytes)
+{
+    const int frame_size = hdr_frame_bytes(hdr, free_format_bytes) + hdr_padding(hdr);
+    BitReader bs;
+    GranuleSide side[4];
+    bs.init(hdr + 4, frame_size - 4);
+    if (hdr_is_crc(hdr)) bs.get(16);
+    if (read_side_info(&bs, side, hdr) < 0) return -1;
+    return (bs.limit - bs.pos)/8;
+}
+
+/* everything a seek leaves behind except the position: empty frame buffer, no sticky error, fresh decoder */
+template <class S>
+void restart_at(ExT<S> *dec, uint64_t offset, int to_skip)
+{
+    dec->offset = offset;
+    dec->to_skip = to_skip;
+    dec->buffer_samples = dec->buffer_consumed = 0;
+    dec->input_consumed = dec->input_filled = 0;
+    dec->last_error = 0;
+    mp3dec_init(&dec->mp3d);
+}
+
+/* mp3dec_ex_seek (minimp3_ex.h:743-893), buffer mode.  Byte positions are taken as they are.  Sample positions go
+ * through the index: decoding restarts MINIMP3_PREDECODE_FRAMES in front of the frame that holds the sample -- for
+ * Layer III further back, until the frames in between can refill the 511-byte bit reservoir -- and the samples
+ * decoded on the way are dropped (to_skip). */
 template <class S>
 int ex_seek(ExT<S> *dec, uint64_t position)
 {
-    size_t i;
     if (!dec) return MP3D_E_PARAM;
     if (!(dec->flags & MP3D_SEEK_TO_SAMPLE))
     {
-        dec->offset = std::min<uint64_t>(position, dec->file.size);
         dec->cur_sample = 0;
-        goto do_exit;
+        restart_at(dec, std::min<uint64_t>(position, dec->file.size), dec->to_skip);
+        return 0;
     }
     if (dec->samples && position > dec->samples) position = dec->samples;
     dec->cur_sample = position;
-    if (position > (UINT64_MAX - (uint64_t)dec->start_delay)) position = UINT64_MAX;
-    else position += dec->start_delay;
-    if (0 == position)
+    const uint64_t target = position > UINT64_MAX - (uint64_t)dec->start_delay ? UINT64_MAX : position + (uint64_t)dec->start_delay;
+    if (target && !dec->indexes_built)
     {
-seek_zero:
-        dec->offset = dec->start_offset;
-        dec->to_skip = 0;
-        goto do_exit;
-    }
-    if (!dec->indexes_built)
-    {   /* opened through a VBR tag or MP3D_DO_NOT_SCAN: build the index now */
+        /* opened through a VBR tag or with MP3D_DO_NOT_SCAN: the index is built now, from the first audio frame */
         dec->indexes_built = 1;
         dec->samples = 0;
         dec->buffer_samples = 0;
-        int ret = mp3dec_iterate_buf(dec->file.buffer + dec->start_offset, dec->file.size - dec->start_offset, load_index<S>, dec);
-        if (ret && MP3D_E_USER != ret) return ret;
-        for (i = 0; i < dec->index.num_frames; i++) dec->index.frames[i].offset += dec->start_offset;
+        const int ret = scan_stream(dec, dec->file.buffer + dec->start_offset, (size_t)(dec->file.size - dec->start_offset), dec->start_offset);
+        if (ret) return ret;
         dec->samples = dec->detected_samples;
     }
-    if (!dec->index.frames) goto seek_zero;
-    i = idx_search(&dec->index, position);
-    if (i)
+    if (!target || !dec->index.frames)
     {
-        int to_fill_bytes = 511;
-        i -= std::min(i, (size_t)MINIMP3_PREDECODE_FRAMES);
-        if (3 == dec->info.layer)
+        restart_at(dec, dec->start_offset, 0);
+        return 0;
+    }
+    const mp3dec_frame_t *entries = dec->index.frames;
+    size_t at = entry_for_sample(dec->index, target);
+    if (at)
+    {
+        at -= std::min(at, (size_t)MINIMP3_PREDECODE_FRAMES);
+        if (dec->info.layer == 3)
         {
-            while (i && to_fill_bytes)
-            {   /* walk back until the bit reservoir can be full when decoding starts */
-                const uint8_t *hdr = dec->file.buffer + dec->index.frames[i - 1].offset;
-                int frame_size = hdr_frame_bytes(hdr, dec->free_format_bytes) + hdr_padding(hdr);
-                BitReader bs;
-                GranuleSide side[4];
-                bs.init(hdr + 4, frame_size - 4);
-                if (hdr_is_crc(hdr)) bs.get(16);
-                i--;
-                if (read_side_info(&bs, side, hdr) < 0) break;
-                int frame_bytes = (bs.limit - bs.pos)/8;
-                to_fill_bytes -= std::min(to_fill_bytes, frame_bytes);
+            int reservoir_gap = 511;
+            while (at && reservoir_gap > 0)
+            {
+                at--;
+                const int payload = l3_payload_bytes(dec->file.buffer + entries[at].offset, dec->free_format_bytes);
+                if (payload < 0) break;
+                reservoir_gap -= payload;
             }
         }
     }
-    dec->offset = dec->index.frames[i].offset;
-    if (position > dec->index.frames[i].sample)
-    {
-        uint64_t skip64 = position - dec->index.frames[i].sample;
-        dec->to_skip = (skip64 > (uint64_t)INT_MAX) ? INT_MAX : (int)skip64;
-    } else
-        dec->to_skip = 0;
-    while ((i + 1) < dec->index.num_frames && !dec->index.frames[i].sample && !dec->index.frames[i + 1].sample)
-    {   /* leading frames that produced nothing */
-        const uint8_t *hdr = dec->file.buffer + dec->index.frames[i].offset;
-        int frame_samples = (int)hdr_frame_samples(hdr)*dec->info.channels;
-        if (dec->to_skip > (INT_MAX - frame_samples)) dec->to_skip = INT_MAX;
-        else dec->to_skip += frame_samples;
-        i++;
-    }
-do_exit:
-    dec->buffer_samples = 0;
-    dec->buffer_consumed = 0;
-    dec->input_consumed = 0;
-    dec->input_filled = 0;
-    dec->last_error = 0;
-    mp3dec_init(&dec->mp3d);
+    const uint64_t restart_offset = entries[at].offset;
+    uint64_t drop = target > entries[at].sample ? target - entries[at].sample : 0;
+    /* leading entries that delivered nothing (their successor still starts at sample 0) are decoded again on the way
+     * and will deliver whole frames then */
+    for (; at + 1 < dec->index.num_frames && !entries[at].sample && !entries[at + 1].sample; at++)
+        drop += (uint64_t)hdr_frame_samples(dec->file.buffer + entries[at].offset)*(uint64_t)dec->info.channels;
+    restart_at(dec, restart_offset, (int)std::min<uint64_t>(drop, (uint64_t)INT_MAX));
     return 0;
 }
 
@@ -246,7 +337,7 @@ do_exit:
  * mp3dec_ex_read* decodes frame after frame from dec->offset, always starting from a freshly initialised decoder
  * (open and every seek end in mp3dec_init, minimp3_ex.h:717, 892).  Instead of one GPU round trip per frame, the
  * frames of a window are decoded in ONE batch call in raw-frame mode -- which is defined as exactly that frame
- * loop -- and handed out one by one.  When a window is used up the next one starts kPreroll frames early with a
+ * loop -- and handed out one by one.  When a window is used up the next one starts a few frames early (preroll_frames) with a
  * fresh decoder and drops their output: the overlap / synthesis state of the decoder only reaches one granule
  * back and the bit reservoir at most 511 bytes, so from there on the samples are those of the uninterrupted loop
  * (the same argument the reference's own seek relies on, minimp3_ex.h:826-871). */
@@ -267,7 +358,11 @@ struct Window
     ~Window() { free(pcm); }
 };
 
-constexpr size_t kPreroll = 16;
+/* Frames a window that starts mid-stream decodes again (and drops) so that the decoder state at its first
+ * delivered frame is that of the uninterrupted loop: the overlap / synthesis history reaches one granule back, the
+ * Layer III bit reservoir 511 BYTES -- at 8 kbit/s that is dozens of frames -- so the count follows the payload
+ * bytes (what mp3dec_ex_seek does, minimp3_ex.h:826-871), with kPrerollMin frames at least. */
+constexpr size_t kPrerollMin = 4, kPrerollMax = 256;
 
 /* frames per window; MP3B_DEBUG_WINDOW_FRAMES shrinks it so that tests cross many window boundaries */
 size_t window_frames()
@@ -275,6 +370,23 @@ size_t window_frames()
     const char *e = getenv("MP3B_DEBUG_WINDOW_FRAMES");
     const long v = e ? atol(e) : 0;
     return v > 0 ? (size_t)v : (size_t)4096;
+}
+
+/* how many of frames[0 .. end) to decode again in front of frames[end]; base = the bytes at file offset base_off */
+size_t preroll_frames(const std::vector<WindowFrame> &frames, size_t end, const uint8_t *base, uint64_t base_off)
+{
+    size_t n = 0;
+    int reservoir_gap = 511;
+    while (n < end && n < kPrerollMax && (n < kPrerollMin || reservoir_gap > 0))
+    {
+        const WindowFrame &f = frames[end - 1 - n];
+        n++;
+        if (!f.found || f.info.layer != 3) continue;      /* nothing found / no reservoir in Layers I and II */
+        const uint8_t *hdr = base + (f.off - base_off) + f.info.frame_offset;
+        const int side = hdr_is_mpeg1(hdr) ? (f.info.channels == 1 ? 17 : 32) : (f.info.channels == 1 ? 9 : 17);
+        reservoir_gap -= std::max(0, f.info.frame_bytes - f.info.frame_offset - 4 - (hdr_is_crc(hdr) ? 2 : 0) - side);
+    }
+    return n;
 }
 
 std::mutex g_win_mu;
@@ -354,8 +466,8 @@ int window_decode_frame(ExT<S> *dec, uint64_t end_offset, S *pcm, mp3dec_frame_i
     } else if (w && !fresh && w->next == w->frames.size() && w->next > 0 &&
                w->frames.back().off + (uint64_t)w->frames.back().info.frame_bytes == dec->offset)
     {
-        /* window used up: the next one re-decodes the last kPreroll frames for the decoder state */
-        const size_t back = std::min(kPreroll, w->frames.size());
+        /* window used up: the next one re-decodes the frames that rebuild the decoder state */
+        const size_t back = preroll_frames(w->frames, w->frames.size(), buf, 0);
         const uint64_t restart = w->frames[w->frames.size() - back].off;
         Window *nw = build_window<S>(buf, restart, end_offset, window_frames() + back);
         drop_window(dec);
@@ -412,7 +524,7 @@ int window_decode_frame(ExT<S> *dec, uint64_t end_offset, S *pcm, mp3dec_frame_i
  * many frames, they are decoded as one window (same machinery as the streaming API) and the following calls are
  * answered from it, as long as each call continues exactly where the previous frame ended, with the same bytes and
  * the same remaining length.  Anything else -- another buffer, a shorter length, a parse-only call, the end of the
- * input -- first brings the caller's mp3dec_t up to date by replaying the last kPreroll frames from a private copy
+ * input -- first brings the caller's mp3dec_t up to date by replaying the last few frames (preroll_frames) from a private copy
  * of the input through the one-frame path, then continues there.  MP3B_FRAME_LOOKAHEAD=0 switches the layer off. */
 struct FrameLook
 {
@@ -422,13 +534,19 @@ struct FrameLook
     uint64_t caller_end = 0;         /* bytes from caller_base to the end of the caller's buffer */
     int float_output = 0;
     uint64_t stamp = 0;
+    uint32_t id = 0;                 /* key of the window: travels in the caller's mp3dec_t as reserv = -id */
     mp3dec_t saved;                  /* w == nullptr: the decoder state the window had reached when it was retired */
     ~FrameLook() { delete w; }
 };
 
+/* The caller's mp3dec_t stays the authority on WHICH state a call continues from: while frames are served from a
+ * window the struct carries the window's key in `reserv` (negative: no real decoder has that), so a copied, moved or
+ * restored mp3dec_t finds its window by value, not by address, and the frame it continues with is identified by the
+ * input pointer.  A key whose window is gone (evicted) restarts the decoder. */
 std::mutex g_look_mu;
-std::unordered_map<const mp3dec_t *, FrameLook *> g_looks;
+std::unordered_map<uint32_t, FrameLook *> g_looks;
 uint64_t g_look_stamp = 0;
+uint32_t g_look_next_id = 0;
 constexpr size_t kMaxLooks = 16;      /* windows alive at once (~20 MB each) */
 constexpr size_t kMaxSaved = 4096;    /* retired windows: saved decoder states */
 constexpr int kMinLookBytes = 16384;
@@ -439,10 +557,10 @@ bool lookahead_enabled()
     return on;
 }
 
-FrameLook *take_look(const mp3dec_t *dec)
+FrameLook *take_look(uint32_t id)
 {
     std::lock_guard<std::mutex> lock(g_look_mu);
-    auto it = g_looks.find(dec);
+    auto it = g_looks.find(id);
     if (it == g_looks.end()) return nullptr;
     FrameLook *l = it->second;
     g_looks.erase(it);
@@ -451,10 +569,15 @@ FrameLook *take_look(const mp3dec_t *dec)
 
 void replay_into(mp3dec_t *dec, const FrameLook *l);
 
-void put_look(const mp3dec_t *dec, FrameLook *l)
+void put_look(FrameLook *l)
 {
     std::lock_guard<std::mutex> lock(g_look_mu);
     l->stamp = ++g_look_stamp;
+    while (!l->id)
+    {
+        g_look_next_id = (g_look_next_id + 1) & 0x7fffffffu;
+        if (g_look_next_id && !g_looks.count(g_look_next_id)) l->id = g_look_next_id;
+    }
     size_t live = 0;
     for (auto &kv : g_looks) live += kv.second->w != nullptr;
     if (live >= kMaxLooks)
@@ -478,16 +601,16 @@ void put_look(const mp3dec_t *dec, FrameLook *l)
         delete oldest->second;
         g_looks.erase(oldest);
     }
-    g_looks[dec] = l;
+    g_looks[l->id] = l;
 }
 
-/* bring *dec to the state it has after the frames handed out so far: fresh decoder + the last kPreroll of them */
+/* bring *dec to the state it has after the frames handed out so far: fresh decoder + the last few of them */
 void replay_into(mp3dec_t *dec, const FrameLook *l)
 {
     const Window *w = l->w;
     mp3dec_init(dec);
     if (!w->next) return;
-    const size_t first = w->next > kPreroll ? w->next - kPreroll : 0;
+    const size_t first = w->next - preroll_frames(w->frames, w->next, l->bytes.data(), w->frames[0].off);
     static thread_local float scratch[MINIMP3_MAX_SAMPLES_PER_FRAME];
     const uint64_t base = w->frames[0].off;
     for (size_t k = first; k < w->next; k++)
@@ -507,11 +630,11 @@ FrameLook *start_look(const uint8_t *mp3, int mp3_bytes, const uint8_t *preroll,
      * that end up in the window is kept */
     /* no frame is longer than 2881 bytes (MPEG-1 Layer II 384 kbit/s at 32 kHz; free format is capped at 2304): a
      * view of that many bytes per frame holds every frame the window can take, the rest of a long buffer stays put */
-    const size_t view = std::min<size_t>((size_t)mp3_bytes, (window_frames() + kPreroll + 2)*2900);
+    const size_t view = std::min<size_t>((size_t)mp3_bytes, (window_frames() + kPrerollMax + 2)*2900);
     std::vector<uint8_t> in(preroll_bytes + view);
     if (preroll_bytes) memcpy(in.data(), preroll, preroll_bytes);
     memcpy(in.data() + preroll_bytes, mp3, view);
-    Window *w = build_window<S>(in.data(), 0, in.size(), window_frames() + kPreroll);
+    Window *w = build_window<S>(in.data(), 0, in.size(), window_frames() + kPrerollMax);
     if (!w) return nullptr;
     size_t k = 0;
     while (k < w->frames.size() && w->frames[k].off < preroll_bytes) k++;
@@ -542,16 +665,24 @@ int serve_frame(FrameLook *l, mp3dec_t *dec, const uint8_t *mp3, S *pcm, mp3dec_
         info->frame_bytes = f.info.frame_bytes;      /* the other fields stay as the caller had them */
     if (f.samples) memcpy(pcm, (const S *)w->pcm + f.pcm_pos, (size_t)f.samples*(size_t)f.info.channels*sizeof(S));
     if (!dec->header[0]) dec->header[0] = 0xff;      /* "not freshly initialised": the state lives in the window */
-    put_look(dec, l);
+    put_look(l);
+    dec->reserv = -(int)l->id;
     return f.samples;
 }
 
 template <class S>
 int frame_lookahead_t(mp3dec_t *dec, const uint8_t *mp3, int mp3_bytes, S *pcm, mp3dec_frame_info_t *info)
 {
-    FrameLook *l = take_look(dec);
     const bool fresh = dec->header[0] == 0;
-    if (l && fresh) { delete l; l = nullptr; }               /* mp3dec_init by the caller: whatever was cached is void */
+    const uint32_t id = (!fresh && dec->reserv < 0) ? (uint32_t)(-(int64_t)dec->reserv) : 0u;
+    FrameLook *l = id ? take_look(id) : nullptr;
+    if (id && !l)
+    {
+        /* the struct points at a window that no longer exists: nothing to continue from, resynchronise */
+        mp3dec_init(dec);
+        dec->reserv = 0;
+        return -1;
+    }
     if (l && !l->w)
     {
         /* this decoder's window was retired while it was idle: its state was saved, hand it back */
@@ -562,6 +693,18 @@ int frame_lookahead_t(mp3dec_t *dec, const uint8_t *mp3, int mp3_bytes, S *pcm, 
     if (l)
     {
         Window *w = l->w;
+        /* which frame does THIS struct continue with?  Usually the window's next one; a copy or an older snapshot
+         * of the struct is placed by its input pointer */
+        if (mp3 >= l->caller_base && (uint64_t)(mp3 - l->caller_base) < l->caller_end)
+        {
+            const uint64_t want = (uint64_t)(mp3 - l->caller_base);
+            if (!(w->next < w->frames.size() && w->frames[w->next].off == want))
+            {
+                auto it = std::lower_bound(w->frames.begin(), w->frames.end(), want,
+                                           [](const WindowFrame &f, uint64_t o) { return f.off < o; });
+                if (it != w->frames.end() && it->off == want) w->next = (size_t)(it - w->frames.begin());
+            }
+        }
         const uint64_t pos = w->next < w->frames.size() ? w->frames[w->next].off
                                                         : w->frames.back().off + (uint64_t)w->frames.back().info.frame_bytes;
         const bool here = pcm && l->float_output == (sizeof(S) == 4) && mp3 == l->caller_base + pos &&
@@ -571,8 +714,8 @@ int frame_lookahead_t(mp3dec_t *dec, const uint8_t *mp3, int mp3_bytes, S *pcm, 
             return serve_frame<S>(l, dec, mp3, pcm, info);
         if (here && w->next == w->frames.size() && mp3_bytes >= kMinLookBytes)
         {
-            /* window used up, the caller goes on: next window, state from the last kPreroll frames */
-            const size_t back = std::min(kPreroll, w->frames.size());
+            /* window used up, the caller goes on: next window, state from the last few frames */
+            const size_t back = preroll_frames(w->frames, w->frames.size(), l->bytes.data(), w->frames[0].off);
             const uint64_t restart = w->frames[w->frames.size() - back].off;
             FrameLook *nl = start_look<S>(mp3, mp3_bytes, l->bytes.data() + restart, (size_t)(pos - restart));
             if (nl)
@@ -592,6 +735,45 @@ int frame_lookahead_t(mp3dec_t *dec, const uint8_t *mp3, int mp3_bytes, S *pcm, 
     return serve_frame<S>(nl, dec, mp3, pcm, info);
 }
 
+/* Decodes frames from dec->offset until dec->buffer holds deliverable samples (minimp3_ex.h:922-975, buffer mode):
+ * samples still owed to a seek (to_skip) are dropped on the way, a change of sample rate / layer -- or of the channel
+ * count, unless MP3D_ALLOW_MONO_STEREO_TRANSITION -- makes the error sticky.  false: end of input or error. */
+template <class S>
+bool refill(ExT<S> *dec, mp3dec_frame_info_t *fi)
+{
+    const uint64_t end = dec->end_offset ? dec->end_offset : dec->file.size;
+    while (dec->buffer_consumed == dec->buffer_samples)
+    {
+        if (dec->offset >= end) return false;
+        const uint8_t *at = dec->file.buffer + dec->offset;
+        const int per_channel = window_decode_frame(dec, end, dec->buffer, fi);
+        dec->buffer_consumed = 0;
+        dec->buffer_samples = per_channel*fi->channels;
+        const bool format_changed = dec->info.hz != fi->hz || dec->info.layer != fi->layer;
+        if (format_changed)
+        {
+            dec->buffer_samples = per_channel;        /* as the reference leaves it */
+            dec->last_error = MP3D_E_DECODE;
+            return false;
+        }
+        if (per_channel)
+        {
+            const int dropped = std::min(dec->buffer_samples, std::max(dec->to_skip, 0));
+            dec->buffer_consumed = dropped;
+            dec->to_skip -= dropped;
+            const bool channels_changed = dec->info.channels != fi->channels && !(dec->flags & MP3D_ALLOW_MONO_STEREO_TRANSITION);
+            if (channels_changed && dec->buffer_consumed != dec->buffer_samples)
+            {
+                dec->last_error = MP3D_E_DECODE;
+                return false;
+            }
+        } else if (dec->to_skip > 0)
+            dec->to_skip -= std::min((int)hdr_frame_samples(at)*fi->channels, dec->to_skip);   /* an undecodable frame still counts */
+        dec->offset += (uint64_t)fi->frame_bytes;
+    }
+    return true;
+}
+
 template <class S>
 size_t ex_read_frame(ExT<S> *dec, S **buf, mp3dec_frame_info_t *frame_info, size_t max_samples)
 {
@@ -600,51 +782,16 @@ size_t ex_read_frame(ExT<S> *dec, S **buf, mp3dec_frame_info_t *frame_info, size
         if (dec) dec->last_error = MP3D_E_PARAM;
         return 0;
     }
-    if (dec->detected_samples && dec->cur_sample >= dec->detected_samples) return 0;
-    if (dec->last_error) return 0;
+    const bool length_known = dec->detected_samples != 0;
+    if ((length_known && dec->cur_sample >= dec->detected_samples) || dec->last_error) return 0;
     *buf = NULL;
-    uint64_t end_offset = dec->end_offset ? dec->end_offset : dec->file.size;
-    while (dec->buffer_consumed == dec->buffer_samples)
-    {
-        const uint8_t *dec_buf = dec->file.buffer + dec->offset;
-        uint64_t buf_size = end_offset - dec->offset;
-        if (!buf_size) return 0;
-        dec->buffer_samples = window_decode_frame(dec, end_offset, dec->buffer, frame_info);
-        dec->buffer_consumed = 0;
-        if (dec->info.hz != frame_info->hz || dec->info.layer != frame_info->layer)
-        {
-            dec->last_error = MP3D_E_DECODE;
-            return 0;
-        }
-        if (dec->buffer_samples)
-        {
-            dec->buffer_samples *= frame_info->channels;
-            if (dec->to_skip > 0)
-            {
-                int skip = std::min(dec->buffer_samples, dec->to_skip);
-                dec->buffer_consumed += skip;
-                dec->to_skip -= skip;
-            }
-            if (!(dec->flags & MP3D_ALLOW_MONO_STEREO_TRANSITION) && dec->buffer_consumed != dec->buffer_samples &&
-                dec->info.channels != frame_info->channels)
-            {
-                dec->last_error = MP3D_E_DECODE;
-                return 0;
-            }
-        } else if (dec->to_skip > 0)
-        {
-            int frame_samples = (int)hdr_frame_samples(dec_buf)*frame_info->channels;
-            dec->to_skip -= std::min(frame_samples, dec->to_skip);
-        }
-        dec->offset += frame_info->frame_bytes;
-    }
-    size_t out = std::min((size_t)(dec->buffer_samples - dec->buffer_consumed), max_samples);
-    if (dec->detected_samples && dec->cur_sample + out >= dec->detected_samples)
-        out = (size_t)(dec->detected_samples - dec->cur_sample);
-    dec->cur_sample += out;
+    if (!refill(dec, frame_info)) return 0;
+    size_t n = std::min((size_t)(dec->buffer_samples - dec->buffer_consumed), max_samples);
+    if (length_known && dec->cur_sample + n >= dec->detected_samples) n = (size_t)(dec->detected_samples - dec->cur_sample);
     *buf = dec->buffer + dec->buffer_consumed;
-    dec->buffer_consumed += (int)out;
-    return out;
+    dec->buffer_consumed += (int)n;
+    dec->cur_sample += n;
+    return n;
 }
 
 template <class S>
@@ -657,17 +804,15 @@ size_t ex_read(ExT<S> *dec, S *buf, size_t samples)
     }
     mp3dec_frame_info_t fi;
     memset(&fi, 0, sizeof(fi));
-    size_t want = samples;
-    while (samples)
+    size_t done = 0;
+    for (S *chunk = NULL; done < samples; )
     {
-        S *frame = NULL;
-        size_t got = ex_read_frame(dec, &frame, &fi, samples);
-        if (!got) break;
-        memcpy(buf, frame, got*sizeof(S));
-        buf += got;
-        samples -= got;
+        const size_t n = ex_read_frame(dec, &chunk, &fi, samples - done);
+        if (!n) break;
+        memcpy(buf + done, chunk, n*sizeof(S));
+        done += n;
     }
-    return want - samples;
+    return done;
 }
 
 template <class S>
@@ -861,27 +1006,11 @@ extern "C" {
 
 int mp3dec_iterate_buf(const uint8_t *buf, size_t buf_size, MP3D_ITERATE_CB callback, void *user_data)
 {
-    const uint8_t *orig = buf;
     if (!buf || (size_t)-1 == buf_size || !callback) return MP3D_E_PARAM;
-    skip_id3(&buf, &buf_size);
-    if (!buf_size) return 0;
-    mp3dec_frame_info_t fi;
-    memset(&fi, 0, sizeof(fi));
-    for (;;)
-    {
-        int free_format_bytes = 0, frame_size = 0;
-        int i = find_frame(buf, (int)std::min(buf_size, (size_t)INT_MAX), &free_format_bytes, &frame_size);
-        buf += i;
-        buf_size -= i;
-        if (i && !frame_size) continue;
-        if (!frame_size) break;
-        fill_info(&fi, buf, frame_size);
-        int ret = callback(user_data, buf, frame_size, free_format_bytes, buf_size, (uint64_t)(buf - orig), &fi);
-        if (ret) return ret;
-        buf += frame_size;
-        buf_size -= frame_size;
-    }
-    return 0;
+    return walk_frames(buf, buf_size, [&](const uint8_t *frame, int frame_size, int free_format_bytes, size_t left, uint64_t offset,
+                                          mp3dec_frame_info_t *fi) {
+        return callback(user_data, frame, frame_size, free_format_bytes, left, offset, fi);
+    });
 }
 
 int mp3dec_iterate_cb(mp3dec_io_t *io, uint8_t *buf, size_t buf_size, MP3D_ITERATE_CB callback, void *user_data)

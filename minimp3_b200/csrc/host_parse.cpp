@@ -83,45 +83,72 @@ int hdr_padding(const uint8_t *h)
     return ((h[1] & 6) == 6) ? 4 : 1;
 }
 
-/* ---- frame sync (minimp3.h:1657-1706) ------------------------------------------------------- */
+/* ---- frame sync (behaviour of mp3d_find_frame / mp3d_match_frame, minimp3.h:1657-1706) -------------------------
+ * A position is accepted as a frame start when its header is valid and the frames it implies line up: up to
+ * kMaxSyncMatches following headers, each found exactly one frame length further, agree with it in version, layer,
+ * sample rate and free-format-ness (running out of input after at least one of them is fine); or when the frame
+ * fills the input exactly from position 0.  Free-format frames carry no length: it is taken from the distance to
+ * the next agreeing header, provided a third one follows at the same distance. */
 
-static int match_frame(const uint8_t *hdr, int mp3_bytes, int frame_bytes)
+/* bytes from this header to the next one */
+static inline int stride_of(const uint8_t *h, int free_format_bytes)
 {
-    int pos = 0;
-    for (int nmatch = 0; nmatch < kMaxSyncMatches; nmatch++)
+    return hdr_frame_bytes(h, free_format_bytes) + hdr_padding(h);
+}
+
+/* avail = bytes from hdr to the end of the input */
+static bool followers_agree(const uint8_t *hdr, int avail, int free_format_bytes)
+{
+    int at = 0;
+    for (int seen = 0; seen < kMaxSyncMatches; seen++)
     {
-        pos += hdr_frame_bytes(hdr + pos, frame_bytes) + hdr_padding(hdr + pos);
-        if (pos + kHdrSize > mp3_bytes) return nmatch > 0;
-        if (!hdr_compare(hdr, hdr + pos)) return 0;
+        at += stride_of(hdr + at, free_format_bytes);
+        if (at + kHdrSize > avail) return seen != 0;
+        if (!hdr_compare(hdr, hdr + at)) return false;
     }
-    return 1;
+    return true;
+}
+
+/* free-format length search: returns the stride (0: none found) and the frame's own byte count without padding.
+ * The candidates keep at least another stride plus a header behind them (the reference's loop bound). */
+static int free_format_stride(const uint8_t *hdr, int avail, int *frame_bytes)
+{
+    for (int stride = kHdrSize; stride < kMaxFreeFormatFrame && 2*stride < avail - kHdrSize; stride++)
+    {
+        if (!hdr_compare(hdr, hdr + stride)) continue;
+        const int own = stride - hdr_padding(hdr);                 /* this frame without its padding byte */
+        const int next = own + hdr_padding(hdr + stride);          /* the stride of the frame behind it */
+        if (stride + next + kHdrSize > avail || !hdr_compare(hdr, hdr + stride + next)) continue;
+        *frame_bytes = own;
+        return stride;
+    }
+    return 0;
 }
 
 int find_frame(const uint8_t *mp3, int mp3_bytes, int *free_format_bytes, int *ptr_frame_bytes)
 {
-    for (int i = 0; i < mp3_bytes - kHdrSize; i++, mp3++)
+    for (int pos = 0; pos < mp3_bytes - kHdrSize; pos++)
     {
-        if (!hdr_valid(mp3)) continue;
-        int frame_bytes = hdr_frame_bytes(mp3, *free_format_bytes);
-        int frame_and_padding = frame_bytes + hdr_padding(mp3);
-
-        /* free format: the frame length is the distance to the next two compatible headers */
-        for (int k = kHdrSize; !frame_bytes && k < kMaxFreeFormatFrame && i + 2*k < mp3_bytes - kHdrSize; k++)
+        const uint8_t *hdr = mp3 + pos;
+        if (!hdr_valid(hdr)) continue;
+        const int avail = mp3_bytes - pos;
+        int frame_bytes = hdr_frame_bytes(hdr, *free_format_bytes);
+        int stride = frame_bytes + hdr_padding(hdr);
+        if (!frame_bytes)
         {
-            if (!hdr_compare(mp3, mp3 + k)) continue;
-            int fb = k - hdr_padding(mp3);
-            int nextfb = fb + hdr_padding(mp3 + k);
-            if (i + k + nextfb + kHdrSize > mp3_bytes || !hdr_compare(mp3, mp3 + k + nextfb)) continue;
-            frame_and_padding = k;
-            frame_bytes = fb;
-            *free_format_bytes = fb;
+            const int s = free_format_stride(hdr, avail, &frame_bytes);
+            if (s)
+            {
+                stride = s;
+                *free_format_bytes = frame_bytes;
+            }
         }
-        bool chain_ok = frame_bytes && i + frame_and_padding <= mp3_bytes && match_frame(mp3, mp3_bytes - i, frame_bytes);
-        bool exact_fit = !i && frame_and_padding == mp3_bytes;
-        if (chain_ok || exact_fit)
+        const bool lined_up = frame_bytes && stride <= avail && followers_agree(hdr, avail, frame_bytes);
+        const bool whole_input = pos == 0 && stride == mp3_bytes;
+        if (lined_up || whole_input)
         {
-            *ptr_frame_bytes = frame_and_padding;
-            return i;
+            *ptr_frame_bytes = stride;
+            return pos;
         }
         *free_format_bytes = 0;
     }
