@@ -888,46 +888,16 @@ int load_buf_frames(mp3dec_t *dec, const uint8_t *buf, size_t buf_size, mp3dec_f
 {
     const size_t orig_size = buf_size;
     memset(info, 0, sizeof(*info));
-    skip_id3(&buf, &buf_size);
-    if (!buf_size) return 0;
     mp3dec_init(dec);
+    StreamHead head;
+    if (!open_stream_head(&buf, &buf_size, &head)) return 0;
     mp3dec_frame_info_t fi;
     memset(&fi, 0, sizeof(fi));
-    uint64_t detected_samples = 0;
-    size_t to_skip = 0;
-    int frame_samples = 0;
-    for (;;)
-    {   /* first frame: stream parameters and the optional Xing/Info tag */
-        int free_format_bytes = 0, frame_size = 0;
-        const int i = find_frame(buf, (int)std::min(buf_size, (size_t)INT_MAX), &free_format_bytes, &frame_size);
-        buf += i;
-        buf_size -= i;
-        if (i && !frame_size) continue;
-        if (!frame_size) return 0;
-        fill_info(&fi, buf, frame_size);
-        frame_samples = (int)hdr_frame_samples(buf)*fi.channels;
-        if (3 == fi.layer)
-        {
-            uint32_t frames;
-            int delay, padding;
-            const int ret = check_vbrtag(buf, frame_size, &frames, &delay, &padding);
-            if (ret > 0)
-            {
-                padding *= fi.channels;
-                to_skip = (size_t)delay*fi.channels;
-                detected_samples = (uint64_t)frame_samples*frames;
-                if (detected_samples >= to_skip) detected_samples -= to_skip;
-                if (padding > 0 && detected_samples >= (uint64_t)padding) detected_samples -= padding;
-                if (!detected_samples) return 0;
-            }
-            if (ret)
-            {
-                buf += frame_size;
-                buf_size -= frame_size;
-            }
-        }
-        break;
-    }
+    fi.channels = head.first.channels; fi.hz = head.first.hz; fi.layer = head.first.layer;
+    fi.bitrate_kbps = head.first.bitrate_kbps; fi.frame_bytes = head.first.frame_bytes;
+    const uint64_t detected_samples = head.detected_samples;
+    size_t to_skip = (size_t)head.to_skip;
+    const int frame_samples = head.frame_samples*fi.channels;
     size_t allocated = MINIMP3_MAX_SAMPLES_PER_FRAME*sizeof(S);
     if (detected_samples) allocated += (size_t)detected_samples*sizeof(S);
     else allocated += (buf_size/fi.frame_bytes)*(size_t)frame_samples*sizeof(S);

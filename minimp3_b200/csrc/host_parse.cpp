@@ -383,6 +383,59 @@ int detect_buf(const uint8_t *buf, size_t buf_size)
     return frame_size ? 0 : -4;
 }
 
+/* ---- the head of a stream as mp3dec_load_buf sees it (minimp3_ex.h:313-371) -------------------------------------
+ * Tags are stepped over, the first frame fixes the stream parameters, and a Layer III first frame that is a
+ * Xing / Info tag is dropped -- with a frame count it also tells the length: frames x samples, minus the encoder
+ * delay in front (to_skip) and the padding behind. */
+bool open_stream_head(const uint8_t **pbuf, size_t *psize, StreamHead *head)
+{
+    const uint8_t *buf = *pbuf;
+    size_t size = *psize;
+    skip_id3(&buf, &size);
+    int frame_size = 0;
+    while (size && !frame_size)
+    {
+        int free_format_bytes = 0;
+        const int junk = find_frame(buf, (int)std::min(size, (size_t)INT_MAX), &free_format_bytes, &frame_size);
+        buf += junk;
+        size -= (size_t)junk;
+        if (!junk && !frame_size) break;       /* nothing left to search */
+    }
+    *pbuf = buf;
+    *psize = size;
+    if (!frame_size) return false;
+    FrameInfo &f = head->first;
+    f.channels = hdr_is_mono(buf) ? 1 : 2;
+    f.hz = (int)hdr_sample_rate_hz(buf);
+    f.layer = hdr_layer(buf);
+    f.bitrate_kbps = (int)hdr_bitrate_kbps(buf);
+    f.frame_bytes = frame_size;
+    f.frame_offset = 0;
+    head->frame_samples = (int)hdr_frame_samples(buf);
+    head->to_skip = head->detected_samples = 0;
+    if (f.layer != 3) return true;
+    uint32_t n_frames = 0;
+    int delay = 0, padding = 0;
+    const int tag = check_vbrtag(buf, frame_size, &n_frames, &delay, &padding);
+    if (tag > 0)
+    {
+        const uint64_t per_frame = (uint64_t)hdr_frame_samples(buf)*(uint64_t)f.channels;
+        uint64_t total = per_frame*n_frames;
+        head->to_skip = (uint64_t)((int64_t)delay*f.channels);
+        if (total >= head->to_skip) total -= head->to_skip;
+        const int64_t pad = (int64_t)padding*f.channels;
+        if (pad > 0 && total >= (uint64_t)pad) total -= (uint64_t)pad;
+        if (!total) return false;              /* a tag that announces nothing */
+        head->detected_samples = total;
+    }
+    if (tag)
+    {
+        *pbuf = buf + frame_size;
+        *psize = size - (size_t)frame_size;
+    }
+    return true;
+}
+
 /* ---- whole-stream walk (minimp3_ex.h:308-525 in buffer mode) ----------------------------------------- */
 
 static void build_tiles(StreamPlan *plan, int tile_granules)
@@ -466,44 +519,11 @@ void walk_stream(const uint8_t *buf, size_t size, uint8_t *md_dst, uint64_t md_b
     FrameInfo first{};
     if (!opt.raw_frames)
     {
-        skip_id3(&buf, &size);
-        if (!size) return;
-        /* first-frame probe: allocation guess in the reference, VBR-tag detection for us */
-        for (;;)
-        {
-            int free_format_bytes = 0, frame_size = 0;
-            int i = find_frame(buf, (int)std::min(size, (size_t)INT_MAX), &free_format_bytes, &frame_size);
-            buf += i;
-            size -= i;
-            if (i && !frame_size) continue;
-            if (!frame_size) return;
-            const uint8_t *hdr = buf;
-            first.channels = hdr_is_mono(hdr) ? 1 : 2;
-            first.hz = (int)hdr_sample_rate_hz(hdr);
-            first.layer = hdr_layer(hdr);
-            first.bitrate_kbps = (int)hdr_bitrate_kbps(hdr);
-            first.frame_bytes = frame_size;
-            int samples = (int)hdr_frame_samples(hdr)*first.channels;
-            if (first.layer != 3) break;
-            uint32_t frames = 0;
-            int delay = 0, padding = 0;
-            int r = check_vbrtag(hdr, frame_size, &frames, &delay, &padding);
-            if (r > 0)
-            {
-                padding *= first.channels;
-                to_skip = (uint64_t)((int64_t)delay*first.channels);
-                detected_samples = (uint64_t)samples*(uint64_t)frames;
-                if (detected_samples >= to_skip) detected_samples -= to_skip;
-                if (padding > 0 && detected_samples >= (uint64_t)padding) detected_samples -= (uint64_t)padding;
-                if (!detected_samples) return;
-            }
-            if (r)
-            {
-                buf += frame_size;
-                size -= frame_size;
-            }
-            break;
-        }
+        StreamHead head;
+        if (!open_stream_head(&buf, &size, &head)) return;
+        first = head.first;
+        to_skip = head.to_skip;
+        detected_samples = head.detected_samples;
         plan->channels = first.channels;
         plan->hz = first.hz;
         plan->layer = first.layer;

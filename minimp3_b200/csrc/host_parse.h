@@ -130,6 +130,18 @@ void skip_id3v1(const uint8_t *buf, size_t *pbuf_size);
 /* minimp3_ex.h:193-263 */
 int check_vbrtag(const uint8_t *frame, int frame_size, uint32_t *frames, int *delay, int *padding);
 
+/* Head of a stream with mp3dec_load_buf semantics (minimp3_ex.h:313-371): tags skipped, first frame found, a
+ * Xing / Info tag frame evaluated and dropped.  On return *pbuf / *psize stand at the first audio frame.  false:
+ * nothing to decode (no frame, or a tag announcing zero samples). */
+struct StreamHead
+{
+    FrameInfo first{};           /* parameters of the first frame (frame_bytes = its size) */
+    int frame_samples = 0;       /* samples per channel of that frame */
+    uint64_t to_skip = 0;        /* channel-inclusive samples of encoder delay to drop */
+    uint64_t detected_samples = 0;   /* stream length the tag announces, 0 = unknown */
+};
+bool open_stream_head(const uint8_t **pbuf, size_t *psize, StreamHead *head);
+
 /* mp3dec_detect_buf (minimp3_ex.h:265-306, buffer flavour) */
 int detect_buf(const uint8_t *buf, size_t buf_size);
 
