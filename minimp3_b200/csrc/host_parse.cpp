@@ -460,7 +460,9 @@ static void build_tiles(StreamPlan *plan, int tile_granules)
         t.pcm_off = pcm_off;
         for (int c = 0; c < 2; c++) { t.halo[c][0] = chain[c][0]; t.halo[c][1] = chain[c][1]; }
         int cnt = 0;
-        while (g < n && cnt < tile_granules)
+        /* Layer III mono tiles take twice the granules (MP3B_TILE_GRANULES_MONO); Layer I/II tiles keep the base size */
+        const int cap = (!first.kind && first.nch == 1) ? tile_granules*(MP3B_TILE_GRANULES_MONO/MP3B_TILE_GRANULES) : tile_granules;
+        while (g < n && cnt < cap)
         {
             const GranuleRef &r = plan->granules[g];
             if (cnt && (r.reset || r.kind != first.kind || r.nch != first.nch || r.gc != first.gc + (uint32_t)(cnt*first.nch))) break;

@@ -3,8 +3,9 @@
  * frame header has the intensity bit set.  Restates L3_intensity_stereo, L3_stereo_top_band,
  * L3_stereo_process and L3_intensity_stereo_band (minimp3.h:911-993).
  *
- * Rare path (only joint-stereo streams that actually use intensity coding): one warp per granule,
- * bands walked in order, lanes spread over the lines of a band.  Works in place on xr.
+ * Only joint-stereo streams that actually use intensity coding come here: one warp per granule.  The two rows
+ * are staged in shared memory with coalesced loads first -- the band walk (up to 39 bands, twice) is a chain of
+ * short dependent steps and must not pay a global round trip per band -- and written back in one sweep.
  */
 #include <cuda_runtime.h>
 
@@ -26,6 +27,7 @@ __constant__ float c_pan[14] = { 0.f, 1.f, 0.21132487f, 0.78867513f, 0.36602540f
 __global__ void __launch_bounds__(kWarps*32) k_l3_intensity_stereo(StereoArgs a)
 {
     __shared__ uint8_t s_ist[kWarps][40];
+    __shared__ float s_rows[kWarps][2][576];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t gi = blockIdx.x*kWarps + warp;
     if (gi >= a.n_granules) return;
@@ -42,20 +44,26 @@ __global__ void __launch_bounds__(kWarps*32) k_l3_intensity_stereo(StereoArgs a)
     const int ext = max(nzl0, nzl1);
 
     for (int k = lane; k < 40; k += 32) s_ist[warp][k] = a.ist_pos[(size_t)gc1*40 + k];
+    float *Ls = s_rows[warp][0], *Rs = s_rows[warp][1];
+    for (int k = lane; k < ext; k += 32)
+    {
+        Ls[k] = k < nzl0 ? L[k] : 0.f;       /* lines at or beyond a row's extent were never written: zero */
+        Rs[k] = k < nzl1 ? R[k] : 0.f;
+    }
     __syncwarp();
 
     /* L3_stereo_top_band: last band (per window class) of the right channel holding a non-zero line */
     int max_band[3] = { -1, -1, -1 };
     {
         int start = 0;
-        for (int i = 0; i < n_sfb; i++)
+        for (int i = 0; i < n_sfb && start < nzl1; i++)
         {
             const int w = sfbw[i];
             bool nz = false;
             for (int k = lane; k < w; k += 32)
             {
                 const int line = start + k;
-                if (line < nzl1 && R[line] != 0.f) nz = true;
+                if (line < nzl1 && Rs[line] != 0.f) nz = true;
             }
             if (__any_sync(0xffffffffu, nz)) max_band[i % 3] = i;
             start += w;
@@ -82,7 +90,7 @@ __global__ void __launch_bounds__(kWarps*32) k_l3_intensity_stereo(StereoArgs a)
     const unsigned max_pos = mpeg1 ? 7 : 64;
     const int mpeg2_sh = d1.scalefac_compress & 1;
     int start = 0;
-    for (int i = 0; sfbw[i]; i++)
+    for (int i = 0; sfbw[i] && start < ext; i++)
     {
         const int w = sfbw[i];
         const unsigned ipos = s_ist[warp][i];
@@ -108,15 +116,20 @@ __global__ void __launch_bounds__(kWarps*32) k_l3_intensity_stereo(StereoArgs a)
         {
             const int line = start + k;
             if (line >= ext) continue;
-            const float l = line < nzl0 ? L[line] : 0.f;
-            const float r = line < nzl1 ? R[line] : 0.f;
+            const float l = Ls[line], r = Rs[line];
             float nl = l, nr = r;
             if (intensity) { nr = MP3_FMUL(l, kr); nl = MP3_FMUL(l, kl); }
             else if (ms_bit) { nl = MP3_FADD(l, r); nr = MP3_FADD(l, -r); }
-            L[line] = nl;
-            R[line] = nr;
+            Ls[line] = nl;
+            Rs[line] = nr;
         }
         start += w;
+    }
+    __syncwarp();
+    for (int k = lane; k < ext; k += 32)
+    {
+        L[k] = Ls[k];
+        R[k] = Rs[k];
     }
     if (lane == 0)
     {

@@ -51,7 +51,8 @@ constexpr int kYFloats = 2*kRows*kYPitch;   /* 10812, aliases XS */
 constexpr int kTFloats = kSlots*288;
 static_assert(sizeof(TileRec) == 256 && MP3B_TILE_SLOTS == kSlots, "tile record layout");
 static_assert(kYFloats <= kXFloats, "Y must fit in the X region");
-static_assert(GT*32 <= kThreads, "one FIR job per thread");
+static_assert(GT*32 <= kThreads, "one FIR job per thread (stereo; a mono tile takes two rounds)");
+static_assert(15 + 18*MP3B_TILE_GRANULES_MONO <= 2*kRows, "a mono tile's rows fit the two channels' rows");
 static_assert(((GT + 2 + kThreads/32 - 1)/(kThreads/32))*2 <= 4, "a warp clears at most four rows, a quarter-warp each");
 static_assert(kXFloats - kYFloats >= GT*2*18*2, "slack behind Y holds the specially rounded outputs");
 
@@ -217,10 +218,8 @@ __device__ __forceinline__ void stage_fir_taps(float *fir_taps, const float *__r
  * helper (j = 0, 16) are parked in shared memory and finished by a separate pass. */
 template <bool FLOAT_OUT, int NCH, int SLOTS, int ROWS>
 __device__ __forceinline__ void fir_phase(const float *ybase, const float *fir_taps, float *special,
-                                          void *pcm, uint64_t pcm_off, int n_gr, int tid)
+                                          void *pcm, uint64_t pcm_off, int i, int j)
 {
-    const int i = tid >> 5, j = tid & 31;
-    if (i >= n_gr) return;
     /* taps as (c[2m], c[2m+1]) pairs, history as (A[h], B[h-1]) pairs: one packed FMA (Blackwell FFMA2) advances
      * the A-sum and the B-sum of the reference formula together; lanes of the pair never mix, so every partial
      * sum is the one two scalar FMA chains would produce */
@@ -301,10 +300,8 @@ __device__ __forceinline__ void fir_phase(const float *ybase, const float *fir_t
 /* the 2-of-32 outputs the reference produces through mp3d_scale_pcm (truncate(x + .5) - (x < 0)).  Warp i parked
  * the values of granule i itself (its lanes 0 and 16), so the pass is warp-local: no block barrier. */
 template <int NCH, int SLOTS>
-__device__ __forceinline__ void special_round_pass(const float *special, void *pcm, uint64_t pcm_off, int n_gr, int tid)
+__device__ __forceinline__ void special_round_pass(const float *special, void *pcm, uint64_t pcm_off, int i, int lane)
 {
-    const int i = tid >> 5, lane = tid & 31;
-    if (i >= n_gr) return;
     __syncwarp();
     for (int k = lane; k < 2*SLOTS; k += 32)
     {
@@ -438,7 +435,9 @@ k_l3_transform(TransformArgs a, const uint16_t *__restrict__ reorder_inv, const 
      * the HBM line order; short blocks are de-interleaved when the IMDCT jobs read them.  No block-wide barrier
      * until the rows are complete. ---- */
     constexpr int kW = kThreads/32;
-    constexpr int kU = (GT + 2 + kW - 1)/kW;   /* granules per warp */
+    constexpr int kU = (GT + 2 + kW - 1)/kW;   /* granules per warp, stereo tile (GT + 2 halo granules) */
+    constexpr int kUm = (MP3B_TILE_GRANULES_MONO + 2 + kW - 1)/kW;   /* mono tile: twice the granules in the same rows */
+    static_assert(kUm <= 4 && MP3B_TILE_GRANULES_MONO + 2 <= MP3B_TILE_SLOTS, "mono tile fits the slots, a quarter-warp per row");
     if (tid == 0 && blockIdx.x + 1024 < a.n_tiles)
         asm volatile("prefetch.global.L2 [%0];" :: "l"(a.tile_recs + blockIdx.x + 1024));   /* a later wave's record */
     if (tid == 32 && blockIdx.x + 1024 < a.n_tiles)
@@ -452,7 +451,7 @@ k_l3_transform(TransformArgs a, const uint16_t *__restrict__ reorder_inv, const 
         const uint2 v = __ldg(reinterpret_cast<const uint2 *>(&rec->slot[(warp + kW*uj)*2 + uch]));
         ts_st.gc = (int)v.x; ts_st.info = v.y;
     }
-    if (lane < kU)
+    if (lane < kUm && warp + kW*lane < MP3B_TILE_SLOTS)
     {
         const uint2 v = __ldg(reinterpret_cast<const uint2 *>(&rec->slot[warp + kW*lane]));
         ts_mono.gc = (int)v.x; ts_mono.info = v.y;
@@ -461,7 +460,7 @@ k_l3_transform(TransformArgs a, const uint16_t *__restrict__ reorder_inv, const 
     const int my_unit = nch == 2 ? warp + kW*uj : warp + kW*lane;
     const int my_ch = nch == 2 ? uch : 0;
     const int my_slot = my_unit*nch + my_ch;
-    const bool has = (nch == 2 ? lane < kU*2 : lane < kU) && my_unit < n_units;
+    const bool has = (nch == 2 ? lane < kU*2 : lane < kUm) && my_unit < n_units;
     const TileSlot ts = nch == 2 ? ts_st : ts_mono;
     const uint32_t bar = smem_addr(&S.mbar[warp]);
     const unsigned has_mask = __ballot_sync(0xffffffffu, has);
@@ -698,12 +697,21 @@ k_l3_transform(TransformArgs a, const uint16_t *__restrict__ reorder_inv, const 
 
     /* ---- phase 5: window FIR + PCM conversion ---- */
     float *special = S.x + kYFloats;     /* slack behind Y: n_gr*2*18*nch floats */
-    if (nch == 2) fir_phase<FLOAT_OUT, 2, 18, kRows>(S.x, S.fir_taps, special, a.pcm, tile.pcm_off, n_gr, tid);
-    else fir_phase<FLOAT_OUT, 1, 18, kRows>(S.x, S.fir_taps, special, a.pcm, tile.pcm_off, n_gr, tid);
-    if (!FLOAT_OUT)
+    if (nch == 2)
     {
-        if (nch == 2) special_round_pass<2, 18>(special, a.pcm, tile.pcm_off, n_gr, tid);
-        else special_round_pass<1, 18>(special, a.pcm, tile.pcm_off, n_gr, tid);
+        if (warp < n_gr)
+        {
+            fir_phase<FLOAT_OUT, 2, 18, kRows>(S.x, S.fir_taps, special, a.pcm, tile.pcm_off, warp, lane);
+            if (!FLOAT_OUT) special_round_pass<2, 18>(special, a.pcm, tile.pcm_off, warp, lane);
+        }
+    } else
+    {
+        /* a mono tile holds twice the granules (same rows of shared memory): a warp takes granules w, w + 8 */
+        for (int i = warp; i < n_gr; i += kThreads/32)
+        {
+            fir_phase<FLOAT_OUT, 1, 18, kRows>(S.x, S.fir_taps, special, a.pcm, tile.pcm_off, i, lane);
+            if (!FLOAT_OUT) special_round_pass<1, 18>(special, a.pcm, tile.pcm_off, i, lane);
+        }
     }
 
     MP3B_STAMP();
@@ -781,12 +789,15 @@ k_l12_synth(Synth12Args a, const float *__restrict__ fir_coef)
     }
     __syncthreads();
     float *special = y + kY12Floats;
-    if (nch == 2) fir_phase<FLOAT_OUT, 2, 12, kRows12>(y, fir_taps, special, a.pcm, tile.pcm_off, n_gr, tid);
-    else fir_phase<FLOAT_OUT, 1, 12, kRows12>(y, fir_taps, special, a.pcm, tile.pcm_off, n_gr, tid);
-    if (!FLOAT_OUT)
+    if (warp < n_gr)
     {
-        if (nch == 2) special_round_pass<2, 12>(special, a.pcm, tile.pcm_off, n_gr, tid);
-        else special_round_pass<1, 12>(special, a.pcm, tile.pcm_off, n_gr, tid);
+        if (nch == 2) fir_phase<FLOAT_OUT, 2, 12, kRows12>(y, fir_taps, special, a.pcm, tile.pcm_off, warp, lane);
+        else fir_phase<FLOAT_OUT, 1, 12, kRows12>(y, fir_taps, special, a.pcm, tile.pcm_off, warp, lane);
+        if (!FLOAT_OUT)
+        {
+            if (nch == 2) special_round_pass<2, 12>(special, a.pcm, tile.pcm_off, warp, lane);
+            else special_round_pass<1, 12>(special, a.pcm, tile.pcm_off, warp, lane);
+        }
     }
     if (a.state_out)
         for (int k = tid; k < nch*15*32; k += kThreads)

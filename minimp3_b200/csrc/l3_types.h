@@ -14,6 +14,8 @@
 #include <stdint.h>
 
 #define MP3B_TILE_GRANULES 8
+/* mono Layer III tiles hold twice the granules: the transform CTA's shared memory is laid out for two channels */
+#define MP3B_TILE_GRANULES_MONO 16
 
 /* GcDesc.flags0 */
 #define GCF_BLOCK_TYPE_MASK 0x03

@@ -57,7 +57,7 @@ static void walk_and_check(const uint8_t *data, size_t size, bool raw, bool allo
     uint64_t tile_samples = 0;
     for (const TileDesc &t : plan.tiles)
     {
-        CHECK(t.n_gr >= 1 && t.n_gr <= MP3B_TILE_GRANULES && (t.nch == 1 || t.nch == 2));
+        CHECK(t.n_gr >= 1 && t.n_gr <= (t.nch == 1 ? MP3B_TILE_GRANULES_MONO : MP3B_TILE_GRANULES) && (t.nch == 1 || t.nch == 2));
         CHECK((uint64_t)t.gc_first + (uint64_t)t.n_gr*t.nch <= plan.n_gc);
         for (int c = 0; c < 2; c++)
             for (int h = 0; h < 2; h++) CHECK(t.halo[c][h] < (int64_t)plan.n_gc);

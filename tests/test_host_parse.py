@@ -84,7 +84,7 @@ def test_tiles_partition_the_granule_list():
         n_gr = 0
         pcm = 0
         for t in w["tiles"]:
-            assert 1 <= t["n_gr"] <= 8 and t["nch"] in (1, 2)
+            assert 1 <= t["n_gr"] <= (16 if t["nch"] == 1 else 8) and t["nch"] in (1, 2)   # mono tiles hold twice the granules
             assert t["pcm_off"] == pcm
             assert t["gc_first"] == w["gr_gc"][n_gr]
             for k in range(int(t["n_gr"])):
