@@ -192,6 +192,8 @@ typedef struct
     int n_devices;                    /* 0 / 1: `device` alone.  2..8: mp3dec_decode_batch_cuda shards the streams over */
     int devices[8];                   /* devices[0 .. n_devices-1] (greedy LPT on input bytes, no collective); */
                                       /* `device` is ignored then.  Plans (mp3dec_batch_plan_*) are single-device. */
+    int gpu_frame_scan;               /* frame sync + reservoir accounting on the GPU (mp3dec_decode_batch_cuda only): */
+                                      /* 0 auto (chunks of >= 64 streams), 1 always, -1 never.  Results do not depend on it. */
 } mp3dec_batch_opts_t;
 
 /* Decodes n_streams independent buffers; per-stream result and return code (infos_out[i], rets_out[i],
@@ -211,6 +213,7 @@ typedef struct
     double finish_ms;            /* waiting for the read-backs + output hand-over (malloc copies) */
     uint64_t h2d_bytes, d2h_bytes;
     int n_chunks, n_devices;
+    int scanned_streams;         /* streams whose frames were found by the GPU frame scan (the rest: host walker) */
 } mp3dec_batch_call_stats_t;
 void mp3dec_batch_last_call_stats(mp3dec_batch_call_stats_t *out);
 

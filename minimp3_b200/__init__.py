@@ -45,7 +45,7 @@ class BatchStream(C.Structure):
 class BatchOpts(C.Structure):
     _fields_ = [("device", C.c_int), ("float_output", C.c_int), ("raw_frames", C.c_int),
                 ("allow_mono_stereo_transition", C.c_int), ("host_threads", C.c_int), ("output", C.c_int),
-                ("cuda_stream", C.c_void_p), ("n_devices", C.c_int), ("devices", C.c_int*8)]
+                ("cuda_stream", C.c_void_p), ("n_devices", C.c_int), ("devices", C.c_int*8), ("gpu_frame_scan", C.c_int)]
 
 
 class BatchStats(C.Structure):
@@ -59,7 +59,7 @@ class BatchStats(C.Structure):
 class BatchCallStats(C.Structure):
     _fields_ = [("total_ms", C.c_double), ("host_parse_ms", C.c_double), ("issue_ms", C.c_double),
                 ("finish_ms", C.c_double), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
-                ("n_chunks", C.c_int), ("n_devices", C.c_int)]
+                ("n_chunks", C.c_int), ("n_devices", C.c_int), ("scanned_streams", C.c_int)]
 
 
 EXPORTS = ["mp3dec_init", "mp3dec_decode_frame", "mp3dec_decode_frame_f32", "mp3dec_f32_to_s16", "mp3dec_detect_buf",
@@ -163,9 +163,10 @@ def _as_u8(data):
 
 
 def _opts(device=0, float_output=False, raw_frames=False, allow_mono_stereo=False, host_threads=0, output=OUT_PINNED,
-          cuda_stream=None, devices=None):
+          cuda_stream=None, devices=None, gpu_frame_scan=0):
     o = BatchOpts(int(device), int(bool(float_output)), int(bool(raw_frames)), int(bool(allow_mono_stereo)),
                   int(host_threads), int(output), C.c_void_p(cuda_stream) if cuda_stream else None)
+    o.gpu_frame_scan = int(gpu_frame_scan)
     if devices:
         o.n_devices = len(devices)
         for i, d in enumerate(devices[:8]):

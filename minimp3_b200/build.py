@@ -17,9 +17,9 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libminimp3_b200.so")
 HARNESS = os.path.join(ROOT, "tests", "_build", "libmp3b_cpu_harness.so")
 
-CU_SOURCES = ["k_entropy.cu", "k_stereo.cu", "k_transform.cu", "k_layer12.cu", "k_sideinfo.cu", "k_order.cu", "capi.cu"]
+CU_SOURCES = ["k_entropy.cu", "k_stereo.cu", "k_transform.cu", "k_layer12.cu", "k_sideinfo.cu", "k_order.cu", "k_scan.cu", "capi.cu"]
 CPP_SOURCES = ["host_parse.cpp", "ex_api.cpp"]
-HEADERS = ["l3_types.h", "l3_math.cuh", "l3_entropy.cuh", "l3_sideinfo.cuh", "l12_decode.cuh", "l3_tables_build.h", "kernels.h", "host_parse.h", "mp3_tables.h",
+HEADERS = ["l3_types.h", "l3_math.cuh", "l3_entropy.cuh", "l3_sideinfo.cuh", "l12_decode.cuh", "l3_tables_build.h", "kernels.h", "host_parse.h", "mp3_hdr.cuh", "mp3_tables.h",
            os.path.join("..", "..", "include", "minimp3_b200.h")]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
@@ -75,7 +75,7 @@ def build_cpu_harness(force=False):
     deps = [src, os.path.join(CSRC, "host_parse.cpp"), os.path.join(CSRC, "host_parse.h"),
             os.path.join(CSRC, "l3_math.cuh"), os.path.join(CSRC, "mp3_tables.h"), os.path.join(CSRC, "l3_types.h"),
             os.path.join(CSRC, "l3_entropy.cuh"), os.path.join(CSRC, "l12_decode.cuh"), os.path.join(CSRC, "l3_tables_build.h"),
-            os.path.join(CSRC, "l3_sideinfo.cuh")]
+            os.path.join(CSRC, "l3_sideinfo.cuh"), os.path.join(CSRC, "mp3_hdr.cuh")]
     if not force and not _newer(HARNESS, deps):
         return HARNESS
     os.makedirs(os.path.dirname(HARNESS), exist_ok=True)

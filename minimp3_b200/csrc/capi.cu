@@ -22,6 +22,7 @@
 #include "../../include/minimp3_b200.h"
 #include "host_parse.h"
 #include "kernels.h"
+#include "mp3_hdr.cuh"
 
 using namespace mp3b;
 
@@ -179,11 +180,16 @@ struct BufferSet
     PinBuf h_md, h_gcs, h_frames, h_tiles, h_ist, h_order, h_gcbase, h_pcm, h_l12, h_tiles12;
     DevBuf d_md, d_gcs, d_frames, d_tiles, d_tile_recs, d_tile_jobs, d_counter, d_istlist, d_order, d_order_sorted, d_order_scratch, d_gcbase, d_xr, d_nzl, d_istpos, d_pcm, d_l12, d_tiles12, d_sub12;
     DevBuf d_tap_q, d_tap_scf, d_tap_sub, d_phase_clk;
+    /* GPU frame scan (k_scan.cu) */
+    PinBuf h_scan, h_sum, h_bases, h_slotmap;
+    DevBuf d_raw, d_scan, d_scan_frames, d_sum, d_bases, d_slotmap;
     void release()
     {
         h_md.release(); h_gcs.release(); h_frames.release(); h_tiles.release(); h_ist.release(); h_order.release(); h_gcbase.release(); h_pcm.release(); h_l12.release(); h_tiles12.release();
         d_l12.release(); d_tiles12.release(); d_sub12.release();
         d_md.release(); d_gcs.release(); d_frames.release(); d_tiles.release(); d_tile_recs.release(); d_tile_jobs.release(); d_counter.release(); d_istlist.release(); d_order.release(); d_order_sorted.release(); d_order_scratch.release(); d_gcbase.release(); d_xr.release(); d_nzl.release();
+        h_scan.release(); h_sum.release(); h_bases.release(); h_slotmap.release();
+        d_raw.release(); d_scan.release(); d_scan_frames.release(); d_sum.release(); d_bases.release(); d_slotmap.release();
         d_istpos.release(); d_pcm.release(); d_tap_q.release(); d_tap_scf.release(); d_tap_sub.release(); d_phase_clk.release();
     }
 };
@@ -288,6 +294,7 @@ struct mp3dec_batch_plan
     size_t sample_size = 2;
     bool taps = false;
     cudaEvent_t ev_kernels = nullptr, ev_d2h = nullptr, ev_h2d = nullptr;
+    std::vector<int> out_index;    /* stream i of the plan is stream out_index[i] of the caller (empty: identity) */
     bool export_on_destroy = false; /* one-call entry point with pinned / device output: the caller holds pointers into bufs */
     bool order_sorted = false;     /* the entropy kernel reads d_order_sorted (order across streams, k_order.cu) */
     bool sort_order = false;
@@ -343,9 +350,27 @@ static int plan_prep(mp3dec_batch_plan_t *P)
     return 0;
 }
 
+static mp3dec_batch_plan_t *plan_create_scan(const mp3dec_batch_stream_t *streams, int n_streams, const mp3dec_batch_opts_t *opts_in,
+                                             int *err, std::vector<int> *rest);
+
 mp3dec_batch_plan_t *mp3dec_batch_plan_create(const mp3dec_batch_stream_t *streams, int n_streams,
                                               const mp3dec_batch_opts_t *opts_in, int *err)
 {
+    int dummy;
+    if (!err) err = &dummy;
+    if (opts_in && opts_in->gpu_frame_scan > 0 && streams && n_streams > 0)
+    {
+        /* a plan is one set of buffers: the scan route is taken when it can take every stream */
+        bool ok = true;
+        for (int i = 0; i < n_streams; i++) ok &= !((!streams[i].buf && streams[i].size) || streams[i].size == (size_t)-1);
+        if (ok)
+        {
+            std::vector<int> rest;
+            mp3dec_batch_plan_t *P = plan_create_scan(streams, n_streams, opts_in, err, &rest);
+            if (P && rest.empty() && cudaStreamSynchronize(P->stream) == cudaSuccess) return P;
+            if (P) { cudaStreamSynchronize(P->stream); mp3dec_batch_plan_destroy(P); }
+        }
+    }
     return plan_create_impl(streams, n_streams, opts_in, err, false);
 }
 
@@ -568,6 +593,280 @@ static mp3dec_batch_plan_t *plan_create_impl(const mp3dec_batch_stream_t *stream
     return P;
 }
 
+/* ---- plan creation through the GPU frame scan (k_scan.cu) ------------------------------------------------------
+ * The host finds where every stream's audio starts (tags, first frame, VBR tag: open_stream_head / find_frame) and
+ * copies the streams into pinned staging; the per-frame work -- header chain, side-info checks, reservoir
+ * accounting, payload concatenation, frame records, tiles -- runs on the device.  Streams the scan cannot take
+ * (Layer I/II, free format, anything irregular: see k_scan.cu) are returned in *rest for the host walker.  The plan
+ * covers the streams it took plus the ones with nothing to decode. */
+static mp3dec_batch_plan_t *plan_create_scan(const mp3dec_batch_stream_t *streams, int n_streams, const mp3dec_batch_opts_t *opts_in,
+                                             int *err, std::vector<int> *rest)
+{
+    *err = 0;
+    mp3dec_batch_opts_t opts;
+    memset(&opts, 0, sizeof(opts));
+    if (opts_in) opts = *opts_in;
+    DeviceCtx *ctx = get_ctx(opts.device);
+    if (!ctx) { *err = MP3D_E_CUDA; return nullptr; }
+    cudaSetDevice(ctx->device);
+    const double t0 = now_ms();
+
+    struct Head
+    {
+        const uint8_t *p = nullptr;
+        size_t size = 0;
+        StreamHead h;
+        int kind = 0;              /* 0 nothing to decode, 1 scan candidate, 2 host walker */
+        uint32_t slot_cap = 0;
+    };
+    std::vector<Head> heads(n_streams);
+    parallel_for(n_streams, opts.host_threads, [&](int i) {
+        Head &H = heads[i];
+        const uint8_t *buf = streams[i].buf;
+        size_t size = streams[i].size;
+        if (size >= (1u << 31)) { H.kind = 2; return; }
+        if (!opts.raw_frames)
+        {
+            if (!open_stream_head(&buf, &size, &H.h)) return;
+        } else
+        {
+            int free_format_bytes = 0, frame_size = 0;
+            const int junk = find_frame(buf, (int)size, &free_format_bytes, &frame_size);
+            if (!frame_size) return;
+            buf += junk;
+            size -= (size_t)junk;
+        }
+        H.p = buf;
+        H.size = size;
+        if (size < 4 || hd_layer(buf) != 3 || hd_is_free_format(buf)) { H.kind = 2; return; }
+        /* shortest frame this stream can hold: lowest bit rate of its version / sample rate, no padding */
+        uint8_t probe[4] = { buf[0], buf[1], (uint8_t)((buf[2] & 0x0C) | 0x10), buf[3] };
+        const int min_fs = std::max(hd_frame_bytes(probe, 0), 24);
+        H.slot_cap = (uint32_t)(size/(size_t)min_fs) + 2;
+        H.kind = 1;
+    });
+    /* candidates: staging offsets and slot groups */
+    std::vector<int> cand;
+    std::vector<uint64_t> raw_base;
+    uint64_t raw_bytes = 0, n_slots = 0;
+    for (int i = 0; i < n_streams; i++)
+    {
+        if (heads[i].kind == 2) rest->push_back(i);
+        if (heads[i].kind != 1) continue;
+        cand.push_back(i);
+        raw_base.push_back(raw_bytes);
+        raw_bytes += round_up(heads[i].size + 16, 16);
+        n_slots += round_up(heads[i].slot_cap, 1u << EMIT_SLOT_SHIFT);
+    }
+    const int nc = (int)cand.size();
+    if (n_slots >= (1ull << 31)) { *err = MP3D_E_PARAM; return nullptr; }
+
+    mp3dec_batch_plan *P = new mp3dec_batch_plan();
+    P->ctx = ctx;
+    P->opts = opts;
+    P->stream = opts.cuda_stream ? (cudaStream_t)opts.cuda_stream : ctx->stream;
+    P->sample_size = opts.float_output ? 4 : 2;
+    P->bufs = acquire_set(ctx);
+    BufferSet &B = *P->bufs;
+    cudaStream_t up = opts.cuda_stream ? P->stream : ctx->stream_h2d;
+    std::vector<ScanSummary> sums(nc);
+    if (nc)
+    {
+        const size_t n_groups = (size_t)(n_slots >> EMIT_SLOT_SHIFT);
+        bool ok = B.h_md.ensure(raw_bytes + 64) && B.d_raw.ensure(raw_bytes + 64) && B.h_scan.ensure((size_t)nc*sizeof(ScanStream)) &&
+                  B.d_scan.ensure((size_t)nc*sizeof(ScanStream)) && B.h_slotmap.ensure(n_groups*4 + 64) && B.d_slotmap.ensure(n_groups*4 + 64) &&
+                  B.d_scan_frames.ensure((size_t)n_slots*sizeof(ScanFrame) + 64) && B.h_sum.ensure((size_t)nc*sizeof(ScanSummary)) &&
+                  B.d_sum.ensure((size_t)nc*sizeof(ScanSummary));
+        if (!ok) { *err = MP3D_E_MEMORY; mp3dec_batch_plan_destroy(P); return nullptr; }
+        ScanStream *hs = (ScanStream *)B.h_scan.p;
+        uint32_t *slotmap = (uint32_t *)B.h_slotmap.p;
+        uint32_t slot = 0;
+        for (int k = 0; k < nc; k++)
+        {
+            const Head &H = heads[cand[k]];
+            hs[k].src_off = raw_base[k];
+            hs[k].size = (uint32_t)H.size;
+            hs[k].slot_base = slot;
+            hs[k].slot_cap = H.slot_cap;
+            memcpy(hs[k].first_hdr, H.p, 4);
+            const uint32_t groups = (uint32_t)(round_up(H.slot_cap, 1u << EMIT_SLOT_SHIFT) >> EMIT_SLOT_SHIFT);
+            for (uint32_t g = 0; g < groups; g++) slotmap[(slot >> EMIT_SLOT_SHIFT) + g] = (uint32_t)k;
+            slot += groups << EMIT_SLOT_SHIFT;
+        }
+        uint8_t *h_raw = (uint8_t *)B.h_md.p;
+        parallel_for(nc, opts.host_threads, [&](int k) {
+            const Head &H = heads[cand[k]];
+            memcpy(h_raw + raw_base[k], H.p, H.size);
+            memset(h_raw + raw_base[k] + H.size, 0, (size_t)(round_up(H.size + 16, 16) - H.size));
+        });
+        cudaMemcpyAsync(B.d_raw.p, h_raw, raw_bytes, cudaMemcpyHostToDevice, up);
+        cudaMemcpyAsync(B.d_scan.p, hs, (size_t)nc*sizeof(ScanStream), cudaMemcpyHostToDevice, up);
+        cudaMemcpyAsync(B.d_slotmap.p, slotmap, n_groups*4, cudaMemcpyHostToDevice, up);
+        ScanArgs sa;
+        sa.raw = (const uint8_t *)B.d_raw.p;
+        sa.streams = (const ScanStream *)B.d_scan.p;
+        sa.n_streams = (uint32_t)nc;
+        sa.frames = (ScanFrame *)B.d_scan_frames.p;
+        sa.summaries = (ScanSummary *)B.d_sum.p;
+        cudaError_t e = launch_stream_scan(sa, up);
+        cudaMemcpyAsync(B.h_sum.p, B.d_sum.p, (size_t)nc*sizeof(ScanSummary), cudaMemcpyDeviceToHost, up);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(up);
+        if (e != cudaSuccess)
+        {
+            fprintf(stderr, "minimp3_b200: frame scan failed: %s\n", cudaGetErrorString(e));
+            *err = MP3D_E_CUDA;
+            mp3dec_batch_plan_destroy(P);
+            return nullptr;
+        }
+        memcpy(sums.data(), B.h_sum.p, (size_t)nc*sizeof(ScanSummary));
+    }
+    const double t_scan = now_ms();
+
+    /* the plan's streams: what the scan took + the streams with nothing to decode (they only get zeroed results) */
+    std::vector<int> cand_of;          /* plan stream -> candidate index or -1 */
+    for (int i = 0, k = 0; i < n_streams; i++)
+    {
+        const bool is_cand = heads[i].kind == 1;
+        if (is_cand && sums[k].status != SCAN_OK) rest->push_back(i);
+        else if (heads[i].kind != 2)
+        {
+            P->out_index.push_back(i);
+            cand_of.push_back(is_cand ? k : -1);
+        }
+        if (is_cand) k++;
+    }
+    std::sort(rest->begin(), rest->end());
+    const int np = (int)P->out_index.size();
+    P->n_streams = np;
+    P->plans.assign(np, StreamPlan());
+    P->pcm_base.assign(np + 1, 0);
+    P->gc_base.assign(np + 1, 0);
+    if (!B.h_bases.ensure((size_t)std::max(nc, 1)*sizeof(StreamBase)) || !B.d_bases.ensure((size_t)std::max(nc, 1)*sizeof(StreamBase)))
+    { *err = MP3D_E_MEMORY; mp3dec_batch_plan_destroy(P); return nullptr; }
+    StreamBase *hb = (StreamBase *)B.h_bases.p;
+    for (int k = 0; k < nc; k++) { memset(&hb[k], 0, sizeof(StreamBase)); }
+    uint64_t gcs = 0, frs = 0, tiles = 0, samples = 0, ists = 0, orders = 0, md = 0, pads = 0;
+    uint32_t max_slots = 0;
+    for (int j = 0; j < np; j++)
+    {
+        P->pcm_base[j] = samples;
+        P->gc_base[j] = gcs;
+        const int k = cand_of[j];
+        if (k < 0) continue;
+        const Head &H = heads[P->out_index[j]];
+        const ScanSummary &S = sums[k];
+        StreamPlan &sp = P->plans[j];
+        const uint64_t per_frame = (uint64_t)hd_frame_samples(H.p)*S.nch;
+        sp.samples_decoded = per_frame*S.n_dec;
+        sp.frames = S.n_frames;
+        sp.frames_decoded = S.n_dec;
+        sp.main_data_bytes = S.md_len;
+        sp.avg_bitrate_kbps = S.n_dec ? (int)(S.kbps_sum/S.n_dec) : 0;
+        if (!opts.raw_frames)
+        {
+            sp.channels = H.h.first.channels; sp.hz = H.h.first.hz; sp.layer = H.h.first.layer;
+            sp.out_skip = std::min<uint64_t>(H.h.to_skip, sp.samples_decoded);
+            sp.out_samples = sp.samples_decoded - sp.out_skip;
+            if (H.h.detected_samples && sp.out_samples > H.h.detected_samples) sp.out_samples = H.h.detected_samples;
+        } else
+        {
+            if (S.n_dec) { sp.channels = S.nch; sp.hz = (int)hd_sample_rate_hz(H.p); sp.layer = 3; }
+            sp.out_samples = sp.samples_decoded;
+        }
+        const uint32_t n_gc = S.n_dec*S.n_gr*S.nch, tg = S.nch == 1 ? MP3B_TILE_GRANULES_MONO : MP3B_TILE_GRANULES;
+        StreamBase &b = hb[k];
+        b.take = 1; b.nch = S.nch; b.n_gr = S.n_gr;
+        b.n_frames = S.n_frames; b.n_dec = S.n_dec;
+        b.md_base = md; b.pcm_base = samples;
+        b.gc_base = (uint32_t)gcs; b.gc_pad_before = (uint32_t)pads; b.fr_base = (uint32_t)frs;
+        b.tile_base = (uint32_t)tiles; b.ist_base = (uint32_t)ists;
+        max_slots = std::max<uint32_t>(max_slots, (uint32_t)round_up(n_gc, 2));
+        pads += round_up(n_gc, 2) - n_gc;
+        gcs += round_up(n_gc, 2);
+        frs += S.n_dec;
+        tiles += ((uint64_t)S.n_dec*S.n_gr + tg - 1)/tg;
+        samples += sp.samples_decoded;
+        ists += S.n_ist;
+        orders += n_gc;
+        md += round_up((size_t)S.md_len + 16, 16);
+        P->n_frames += S.n_dec;
+        P->input_bytes += S.md_len;
+    }
+    /* streams that were dropped keep a tile_base so that k_stream_tiles' search stays monotonic */
+    {
+        uint32_t tb = (uint32_t)tiles;
+        for (int k = nc - 1; k >= 0; k--)
+        {
+            if (hb[k].take) tb = hb[k].tile_base;
+            else hb[k].tile_base = tb;
+        }
+    }
+    P->pcm_base[np] = samples;
+    P->gc_base[np] = gcs;
+    P->md_bytes = md + 4096;
+    P->n_gc = gcs; P->n_tiles = tiles; P->n_samples = samples; P->n_ist = ists; P->n_order = orders;
+    if (gcs >= (1ull << 31)) { *err = MP3D_E_PARAM; mp3dec_batch_plan_destroy(P); return nullptr; }
+
+    const bool sort_order = frs && orders >= kMinOrderSort && np >= 2;
+    const size_t order_scratch = sort_order ? order_sort_scratch_bytes((uint32_t)orders, (uint32_t)np) : 0;
+    bool ok = B.d_md.ensure(P->md_bytes) && B.d_gcs.ensure((size_t)gcs*sizeof(GcDesc) + 64) && B.d_frames.ensure((size_t)frs*sizeof(FrameRec) + 64) &&
+              B.d_tiles.ensure((size_t)tiles*sizeof(TileDesc) + 64) && B.d_tile_recs.ensure((size_t)tiles*sizeof(TileRec) + 256) &&
+              B.d_tile_jobs.ensure((size_t)tiles*MP3B_TILE_JOBS*2 + 256) && B.d_counter.ensure(256) && B.d_istlist.ensure((size_t)ists*4 + 64) &&
+              B.d_order.ensure((size_t)orders*4 + 64) &&
+              (!sort_order || (B.d_order_sorted.ensure((size_t)orders*4 + 64) && B.d_order_scratch.ensure(order_scratch) &&
+                               B.h_gcbase.ensure(((size_t)np + 1)*4 + 64) && B.d_gcbase.ensure(((size_t)np + 1)*4 + 64))) &&
+              B.d_xr.ensure((size_t)gcs*576*sizeof(float) + 64) && B.d_nzl.ensure((size_t)gcs*2 + 64) &&
+              B.d_istpos.ensure((size_t)gcs*40 + 64) && B.d_pcm.ensure((size_t)samples*P->sample_size + 64);
+    if (!ok) { *err = MP3D_E_MEMORY; mp3dec_batch_plan_destroy(P); return nullptr; }
+    if (nc) cudaMemcpyAsync(B.d_bases.p, hb, (size_t)nc*sizeof(StreamBase), cudaMemcpyHostToDevice, up);
+    if (sort_order)
+    {
+        uint32_t *gb = (uint32_t *)B.h_gcbase.p;
+        for (int j = 0; j <= np; j++) gb[j] = (uint32_t)P->gc_base[j];
+        cudaMemcpyAsync(B.d_gcbase.p, gb, ((size_t)np + 1)*4, cudaMemcpyHostToDevice, up);
+    }
+    cudaMemsetAsync(B.d_md.p, 0, P->md_bytes, up);            /* slack between the streams and the guard behind them */
+    if (gcs) cudaMemsetAsync(B.d_gcs.p, 0, (size_t)gcs*sizeof(GcDesc), up);   /* padding slots are never written */
+    if (nc && frs)
+    {
+        EmitArgs ea;
+        ea.raw = (const uint8_t *)B.d_raw.p;
+        ea.streams = (const ScanStream *)B.d_scan.p;
+        ea.bases = (const StreamBase *)B.d_bases.p;
+        ea.n_streams = (uint32_t)nc;
+        ea.slot_stream = (const uint32_t *)B.d_slotmap.p;
+        ea.frames = (const ScanFrame *)B.d_scan_frames.p;
+        ea.n_slots = (uint32_t)n_slots;
+        ea.frame_recs = (FrameRec *)B.d_frames.p;
+        ea.order = (uint32_t *)B.d_order.p;
+        ea.ist_list = (uint32_t *)B.d_istlist.p;
+        ea.md = (uint8_t *)B.d_md.p;
+        ea.tiles = (TileDesc *)B.d_tiles.p;
+        ea.n_tiles = (uint32_t)tiles;
+        if (launch_stream_emit(ea, up) != cudaSuccess) { *err = MP3D_E_CUDA; mp3dec_batch_plan_destroy(P); return nullptr; }
+    }
+    if (up != P->stream)
+    {
+        cudaEventCreateWithFlags(&P->ev_h2d, cudaEventDisableTiming);
+        cudaEventRecord(P->ev_h2d, up);
+        cudaStreamWaitEvent(P->stream, P->ev_h2d, 0);
+    }
+    P->sort_order = sort_order; P->order_scratch = order_scratch; P->max_slots = max_slots; P->n_frame_recs = frs;
+    if (plan_prep(P) != 0) { *err = MP3D_E_CUDA; mp3dec_batch_plan_destroy(P); return nullptr; }
+    P->stats.input_bytes = P->input_bytes;
+    P->stats.samples = samples;
+    P->stats.n_granule_channels = gcs;
+    P->stats.n_tiles = tiles;
+    P->stats.n_istereo_granules = ists;
+    P->stats.n_frames = P->n_frames;
+    P->stats.h2d_bytes = raw_bytes + (uint64_t)nc*(sizeof(ScanStream) + sizeof(StreamBase)) + (n_slots >> EMIT_SLOT_SHIFT)*4;
+    P->stats.kernels_per_run = (orders ? 1 : 0) + (ists ? 1 : 0) + (tiles ? 2 : 0);
+    P->stats.kernels_prep = (nc ? 4 : 0) + (frs ? 1 : 0) + (sort_order ? 2 : 0);
+    P->stats.host_parse_ms = (t_scan - t0) + (now_ms() - t_scan);
+    P->stats.h2d_ms = 0;
+    return P;
+}
+
 int mp3dec_batch_plan_enable_taps(mp3dec_batch_plan_t *P)
 {
     if (!P) return MP3D_E_PARAM;
@@ -759,9 +1058,10 @@ static int plan_finish_fetch(mp3dec_batch_plan_t *P, mp3dec_file_info_t *infos, 
     std::atomic<int> oom(0);
     parallel_for(P->n_streams, mode == MP3D_BATCH_OUT_MALLOC ? P->opts.host_threads : 1, [&](int i) {
         const StreamPlan &sp = P->plans[i];
-        if (rets) rets[i] = sp.ret;
+        const int o = P->out_index.empty() ? i : P->out_index[i];
+        if (rets) rets[o] = sp.ret;
         if (!infos) return;
-        mp3dec_file_info_t &fi = infos[i];
+        mp3dec_file_info_t &fi = infos[o];
         memset(&fi, 0, sizeof(fi));
         fi.samples = (size_t)sp.out_samples;
         fi.channels = sp.channels; fi.hz = sp.hz; fi.layer = sp.layer; fi.avg_bitrate_kbps = sp.avg_bitrate_kbps;
@@ -772,7 +1072,7 @@ static int plan_finish_fetch(mp3dec_batch_plan_t *P, mp3dec_file_info_t *infos, 
         else
         {
             void *m = malloc((size_t)sp.out_samples*ss);
-            if (!m) { oom = 1; fi.samples = 0; if (rets) rets[i] = MP3D_E_MEMORY; return; }
+            if (!m) { oom = 1; fi.samples = 0; if (rets) rets[o] = MP3D_E_MEMORY; return; }
             memcpy(m, host + first, (size_t)sp.out_samples*ss);
             fi.buffer = (mp3d_sample_t *)m;
         }
@@ -896,6 +1196,7 @@ static int decode_batch_multi(const mp3dec_batch_stream_t *streams, int n_stream
         cs.finish_ms = std::max(cs.finish_ms, stats[d].finish_ms);
         cs.h2d_bytes += stats[d].h2d_bytes; cs.d2h_bytes += stats[d].d2h_bytes;
         cs.n_chunks += stats[d].n_chunks;
+        cs.scanned_streams += stats[d].scanned_streams;
     }
     cs.n_devices = nd;
     cs.total_ms = now_ms() - call_t0;
@@ -928,24 +1229,13 @@ int mp3dec_decode_batch_cuda(const mp3dec_batch_stream_t *streams, int n_streams
         n_chunks = std::min(n_chunks, n_streams/32);
         if (n_chunks < 1) n_chunks = 1;
     }
-    if (n_chunks == 1)
-    {
-        mp3dec_batch_plan_t *P = mp3dec_batch_plan_create(streams, n_streams, opts, &err);
-        if (!P) return err;
-        P->export_on_destroy = exports;
-        cs.n_chunks = 1; cs.n_devices = 1;
-        cs.host_parse_ms = P->stats.host_parse_ms;
-        cs.h2d_bytes = P->stats.h2d_bytes;
-        cs.d2h_bytes = (P->opts.output == MP3D_BATCH_OUT_DEVICE) ? 0 : P->n_samples*P->sample_size;
-        err = mp3dec_batch_plan_run(P);
-        cs.issue_ms = now_ms() - call_t0;
-        if (!err) err = mp3dec_batch_plan_fetch(P, infos_out, rets_out);
-        mp3dec_batch_plan_destroy(P);
-        cs.total_ms = now_ms() - call_t0;
-        cs.finish_ms = cs.total_ms - cs.issue_ms;
-        return err;
-    }
-    std::vector<mp3dec_batch_plan_t *> plans(n_chunks, nullptr);
+    /* frame sync on the GPU (k_scan.cu) for chunks with enough streams to keep it busy: per-frame host work drops to
+     * one staging copy; streams the scan hands back (Layer I/II, free format, anything irregular) go through the host
+     * walker in a second plan of the same chunk.  opts.gpu_frame_scan: 0 auto, 1 always, -1 never. */
+    static const int scan_env = [] { const char *e = getenv("MP3B_GPU_SCAN"); return e ? atoi(e) : 0; }();
+    const int scan_mode = scan_env ? scan_env : (opts ? opts->gpu_frame_scan : 0);
+    struct Part { mp3dec_batch_plan_t *plan; int first; };
+    std::vector<Part> parts;
     std::vector<int> first(n_chunks + 1);
     /* small first chunks get the PCIe read-back going early; the later ones amortise launch overheads */
     {
@@ -962,40 +1252,59 @@ int mp3dec_decode_batch_cuda(const mp3dec_batch_stream_t *streams, int n_streams
     }
     static const bool dbg_timing = getenv("MP3B_DEBUG_TIMING") != nullptr;
     const double tt0 = now_ms();
+    auto launch = [&](mp3dec_batch_plan_t *P, int first_stream) {
+        parts.push_back(Part{ P, first_stream });
+        P->export_on_destroy = exports;
+        cs.host_parse_ms += P->stats.host_parse_ms;
+        cs.h2d_bytes += P->stats.h2d_bytes;
+        if (P->opts.output != MP3D_BATCH_OUT_DEVICE) cs.d2h_bytes += P->n_samples*P->sample_size;
+        int e = mp3dec_batch_plan_run(P);
+        if (!e) e = plan_begin_fetch(P, P->ctx->stream_d2h);
+        return e;
+    };
     for (int c = 0; c < n_chunks && !err; c++)
     {
         const double a0 = now_ms();
-        plans[c] = plan_create_impl(streams + first[c], first[c + 1] - first[c], opts, &err, true);
-        if (!plans[c]) break;
-        plans[c]->export_on_destroy = exports;
-        cs.host_parse_ms += plans[c]->stats.host_parse_ms;
-        cs.h2d_bytes += plans[c]->stats.h2d_bytes;
-        if (plans[c]->opts.output != MP3D_BATCH_OUT_DEVICE) cs.d2h_bytes += plans[c]->n_samples*plans[c]->sample_size;
-        const double a1 = now_ms();
-        err = mp3dec_batch_plan_run(plans[c]);
-        const double a2 = now_ms();
-        if (!err) err = plan_begin_fetch(plans[c], plans[c]->ctx->stream_d2h);
-        const double a3 = now_ms();
-        if (dbg_timing)
-            fprintf(stderr, "chunk %d: %d streams, create %.3f ms (walk stages %.3f), run %.3f, begin_fetch %.3f, t=%.3f\n", c,
-                    first[c + 1] - first[c], a1 - a0, plans[c]->stats.host_parse_ms, a2 - a1, a3 - a2, a3 - tt0);
+        const int n_c = first[c + 1] - first[c];
+        const bool scan = scan_mode > 0 || (scan_mode == 0 && n_c >= 64);
+        if (scan)
+        {
+            std::vector<int> rest;
+            mp3dec_batch_plan_t *P = plan_create_scan(streams + first[c], n_c, opts, &err, &rest);
+            if (!P) break;
+            cs.scanned_streams += n_c - (int)rest.size();
+            err = launch(P, first[c]);
+            if (!err && !rest.empty())
+            {
+                std::vector<mp3dec_batch_stream_t> sub(rest.size());
+                for (size_t k = 0; k < rest.size(); k++) sub[k] = streams[first[c] + rest[k]];
+                mp3dec_batch_plan_t *Q = plan_create_impl(sub.data(), (int)sub.size(), opts, &err, true);
+                if (!Q) break;
+                Q->out_index = rest;
+                err = launch(Q, first[c]);
+            }
+        } else
+        {
+            mp3dec_batch_plan_t *P = plan_create_impl(streams + first[c], n_c, opts, &err, true);
+            if (!P) break;
+            err = launch(P, first[c]);
+        }
+        if (dbg_timing) fprintf(stderr, "chunk %d: %d streams, issued in %.3f ms, t=%.3f\n", c, n_c, now_ms() - a0, now_ms() - tt0);
     }
     const double tt1 = now_ms();
-    for (int c = 0; c < n_chunks; c++)
+    for (Part &pt : parts)
     {
-        if (!plans[c]) continue;
         if (!err)
-            err = plan_finish_fetch(plans[c], infos_out ? infos_out + first[c] : nullptr, rets_out ? rets_out + first[c] : nullptr);
+            err = plan_finish_fetch(pt.plan, infos_out ? infos_out + pt.first : nullptr, rets_out ? rets_out + pt.first : nullptr);
         else
-            cudaStreamSynchronize(plans[c]->stream);
+            cudaStreamSynchronize(pt.plan->stream);
     }
     const double tt2 = now_ms();
-    for (int c = 0; c < n_chunks; c++)
-        if (plans[c])
-        {
-            if (err) cudaStreamSynchronize(plans[c]->ctx->stream_d2h);
-            mp3dec_batch_plan_destroy(plans[c]);
-        }
+    for (Part &pt : parts)
+    {
+        if (err) cudaStreamSynchronize(pt.plan->ctx->stream_d2h);
+        mp3dec_batch_plan_destroy(pt.plan);
+    }
     if (dbg_timing) fprintf(stderr, "issue %.3f ms, finish %.3f ms, destroy %.3f ms\n", tt1 - tt0, tt2 - tt1, now_ms() - tt2);
     cs.n_chunks = n_chunks; cs.n_devices = 1;
     cs.issue_ms = tt1 - call_t0; cs.finish_ms = tt2 - tt1; cs.total_ms = now_ms() - call_t0;

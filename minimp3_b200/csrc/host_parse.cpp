@@ -10,6 +10,7 @@
 #include <algorithm>
 
 #include "l12_decode.cuh"
+#include "mp3_hdr.cuh"
 #include "mp3_tables.h"
 
 namespace mp3b {
@@ -19,69 +20,15 @@ static const int kMaxFreeFormatFrame = 2304;   /* minimp3.h:49 */
 static const int kMaxSyncMatches = 10;         /* minimp3.h:50-52 */
 static const int kMaxReservoir = 511;          /* minimp3.h:56 */
 
-/* ---- header math (minimp3.h:264-314) ------------------------------------------------------- */
+/* ---- header math: shared with the GPU frame scan (mp3_hdr.cuh) ------------------------------------------------ */
 
-bool hdr_valid(const uint8_t *h)
-{
-    if (h[0] != 0xff) return false;
-    bool sync = (h[1] & 0xF0) == 0xF0 || (h[1] & 0xFE) == 0xE2;   /* MPEG-1/2, or MPEG-2.5 Layer III */
-    int layer_bits = (h[1] >> 1) & 3, bitrate = h[2] >> 4, sr = (h[2] >> 2) & 3;
-    return sync && layer_bits != 0 && bitrate != 15 && sr != 3;
-}
-
-bool hdr_compare(const uint8_t *h1, const uint8_t *h2)
-{
-    /* same version/layer/protection-insensitive id bits, same sample rate, same free-format-ness */
-    if (!hdr_valid(h2)) return false;
-    if ((h1[1] ^ h2[1]) & 0xFE) return false;
-    if ((h1[2] ^ h2[2]) & 0x0C) return false;
-    bool ff1 = (h1[2] & 0xF0) == 0, ff2 = (h2[2] & 0xF0) == 0;
-    return ff1 == ff2;
-}
-
-unsigned hdr_bitrate_kbps(const uint8_t *h)
-{
-    /* ISO 11172-3 2.4.2.3 / 13818-3 2.4.2.3 bitrate index tables, kbit/s */
-    static const uint16_t kbps_lsf[3][15] = {
-        { 0, 8, 16, 24, 32, 40, 48, 56, 64, 80, 96, 112, 128, 144, 160 },         /* layer III */
-        { 0, 8, 16, 24, 32, 40, 48, 56, 64, 80, 96, 112, 128, 144, 160 },         /* layer II  */
-        { 0, 32, 48, 56, 64, 80, 96, 112, 128, 144, 160, 176, 192, 224, 256 } };  /* layer I   */
-    static const uint16_t kbps_m1[3][15] = {
-        { 0, 32, 40, 48, 56, 64, 80, 96, 112, 128, 160, 192, 224, 256, 320 },
-        { 0, 32, 48, 56, 64, 80, 96, 112, 128, 160, 192, 224, 256, 320, 384 },
-        { 0, 32, 64, 96, 128, 160, 192, 224, 256, 288, 320, 352, 384, 416, 448 } };
-    int row = ((h[1] >> 1) & 3) - 1;  /* layer bits: 1 = III, 2 = II, 3 = I */
-    int idx = h[2] >> 4;
-    return hdr_is_mpeg1(h) ? kbps_m1[row][idx] : kbps_lsf[row][idx];
-}
-
-unsigned hdr_sample_rate_hz(const uint8_t *h)
-{
-    static const unsigned base[3] = { 44100, 48000, 32000 };
-    unsigned hz = base[(h[2] >> 2) & 3];
-    if (!hdr_is_mpeg1(h)) hz >>= 1;          /* MPEG-2 */
-    if (!(h[1] & 0x10)) hz >>= 1;            /* MPEG-2.5 */
-    return hz;
-}
-
-unsigned hdr_frame_samples(const uint8_t *h)
-{
-    if ((h[1] & 6) == 6) return 384;                  /* layer I */
-    return ((h[1] & 14) == 2) ? 576 : 1152;           /* LSF layer III : everything else */
-}
-
-int hdr_frame_bytes(const uint8_t *h, int free_format_size)
-{
-    int bytes = (int)(hdr_frame_samples(h)*hdr_bitrate_kbps(h)*125/hdr_sample_rate_hz(h));
-    if ((h[1] & 6) == 6) bytes &= ~3;                 /* layer I slots are 4 bytes */
-    return bytes ? bytes : free_format_size;
-}
-
-int hdr_padding(const uint8_t *h)
-{
-    if (!(h[2] & 0x2)) return 0;
-    return ((h[1] & 6) == 6) ? 4 : 1;
-}
+bool hdr_valid(const uint8_t *h) { return hd_valid(h); }
+bool hdr_compare(const uint8_t *h1, const uint8_t *h2) { return hd_compare(h1, h2); }
+unsigned hdr_bitrate_kbps(const uint8_t *h) { return hd_bitrate_kbps(h); }
+unsigned hdr_sample_rate_hz(const uint8_t *h) { return hd_sample_rate_hz(h); }
+unsigned hdr_frame_samples(const uint8_t *h) { return hd_frame_samples(h); }
+int hdr_frame_bytes(const uint8_t *h, int free_format_size) { return hd_frame_bytes(h, free_format_size); }
+int hdr_padding(const uint8_t *h) { return hd_padding(h); }
 
 /* ---- frame sync (behaviour of mp3d_find_frame / mp3d_match_frame, minimp3.h:1657-1706) -------------------------
  * A position is accepted as a frame start when its header is valid and the frames it implies line up: up to

@@ -85,6 +85,79 @@ struct Synth12Args
     float *state_out;
 };
 
+/* ---- GPU frame scan (k_scan.cu) ---- */
+#define SCAN_OK        0
+#define SCAN_IRREGULAR 1      /* the host walker takes the stream (resync, channel change, bad side info, short tail) */
+#define SCANF_DECODABLE 1     /* the bit reservoir holds the frame's main_data_begin bytes */
+#define SCANF_ISTEREO   2     /* stereo frame with the intensity bit set */
+#define EMIT_SLOT_SHIFT 6     /* streams own ScanFrame slots in groups of 64 */
+
+struct ScanStream              /* host -> device, one per stream handed to the scan */
+{
+    uint64_t src_off;          /* first audio frame of the stream in the raw buffer */
+    uint32_t size;             /* bytes from there to the end of the stream */
+    uint32_t slot_base;        /* first ScanFrame slot (multiple of 64) */
+    uint32_t slot_cap;         /* slots the stream may fill: size / shortest possible frame */
+    uint8_t first_hdr[4];      /* header of the first frame (found and verified by the host's frame search) */
+};
+
+struct ScanFrame               /* one frame as the scan found it */
+{
+    uint32_t pos;              /* offset of the header from src_off */
+    uint16_t frame_size;
+    uint8_t payload_off;       /* header + CRC + side info */
+    uint8_t flags;             /* SCANF_* */
+    uint16_t main_data_begin;
+    uint16_t pad;
+    uint32_t md_before;        /* main-data bytes of the stream in front of this frame's payload */
+    uint32_t dec_index;        /* decodable frames in front of this one */
+    uint32_t ist_before;       /* intensity-stereo granules in front of this one */
+};
+
+struct ScanSummary
+{
+    uint32_t n_frames, n_dec, n_ist, kbps_sum, md_len;
+    uint8_t status, nch, n_gr, pad;
+    uint32_t pad2[2];
+};
+
+struct StreamBase              /* host -> device after the prefix sums: where a stream's records go */
+{
+    uint64_t md_base, pcm_base;
+    uint32_t n_frames, n_dec;
+    uint32_t gc_base, gc_pad_before, fr_base, tile_base, ist_base;
+    uint8_t take, nch, n_gr, pad;
+};
+
+struct ScanArgs
+{
+    const uint8_t *raw;
+    const ScanStream *streams;
+    uint32_t n_streams;
+    ScanFrame *frames;
+    ScanSummary *summaries;
+};
+
+struct EmitArgs
+{
+    const uint8_t *raw;
+    const ScanStream *streams;
+    const StreamBase *bases;
+    uint32_t n_streams;
+    const uint32_t *slot_stream;   /* stream of every group of 64 slots */
+    const ScanFrame *frames;
+    uint32_t n_slots;
+    FrameRec *frame_recs;
+    uint32_t *order;
+    uint32_t *ist_list;
+    uint8_t *md;
+    TileDesc *tiles;
+    uint32_t n_tiles;
+};
+
+cudaError_t launch_stream_scan(const ScanArgs &a, cudaStream_t s);
+cudaError_t launch_stream_emit(const EmitArgs &a, cudaStream_t s);
+
 int tables_upload(DeviceTables *t);
 void tables_free(DeviceTables *t);
 

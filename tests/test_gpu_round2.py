@@ -246,3 +246,79 @@ def test_pinned_outputs_survive_internal_batch_calls(m, ref):
     for k, v in zip(keep, views):
         assert np.array_equal(k, v["pcm"])
     m.load().mp3dec_batch_release_outputs(0)
+
+
+# ---- frame sync + reservoir accounting on the GPU (k_scan.cu) ------------------------------------
+
+SCAN_REGULAR = ["l3-compl", "l3-he_32khz", "l3-he_44khz", "l3-he_48khz", "l3-hecommon", "l3-si", "l3-si_block",
+                "l3-si_huff", "l3-sin1k0db", "M2L3_bitrate_16_all", "M2L3_bitrate_22_all", "M2L3_bitrate_24_all",
+                "M2L3_compl24", "M2L3_noise", "l3-nonstandard-sin1k0db_lame_vbrtag"]
+
+
+def _call(m, datas, **kw):
+    b = m._Batch(datas, output=m.OUT_MALLOC, **kw)
+    b.call()
+    st = b.call_stats()
+    rets, outs = b.results()
+    return rets, outs, st
+
+
+@pytest.mark.parametrize("raw", [False, True])
+def test_gpu_frame_scan_is_invisible(raw, m):
+    """one batch through the GPU frame scan (forced) and through the host walker: same return codes, stream
+    parameters and PCM bytes for every stream -- regular Layer III streams (scanned), Layer I/II, free format,
+    mono/stereo switches, tags, damage, junk and empty buffers (handed back to the host walker or empty)"""
+    rng = np.random.default_rng(99)
+    names = SCAN_REGULAR + ["l3-he_free", "l3-he_mode", "l3-test45", "l1-fl1", "l2-fl10", "l3-nonstandard-id3v2",
+                            "l3-nonstandard-id3v1-apetag", "l3-nonstandard-apetag", "l3-nonstandard-vbrtag-only",
+                            "l3-nonstandard-small", "l3-nonstandard-compl-sideinfo-size", "l3-nonstandard-he_44_48khz"]
+    datas = [load_vector(n) for n in names]
+    base = load_vector("l3-sin1k0db")
+    for t in range(12):
+        b = bytearray(base)
+        if t % 3 == 0:
+            for _ in range(4):
+                b[int(rng.integers(0, len(b)))] = int(rng.integers(0, 256))
+        elif t % 3 == 1:
+            b = b[int(rng.integers(1, 3000)):int(rng.integers(60000, len(b)))]
+        else:
+            p, n = int(rng.integers(0, len(b) - 500)), int(rng.integers(1, 500))
+            del b[p:p + n]
+        datas.append(bytes(b))
+    datas += [b"", b"\xff"*777, base[:100], base + base]
+    r0, o0, s0 = _call(m, datas, raw_frames=raw, allow_mono_stereo=True, gpu_frame_scan=-1)
+    r1, o1, s1 = _call(m, datas, raw_frames=raw, allow_mono_stereo=True, gpu_frame_scan=1)
+    assert s0["scanned_streams"] == 0 and s1["scanned_streams"] >= len(SCAN_REGULAR)
+    assert r0 == r1
+    for i, (a, b) in enumerate(zip(o0, o1)):
+        assert (a["samples"], a["channels"], a["hz"], a["layer"], a["avg_bitrate_kbps"]) == \
+               (b["samples"], b["channels"], b["hz"], b["layer"], b["avg_bitrate_kbps"]), i
+        assert np.array_equal(a["pcm"], b["pcm"]), i
+
+
+@pytest.mark.parametrize("name", SCAN_REGULAR)
+def test_gpu_frame_scan_descriptors_match_host_walk(name, m):
+    """the records the scan kernels emit lead to byte-identical granule descriptors (bit offsets into the main data
+    included), the same lane-order set and the same PCM as the host walk of the stream"""
+    data = load_vector(name)
+    res = []
+    for scan in (-1, 1):
+        p = m.BatchPlan([data, data], raw_frames=True, gpu_frame_scan=scan)
+        p.run()
+        rets, outs = p.fetch()
+        res.append((np.ascontiguousarray(p.read_tap(4)), np.sort(p.read_tap(8)), outs, dict(p.stats)))
+        p.close()
+    (d0, o0, out0, st0), (d1, o1, out1, st1) = res
+    assert st0["n_frames"] == st1["n_frames"] and st0["n_tiles"] == st1["n_tiles"] and st0["samples"] == st1["samples"]
+    real = np.where(d0.view(np.uint8).reshape(len(d0), -1).any(axis=1))[0]
+    a = d0.view(np.uint8).reshape(len(d0), -1)[real].copy()
+    b = d1.view(np.uint8).reshape(len(d1), -1)[real].copy()
+    # bit offsets are relative to each route's own main-data layout: compare them relative to the stream's first
+    off0 = a[:, :8].copy().view(np.uint64).ravel()
+    off1 = b[:, :8].copy().view(np.uint64).ravel()
+    half = len(real)//2
+    assert np.array_equal(off0[:half] - off0[0], off1[:half] - off1[0])
+    assert np.array_equal(a[:, 8:], b[:, 8:])
+    assert np.array_equal(o0, o1)
+    for x, y in zip(out0, out1):
+        assert np.array_equal(x["pcm"], y["pcm"])
