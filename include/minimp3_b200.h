@@ -193,7 +193,11 @@ typedef struct
     int devices[8];                   /* devices[0 .. n_devices-1] (greedy LPT on input bytes, no collective); */
                                       /* `device` is ignored then.  Plans (mp3dec_batch_plan_*) are single-device. */
     int gpu_frame_scan;               /* frame sync + reservoir accounting on the GPU (mp3dec_decode_batch_cuda only): */
-                                      /* 0 auto (chunks of >= 64 streams), 1 always, -1 never.  Results do not depend on it. */
+                                      /* 0 auto (on when pinned_inputs is given: without it the host's staging copy */
+                                      /* dominates and the scan only adds latency), 1 always, -1 never.  Results do not depend on it. */
+    const void *pinned_inputs;        /* optional: a page-locked (cudaHostAlloc / cudaHostRegister) region that holds the */
+    size_t pinned_inputs_bytes;       /* stream buffers.  With the GPU frame scan the streams are then uploaded straight */
+                                      /* from it (no staging copy); NULL / 0: any memory, staged through the library's slab. */
 } mp3dec_batch_opts_t;
 
 /* Decodes n_streams independent buffers; per-stream result and return code (infos_out[i], rets_out[i],

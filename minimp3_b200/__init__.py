@@ -45,7 +45,7 @@ class BatchStream(C.Structure):
 class BatchOpts(C.Structure):
     _fields_ = [("device", C.c_int), ("float_output", C.c_int), ("raw_frames", C.c_int),
                 ("allow_mono_stereo_transition", C.c_int), ("host_threads", C.c_int), ("output", C.c_int),
-                ("cuda_stream", C.c_void_p), ("n_devices", C.c_int), ("devices", C.c_int*8), ("gpu_frame_scan", C.c_int)]
+                ("cuda_stream", C.c_void_p), ("n_devices", C.c_int), ("devices", C.c_int*8), ("gpu_frame_scan", C.c_int), ("pinned_inputs", C.c_void_p), ("pinned_inputs_bytes", C.c_size_t)]
 
 
 class BatchStats(C.Structure):
@@ -163,10 +163,12 @@ def _as_u8(data):
 
 
 def _opts(device=0, float_output=False, raw_frames=False, allow_mono_stereo=False, host_threads=0, output=OUT_PINNED,
-          cuda_stream=None, devices=None, gpu_frame_scan=0):
+          cuda_stream=None, devices=None, gpu_frame_scan=0, pinned_inputs=None):
     o = BatchOpts(int(device), int(bool(float_output)), int(bool(raw_frames)), int(bool(allow_mono_stereo)),
                   int(host_threads), int(output), C.c_void_p(cuda_stream) if cuda_stream else None)
     o.gpu_frame_scan = int(gpu_frame_scan)
+    if pinned_inputs is not None:       # (address, bytes) of a page-locked region holding the stream buffers
+        o.pinned_inputs, o.pinned_inputs_bytes = C.c_void_p(int(pinned_inputs[0])), int(pinned_inputs[1])
     if devices:
         o.n_devices = len(devices)
         for i, d in enumerate(devices[:8]):

@@ -294,6 +294,7 @@ struct mp3dec_batch_plan
     size_t sample_size = 2;
     bool taps = false;
     cudaEvent_t ev_kernels = nullptr, ev_d2h = nullptr, ev_h2d = nullptr;
+    cudaStream_t scan_stream = nullptr;   /* GPU frame scan route: upload + scan + record kernels of this plan */
     std::vector<int> out_index;    /* stream i of the plan is stream out_index[i] of the caller (empty: identity) */
     bool export_on_destroy = false; /* one-call entry point with pinned / device output: the caller holds pointers into bufs */
     bool order_sorted = false;     /* the entropy kernel reads d_order_sorted (order across streams, k_order.cu) */
@@ -599,8 +600,38 @@ static mp3dec_batch_plan_t *plan_create_impl(const mp3dec_batch_stream_t *stream
  * accounting, payload concatenation, frame records, tiles -- runs on the device.  Streams the scan cannot take
  * (Layer I/II, free format, anything irregular: see k_scan.cu) are returned in *rest for the host walker.  The plan
  * covers the streams it took plus the ones with nothing to decode. */
-static mp3dec_batch_plan_t *plan_create_scan(const mp3dec_batch_stream_t *streams, int n_streams, const mp3dec_batch_opts_t *opts_in,
-                                             int *err, std::vector<int> *rest)
+struct ScanHead
+{
+    const uint8_t *p = nullptr;    /* first audio frame */
+    size_t size = 0;
+    StreamHead h;
+    int kind = 0;                  /* 0 nothing to decode, 1 scan candidate, 2 host walker */
+    uint32_t slot_cap = 0;
+};
+
+/* a scan in flight: everything up to the scan kernel is queued, the summaries are on their way back */
+struct ScanJob
+{
+    mp3dec_batch_plan *P = nullptr;
+    mp3dec_batch_opts_t opts;
+    int n_streams = 0, nc = 0;
+    std::vector<ScanHead> heads;
+    std::vector<int> cand, rest;
+    uint64_t raw_bytes = 0, n_slots = 0;
+    cudaStream_t up = nullptr;
+    cudaEvent_t ev_sum = nullptr;
+    double t0 = 0, t_heads = 0, t_issue = 0;
+};
+
+static void scan_job_free(ScanJob *J)
+{
+    if (!J) return;
+    if (J->ev_sum) cudaEventDestroy(J->ev_sum);
+    delete J;
+}
+
+/* first half: stream heads on the host, staging copy, upload, scan kernel, summaries on their way back (asynchronous) */
+static ScanJob *scan_begin(const mp3dec_batch_stream_t *streams, int n_streams, const mp3dec_batch_opts_t *opts_in, int *err)
 {
     *err = 0;
     mp3dec_batch_opts_t opts;
@@ -611,17 +642,15 @@ static mp3dec_batch_plan_t *plan_create_scan(const mp3dec_batch_stream_t *stream
     cudaSetDevice(ctx->device);
     const double t0 = now_ms();
 
-    struct Head
-    {
-        const uint8_t *p = nullptr;
-        size_t size = 0;
-        StreamHead h;
-        int kind = 0;              /* 0 nothing to decode, 1 scan candidate, 2 host walker */
-        uint32_t slot_cap = 0;
-    };
-    std::vector<Head> heads(n_streams);
+    ScanJob *J = new ScanJob();
+    J->opts = opts;
+    J->n_streams = n_streams;
+    J->t0 = t0;
+    J->heads.resize(n_streams);
+    std::vector<ScanHead> &heads = J->heads;
+    std::vector<int> *rest = &J->rest;
     parallel_for(n_streams, opts.host_threads, [&](int i) {
-        Head &H = heads[i];
+        ScanHead &H = heads[i];
         const uint8_t *buf = streams[i].buf;
         size_t size = streams[i].size;
         if (size >= (1u << 31)) { H.kind = 2; return; }
@@ -645,8 +674,9 @@ static mp3dec_batch_plan_t *plan_create_scan(const mp3dec_batch_stream_t *stream
         H.slot_cap = (uint32_t)(size/(size_t)min_fs) + 2;
         H.kind = 1;
     });
+    J->t_heads = now_ms();
     /* candidates: staging offsets and slot groups */
-    std::vector<int> cand;
+    std::vector<int> &cand = J->cand;
     std::vector<uint64_t> raw_base;
     uint64_t raw_bytes = 0, n_slots = 0;
     for (int i = 0; i < n_streams; i++)
@@ -656,10 +686,33 @@ static mp3dec_batch_plan_t *plan_create_scan(const mp3dec_batch_stream_t *stream
         cand.push_back(i);
         raw_base.push_back(raw_bytes);
         raw_bytes += round_up(heads[i].size + 16, 16);
-        n_slots += round_up(heads[i].slot_cap, 1u << EMIT_SLOT_SHIFT);
+        n_slots += heads[i].slot_cap;
     }
     const int nc = (int)cand.size();
-    if (n_slots >= (1ull << 31)) { *err = MP3D_E_PARAM; return nullptr; }
+    /* direct upload: every candidate inside the caller's page-locked region, and the span they cover not much
+     * larger than their bytes (it is uploaded whole, gaps included) */
+    bool direct = false;
+    const uint8_t *slab_lo = nullptr;
+    if (nc && opts.pinned_inputs && opts.pinned_inputs_bytes)
+    {
+        const uint8_t *lo = heads[cand[0]].p, *hi = lo;
+        uint64_t sum = 0;
+        for (int k : cand)
+        {
+            lo = std::min(lo, heads[k].p);
+            hi = std::max(hi, heads[k].p + heads[k].size);
+            sum += heads[k].size;
+        }
+        const uint8_t *r0 = (const uint8_t *)opts.pinned_inputs, *r1 = r0 + opts.pinned_inputs_bytes;
+        if (lo >= r0 && hi <= r1 && (uint64_t)(hi - lo) <= sum + sum/4 + 65536)
+        {
+            direct = true;
+            slab_lo = lo;
+            raw_bytes = (uint64_t)(hi - lo);
+        }
+    }
+    J->nc = nc; J->raw_bytes = raw_bytes; J->n_slots = n_slots;
+    if (n_slots >= (1ull << 31)) { *err = MP3D_E_PARAM; scan_job_free(J); return nullptr; }
 
     mp3dec_batch_plan *P = new mp3dec_batch_plan();
     P->ctx = ctx;
@@ -668,40 +721,50 @@ static mp3dec_batch_plan_t *plan_create_scan(const mp3dec_batch_stream_t *stream
     P->sample_size = opts.float_output ? 4 : 2;
     P->bufs = acquire_set(ctx);
     BufferSet &B = *P->bufs;
-    cudaStream_t up = opts.cuda_stream ? P->stream : ctx->stream_h2d;
-    std::vector<ScanSummary> sums(nc);
+    J->P = P;
+    /* the scans of a call's chunks must not queue up behind each other (each walks its streams frame by frame at
+     * memory latency): every scan plan brings its own stream for the upload, the scan and the record kernels */
+    if (opts.cuda_stream) P->scan_stream = nullptr;
+    else if (cudaStreamCreateWithFlags(&P->scan_stream, cudaStreamNonBlocking) != cudaSuccess) P->scan_stream = nullptr;
+    cudaStream_t up = P->scan_stream ? P->scan_stream : P->stream;
+    J->up = up;
+    J->t_issue = now_ms();
     if (nc)
     {
-        const size_t n_groups = (size_t)(n_slots >> EMIT_SLOT_SHIFT);
-        bool ok = B.h_md.ensure(raw_bytes + 64) && B.d_raw.ensure(raw_bytes + 64) && B.h_scan.ensure((size_t)nc*sizeof(ScanStream)) &&
-                  B.d_scan.ensure((size_t)nc*sizeof(ScanStream)) && B.h_slotmap.ensure(n_groups*4 + 64) && B.d_slotmap.ensure(n_groups*4 + 64) &&
+        bool ok = (direct || B.h_md.ensure(raw_bytes + 64)) && B.d_raw.ensure(raw_bytes + 64) && B.h_scan.ensure((size_t)nc*sizeof(ScanStream)) &&
+                  B.d_scan.ensure((size_t)nc*sizeof(ScanStream)) &&
                   B.d_scan_frames.ensure((size_t)n_slots*sizeof(ScanFrame) + 64) && B.h_sum.ensure((size_t)nc*sizeof(ScanSummary)) &&
                   B.d_sum.ensure((size_t)nc*sizeof(ScanSummary));
-        if (!ok) { *err = MP3D_E_MEMORY; mp3dec_batch_plan_destroy(P); return nullptr; }
+        if (!ok) { *err = MP3D_E_MEMORY; mp3dec_batch_plan_destroy(P); scan_job_free(J); return nullptr; }
         ScanStream *hs = (ScanStream *)B.h_scan.p;
-        uint32_t *slotmap = (uint32_t *)B.h_slotmap.p;
         uint32_t slot = 0;
         for (int k = 0; k < nc; k++)
         {
-            const Head &H = heads[cand[k]];
+            const ScanHead &H = heads[cand[k]];
             hs[k].src_off = raw_base[k];
             hs[k].size = (uint32_t)H.size;
             hs[k].slot_base = slot;
             hs[k].slot_cap = H.slot_cap;
             memcpy(hs[k].first_hdr, H.p, 4);
-            const uint32_t groups = (uint32_t)(round_up(H.slot_cap, 1u << EMIT_SLOT_SHIFT) >> EMIT_SLOT_SHIFT);
-            for (uint32_t g = 0; g < groups; g++) slotmap[(slot >> EMIT_SLOT_SHIFT) + g] = (uint32_t)k;
-            slot += groups << EMIT_SLOT_SHIFT;
+            slot += H.slot_cap;
         }
-        uint8_t *h_raw = (uint8_t *)B.h_md.p;
-        parallel_for(nc, opts.host_threads, [&](int k) {
-            const Head &H = heads[cand[k]];
-            memcpy(h_raw + raw_base[k], H.p, H.size);
-            memset(h_raw + raw_base[k] + H.size, 0, (size_t)(round_up(H.size + 16, 16) - H.size));
-        });
-        cudaMemcpyAsync(B.d_raw.p, h_raw, raw_bytes, cudaMemcpyHostToDevice, up);
+        if (direct)
+        {
+            /* the caller vouches that the stream buffers sit in page-locked memory (opts.pinned_inputs): the DMA
+             * engine reads them where they are, the host touches nothing but the stream heads */
+            for (int k = 0; k < nc; k++) hs[k].src_off = (uint64_t)(heads[cand[k]].p - slab_lo);
+            cudaMemcpyAsync(B.d_raw.p, slab_lo, raw_bytes, cudaMemcpyHostToDevice, up);
+        } else
+        {
+            uint8_t *h_raw = (uint8_t *)B.h_md.p;
+            parallel_for(nc, opts.host_threads, [&](int k) {
+                const ScanHead &H = heads[cand[k]];
+                memcpy(h_raw + raw_base[k], H.p, H.size);
+                memset(h_raw + raw_base[k] + H.size, 0, (size_t)(round_up(H.size + 16, 16) - H.size));
+            });
+            cudaMemcpyAsync(B.d_raw.p, h_raw, raw_bytes, cudaMemcpyHostToDevice, up);
+        }
         cudaMemcpyAsync(B.d_scan.p, hs, (size_t)nc*sizeof(ScanStream), cudaMemcpyHostToDevice, up);
-        cudaMemcpyAsync(B.d_slotmap.p, slotmap, n_groups*4, cudaMemcpyHostToDevice, up);
         ScanArgs sa;
         sa.raw = (const uint8_t *)B.d_raw.p;
         sa.streams = (const ScanStream *)B.d_scan.p;
@@ -710,15 +773,62 @@ static mp3dec_batch_plan_t *plan_create_scan(const mp3dec_batch_stream_t *stream
         sa.summaries = (ScanSummary *)B.d_sum.p;
         cudaError_t e = launch_stream_scan(sa, up);
         cudaMemcpyAsync(B.h_sum.p, B.d_sum.p, (size_t)nc*sizeof(ScanSummary), cudaMemcpyDeviceToHost, up);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(up);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&J->ev_sum, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventRecord(J->ev_sum, up);
         if (e != cudaSuccess)
         {
             fprintf(stderr, "minimp3_b200: frame scan failed: %s\n", cudaGetErrorString(e));
             *err = MP3D_E_CUDA;
             mp3dec_batch_plan_destroy(P);
+            scan_job_free(J);
+            return nullptr;
+        }
+    }
+    J->t_issue = now_ms();
+    return J;
+}
+
+/* second half: summaries in hand -> where every stream's records go, the record kernels, side info, lane order.
+ * Streams the scan handed back are appended to *rest (indices into the job's streams). */
+static mp3dec_batch_plan_t *scan_finish(ScanJob *J, int *err, std::vector<int> *rest)
+{
+    *err = 0;
+    mp3dec_batch_plan *P = J->P;
+    const mp3dec_batch_opts_t opts = J->opts;
+    DeviceCtx *ctx = P->ctx;
+    cudaSetDevice(ctx->device);
+    BufferSet &B = *P->bufs;
+    const int n_streams = J->n_streams, nc = J->nc;
+    const std::vector<ScanHead> &heads = J->heads;
+    const std::vector<int> &cand = J->cand;
+    const uint64_t raw_bytes = J->raw_bytes, n_slots = J->n_slots;
+    cudaStream_t up = J->up;
+    const double t0 = J->t0, t_heads = J->t_heads, t_issue = J->t_issue;
+    *rest = J->rest;
+    std::vector<ScanSummary> sums(nc);
+    const double t_wait0 = now_ms();
+    if (nc)
+    {
+        const cudaError_t e = cudaEventSynchronize(J->ev_sum);
+        if (e != cudaSuccess)
+        {
+            fprintf(stderr, "minimp3_b200: frame scan failed: %s\n", cudaGetErrorString(e));
+            *err = MP3D_E_CUDA;
+            mp3dec_batch_plan_destroy(P);
+            scan_job_free(J);
             return nullptr;
         }
         memcpy(sums.data(), B.h_sum.p, (size_t)nc*sizeof(ScanSummary));
+        /* streams that end in a cut frame or a little junk: the reference restarts its frame search on those last
+         * bytes; so do we, with the same search.  Nothing found (the rule): the stream simply ends there. */
+        parallel_for(nc, opts.host_threads, [&](int k) {
+            ScanSummary &S = sums[k];
+            if (S.status != SCAN_TAIL) return;
+            const ScanHead &H = heads[cand[k]];
+            int free_format_bytes = 0, frame_size = 0;
+            find_frame(H.p + S.tail_pos, (int)(H.size - S.tail_pos), &free_format_bytes, &frame_size);
+            S.status = frame_size ? SCAN_IRREGULAR : SCAN_OK;
+        });
     }
     const double t_scan = now_ms();
 
@@ -742,7 +852,7 @@ static mp3dec_batch_plan_t *plan_create_scan(const mp3dec_batch_stream_t *stream
     P->pcm_base.assign(np + 1, 0);
     P->gc_base.assign(np + 1, 0);
     if (!B.h_bases.ensure((size_t)std::max(nc, 1)*sizeof(StreamBase)) || !B.d_bases.ensure((size_t)std::max(nc, 1)*sizeof(StreamBase)))
-    { *err = MP3D_E_MEMORY; mp3dec_batch_plan_destroy(P); return nullptr; }
+    { *err = MP3D_E_MEMORY; mp3dec_batch_plan_destroy(P); scan_job_free(J); return nullptr; }
     StreamBase *hb = (StreamBase *)B.h_bases.p;
     for (int k = 0; k < nc; k++) { memset(&hb[k], 0, sizeof(StreamBase)); }
     uint64_t gcs = 0, frs = 0, tiles = 0, samples = 0, ists = 0, orders = 0, md = 0, pads = 0;
@@ -753,7 +863,7 @@ static mp3dec_batch_plan_t *plan_create_scan(const mp3dec_batch_stream_t *stream
         P->gc_base[j] = gcs;
         const int k = cand_of[j];
         if (k < 0) continue;
-        const Head &H = heads[P->out_index[j]];
+        const ScanHead &H = heads[P->out_index[j]];
         const ScanSummary &S = sums[k];
         StreamPlan &sp = P->plans[j];
         const uint64_t per_frame = (uint64_t)hd_frame_samples(H.p)*S.nch;
@@ -792,20 +902,27 @@ static mp3dec_batch_plan_t *plan_create_scan(const mp3dec_batch_stream_t *stream
         P->n_frames += S.n_dec;
         P->input_bytes += S.md_len;
     }
-    /* streams that were dropped keep a tile_base so that k_stream_tiles' search stays monotonic */
+    /* the kernels find a frame's / a tile's stream by binary search over these bases: streams that were dropped take
+     * the base of the next taken one (they own nothing), so that the arrays stay monotonic */
+    uint64_t scan_frames = 0;
+    for (int k = 0; k < nc; k++)
     {
-        uint32_t tb = (uint32_t)tiles;
+        hb[k].frame_base = (uint32_t)scan_frames;
+        if (hb[k].take) scan_frames += hb[k].n_frames;
+    }
+    {
+        uint32_t tb = (uint32_t)tiles, fb = (uint32_t)scan_frames;
         for (int k = nc - 1; k >= 0; k--)
         {
-            if (hb[k].take) tb = hb[k].tile_base;
-            else hb[k].tile_base = tb;
+            if (hb[k].take) { tb = hb[k].tile_base; fb = hb[k].frame_base; }
+            else { hb[k].tile_base = tb; hb[k].frame_base = fb; }
         }
     }
     P->pcm_base[np] = samples;
     P->gc_base[np] = gcs;
     P->md_bytes = md + 4096;
     P->n_gc = gcs; P->n_tiles = tiles; P->n_samples = samples; P->n_ist = ists; P->n_order = orders;
-    if (gcs >= (1ull << 31)) { *err = MP3D_E_PARAM; mp3dec_batch_plan_destroy(P); return nullptr; }
+    if (gcs >= (1ull << 31)) { *err = MP3D_E_PARAM; mp3dec_batch_plan_destroy(P); scan_job_free(J); return nullptr; }
 
     const bool sort_order = frs && orders >= kMinOrderSort && np >= 2;
     const size_t order_scratch = sort_order ? order_sort_scratch_bytes((uint32_t)orders, (uint32_t)np) : 0;
@@ -817,7 +934,7 @@ static mp3dec_batch_plan_t *plan_create_scan(const mp3dec_batch_stream_t *stream
                                B.h_gcbase.ensure(((size_t)np + 1)*4 + 64) && B.d_gcbase.ensure(((size_t)np + 1)*4 + 64))) &&
               B.d_xr.ensure((size_t)gcs*576*sizeof(float) + 64) && B.d_nzl.ensure((size_t)gcs*2 + 64) &&
               B.d_istpos.ensure((size_t)gcs*40 + 64) && B.d_pcm.ensure((size_t)samples*P->sample_size + 64);
-    if (!ok) { *err = MP3D_E_MEMORY; mp3dec_batch_plan_destroy(P); return nullptr; }
+    if (!ok) { *err = MP3D_E_MEMORY; mp3dec_batch_plan_destroy(P); scan_job_free(J); return nullptr; }
     if (nc) cudaMemcpyAsync(B.d_bases.p, hb, (size_t)nc*sizeof(StreamBase), cudaMemcpyHostToDevice, up);
     if (sort_order)
     {
@@ -834,16 +951,15 @@ static mp3dec_batch_plan_t *plan_create_scan(const mp3dec_batch_stream_t *stream
         ea.streams = (const ScanStream *)B.d_scan.p;
         ea.bases = (const StreamBase *)B.d_bases.p;
         ea.n_streams = (uint32_t)nc;
-        ea.slot_stream = (const uint32_t *)B.d_slotmap.p;
         ea.frames = (const ScanFrame *)B.d_scan_frames.p;
-        ea.n_slots = (uint32_t)n_slots;
+        ea.n_frames = (uint32_t)scan_frames;
         ea.frame_recs = (FrameRec *)B.d_frames.p;
         ea.order = (uint32_t *)B.d_order.p;
         ea.ist_list = (uint32_t *)B.d_istlist.p;
         ea.md = (uint8_t *)B.d_md.p;
         ea.tiles = (TileDesc *)B.d_tiles.p;
         ea.n_tiles = (uint32_t)tiles;
-        if (launch_stream_emit(ea, up) != cudaSuccess) { *err = MP3D_E_CUDA; mp3dec_batch_plan_destroy(P); return nullptr; }
+        if (launch_stream_emit(ea, up) != cudaSuccess) { *err = MP3D_E_CUDA; mp3dec_batch_plan_destroy(P); scan_job_free(J); return nullptr; }
     }
     if (up != P->stream)
     {
@@ -852,19 +968,31 @@ static mp3dec_batch_plan_t *plan_create_scan(const mp3dec_batch_stream_t *stream
         cudaStreamWaitEvent(P->stream, P->ev_h2d, 0);
     }
     P->sort_order = sort_order; P->order_scratch = order_scratch; P->max_slots = max_slots; P->n_frame_recs = frs;
-    if (plan_prep(P) != 0) { *err = MP3D_E_CUDA; mp3dec_batch_plan_destroy(P); return nullptr; }
+    if (plan_prep(P) != 0) { *err = MP3D_E_CUDA; mp3dec_batch_plan_destroy(P); scan_job_free(J); return nullptr; }
     P->stats.input_bytes = P->input_bytes;
     P->stats.samples = samples;
     P->stats.n_granule_channels = gcs;
     P->stats.n_tiles = tiles;
     P->stats.n_istereo_granules = ists;
     P->stats.n_frames = P->n_frames;
-    P->stats.h2d_bytes = raw_bytes + (uint64_t)nc*(sizeof(ScanStream) + sizeof(StreamBase)) + (n_slots >> EMIT_SLOT_SHIFT)*4;
+    P->stats.h2d_bytes = raw_bytes + (uint64_t)nc*(sizeof(ScanStream) + sizeof(StreamBase));
     P->stats.kernels_per_run = (orders ? 1 : 0) + (ists ? 1 : 0) + (tiles ? 2 : 0);
     P->stats.kernels_prep = (nc ? 4 : 0) + (frs ? 1 : 0) + (sort_order ? 2 : 0);
-    P->stats.host_parse_ms = (t_scan - t0) + (now_ms() - t_scan);
+    P->stats.host_parse_ms = (t_issue - t0) + (now_ms() - t_scan);     /* host work; the wait for the scan is not */
     P->stats.h2d_ms = 0;
+    static const bool dbg = getenv("MP3B_DEBUG_TIMING") != nullptr;
+    if (dbg) fprintf(stderr, "  scan plan: %d streams (%d candidates, %d taken+empty), heads %.3f ms, staging+issue %.3f ms, scan wait %.3f ms, records %.3f ms\n",
+                     n_streams, nc, np, t_heads - t0, t_issue - t_heads, t_scan - t_wait0, now_ms() - t_scan);
+    scan_job_free(J);
     return P;
+}
+
+/* both halves in a row (plans, single chunks) */
+static mp3dec_batch_plan_t *plan_create_scan(const mp3dec_batch_stream_t *streams, int n_streams, const mp3dec_batch_opts_t *opts_in,
+                                             int *err, std::vector<int> *rest)
+{
+    ScanJob *J = scan_begin(streams, n_streams, opts_in, err);
+    return J ? scan_finish(J, err, rest) : nullptr;
 }
 
 int mp3dec_batch_plan_enable_taps(mp3dec_batch_plan_t *P)
@@ -1105,6 +1233,7 @@ void mp3dec_batch_plan_destroy(mp3dec_batch_plan_t *P)
     if (P->ev_kernels) cudaEventDestroy(P->ev_kernels);
     if (P->ev_d2h) cudaEventDestroy(P->ev_d2h);
     if (P->ev_h2d) cudaEventDestroy(P->ev_h2d);
+    if (P->scan_stream) cudaStreamDestroy(P->scan_stream);
     if (P->bufs)
     {
         if (P->export_on_destroy)
@@ -1147,7 +1276,19 @@ static int decode_batch_multi(const mp3dec_batch_stream_t *streams, int n_stream
     std::vector<size_t> sizes(n_streams);
     for (int i = 0; i < n_streams; i++) sizes[i] = streams[i].size;
     std::vector<int> shard_of(n_streams);
-    mp3dec_batch_shard(sizes.data(), n_streams, nd, shard_of.data());
+    if (opts->pinned_inputs && opts->pinned_inputs_bytes)
+    {
+        /* streams in a caller-pinned slab are uploaded where they are, as one span per chunk: give every device a
+         * contiguous run of streams (equal bytes) instead of the LPT scatter */
+        uint64_t total = 0, acc = 0;
+        for (int i = 0; i < n_streams; i++) total += sizes[i];
+        for (int i = 0; i < n_streams; i++)
+        {
+            shard_of[i] = (int)std::min<uint64_t>((uint64_t)nd - 1, total ? (acc + sizes[i]/2)*(uint64_t)nd/total : 0);
+            acc += sizes[i];
+        }
+    } else
+        mp3dec_batch_shard(sizes.data(), n_streams, nd, shard_of.data());
     std::vector<std::vector<int>> ids(nd);
     for (int i = 0; i < n_streams; i++) ids[shard_of[i]].push_back(i);
     /* one pool per device slot, each with an equal share of the cores; created on first use, kept */
@@ -1229,9 +1370,9 @@ int mp3dec_decode_batch_cuda(const mp3dec_batch_stream_t *streams, int n_streams
         n_chunks = std::min(n_chunks, n_streams/32);
         if (n_chunks < 1) n_chunks = 1;
     }
-    /* frame sync on the GPU (k_scan.cu) for chunks with enough streams to keep it busy: per-frame host work drops to
-     * one staging copy; streams the scan hands back (Layer I/II, free format, anything irregular) go through the host
-     * walker in a second plan of the same chunk.  opts.gpu_frame_scan: 0 auto, 1 always, -1 never. */
+    /* frame sync on the GPU (k_scan.cu): per-frame host work disappears; streams the scan hands back (Layer I/II, free
+     * format, anything irregular) go through the host walker in a second plan of the same chunk.
+     * opts.gpu_frame_scan: 0 auto (see below), 1 always, -1 never. */
     static const int scan_env = [] { const char *e = getenv("MP3B_GPU_SCAN"); return e ? atoi(e) : 0; }();
     const int scan_mode = scan_env ? scan_env : (opts ? opts->gpu_frame_scan : 0);
     struct Part { mp3dec_batch_plan_t *plan; int first; };
@@ -1262,15 +1403,28 @@ int mp3dec_decode_batch_cuda(const mp3dec_batch_stream_t *streams, int n_streams
         if (!e) e = plan_begin_fetch(P, P->ctx->stream_d2h);
         return e;
     };
+    /* all scans of the call are started first: each walks its streams frame by frame at memory latency (~1 ms), and
+     * they overlap each other, the uploads of the later chunks and the decode kernels of the earlier ones */
+    std::vector<ScanJob *> jobs(n_chunks, nullptr);
+    for (int c = 0; c < n_chunks && !err; c++)
+    {
+        const int n_c = first[c + 1] - first[c];
+        /* auto: only where it pays.  With pageable inputs the host has to copy every byte into the staging slab either
+         * way -- that copy, not the frame walk, is what the host stage costs (measured: 4.2 ms of 4.5 ms on config 2) --
+         * and the scan only adds its latency; with inputs the caller pinned (opts.pinned_inputs) the copy disappears
+         * and the host is left with the stream heads. */
+        const bool pays = opts && opts->pinned_inputs && opts->pinned_inputs_bytes && n_c >= 64;
+        if (scan_mode > 0 || (scan_mode == 0 && pays)) jobs[c] = scan_begin(streams + first[c], n_c, opts, &err);
+    }
     for (int c = 0; c < n_chunks && !err; c++)
     {
         const double a0 = now_ms();
         const int n_c = first[c + 1] - first[c];
-        const bool scan = scan_mode > 0 || (scan_mode == 0 && n_c >= 64);
-        if (scan)
+        if (jobs[c])
         {
             std::vector<int> rest;
-            mp3dec_batch_plan_t *P = plan_create_scan(streams + first[c], n_c, opts, &err, &rest);
+            mp3dec_batch_plan_t *P = scan_finish(jobs[c], &err, &rest);
+            jobs[c] = nullptr;
             if (!P) break;
             cs.scanned_streams += n_c - (int)rest.size();
             err = launch(P, first[c]);
@@ -1291,6 +1445,13 @@ int mp3dec_decode_batch_cuda(const mp3dec_batch_stream_t *streams, int n_streams
         }
         if (dbg_timing) fprintf(stderr, "chunk %d: %d streams, issued in %.3f ms, t=%.3f\n", c, n_c, now_ms() - a0, now_ms() - tt0);
     }
+    for (ScanJob *J : jobs)
+        if (J)
+        {   /* an error ended the call early: let the queued work drain, drop the rest */
+            cudaStreamSynchronize(J->up);
+            mp3dec_batch_plan_destroy(J->P);
+            scan_job_free(J);
+        }
     const double tt1 = now_ms();
     for (Part &pt : parts)
     {

@@ -87,16 +87,17 @@ struct Synth12Args
 
 /* ---- GPU frame scan (k_scan.cu) ---- */
 #define SCAN_OK        0
-#define SCAN_IRREGULAR 1      /* the host walker takes the stream (resync, channel change, bad side info, short tail) */
+#define SCAN_IRREGULAR 1      /* the host walker takes the stream (resync, channel change, bad side info) */
+#define SCAN_TAIL      2      /* regular up to tail_pos; what follows is too short for a frame or not a frame (<= SCAN_TAIL_MAX bytes) */
+#define SCAN_TAIL_MAX  16384u
 #define SCANF_DECODABLE 1     /* the bit reservoir holds the frame's main_data_begin bytes */
 #define SCANF_ISTEREO   2     /* stereo frame with the intensity bit set */
-#define EMIT_SLOT_SHIFT 6     /* streams own ScanFrame slots in groups of 64 */
 
 struct ScanStream              /* host -> device, one per stream handed to the scan */
 {
     uint64_t src_off;          /* first audio frame of the stream in the raw buffer */
     uint32_t size;             /* bytes from there to the end of the stream */
-    uint32_t slot_base;        /* first ScanFrame slot (multiple of 64) */
+    uint32_t slot_base;        /* first ScanFrame slot */
     uint32_t slot_cap;         /* slots the stream may fill: size / shortest possible frame */
     uint8_t first_hdr[4];      /* header of the first frame (found and verified by the host's frame search) */
 };
@@ -118,7 +119,8 @@ struct ScanSummary
 {
     uint32_t n_frames, n_dec, n_ist, kbps_sum, md_len;
     uint8_t status, nch, n_gr, pad;
-    uint32_t pad2[2];
+    uint32_t tail_pos;         /* where the scan stopped (offset from the first audio frame) */
+    uint32_t pad2;
 };
 
 struct StreamBase              /* host -> device after the prefix sums: where a stream's records go */
@@ -126,6 +128,7 @@ struct StreamBase              /* host -> device after the prefix sums: where a 
     uint64_t md_base, pcm_base;
     uint32_t n_frames, n_dec;
     uint32_t gc_base, gc_pad_before, fr_base, tile_base, ist_base;
+    uint32_t frame_base;       /* frames (decodable or not) of the taken streams in front of this one; monotonic over all streams */
     uint8_t take, nch, n_gr, pad;
 };
 
@@ -144,9 +147,8 @@ struct EmitArgs
     const ScanStream *streams;
     const StreamBase *bases;
     uint32_t n_streams;
-    const uint32_t *slot_stream;   /* stream of every group of 64 slots */
     const ScanFrame *frames;
-    uint32_t n_slots;
+    uint32_t n_frames;             /* frames of all taken streams */
     FrameRec *frame_recs;
     uint32_t *order;
     uint32_t *ist_list;

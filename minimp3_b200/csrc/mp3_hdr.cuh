@@ -40,18 +40,28 @@ MP3H_HD bool hd_compare(const uint8_t *h1, const uint8_t *h2)
 }
 
 /* ISO 11172-3 / 13818-3 2.4.2.3 bitrate index tables in kbit/s, halved to fit a byte; row = 3 x (MPEG-1) + layer
- * bits - 1 (layer bits: 1 = III, 2 = II, 3 = I) */
+ * bits - 1 (layer bits: 1 = III, 2 = II, 3 = I).  One copy per address space: a table inside the function would be
+ * rebuilt on the stack by every device call. */
+#define MP3H_HALF_KBPS { \
+        { 0, 4, 8, 12, 16, 20, 24, 28, 32, 40, 48, 56, 64, 72, 80 },              /* LSF layer III */ \
+        { 0, 4, 8, 12, 16, 20, 24, 28, 32, 40, 48, 56, 64, 72, 80 },              /* LSF layer II  */ \
+        { 0, 16, 24, 28, 32, 40, 48, 56, 64, 72, 80, 88, 96, 112, 128 },          /* LSF layer I   */ \
+        { 0, 16, 20, 24, 28, 32, 40, 48, 56, 64, 80, 96, 112, 128, 160 },         /* MPEG-1 layer III */ \
+        { 0, 16, 24, 28, 32, 40, 48, 56, 64, 80, 96, 112, 128, 160, 192 },        /* MPEG-1 layer II  */ \
+        { 0, 16, 32, 48, 64, 80, 96, 112, 128, 144, 160, 176, 192, 208, 224 } }   /* MPEG-1 layer I   */
+static const uint8_t k_half_kbps_host[6][15] = MP3H_HALF_KBPS;
+#if defined(__CUDACC__)
+static __device__ const uint8_t k_half_kbps_dev[6][15] = MP3H_HALF_KBPS;
+#endif
+
 MP3H_HD unsigned hd_bitrate_kbps(const uint8_t *h)
 {
-    const uint8_t half_kbps[6][15] = {
-        { 0, 4, 8, 12, 16, 20, 24, 28, 32, 40, 48, 56, 64, 72, 80 },              /* LSF layer III */
-        { 0, 4, 8, 12, 16, 20, 24, 28, 32, 40, 48, 56, 64, 72, 80 },              /* LSF layer II  */
-        { 0, 16, 24, 28, 32, 40, 48, 56, 64, 72, 80, 88, 96, 112, 128 },          /* LSF layer I   */
-        { 0, 16, 20, 24, 28, 32, 40, 48, 56, 64, 80, 96, 112, 128, 160 },         /* MPEG-1 layer III */
-        { 0, 16, 24, 28, 32, 40, 48, 56, 64, 80, 96, 112, 128, 160, 192 },        /* MPEG-1 layer II  */
-        { 0, 16, 32, 48, 64, 80, 96, 112, 128, 144, 160, 176, 192, 208, 224 } };  /* MPEG-1 layer I   */
     const int row = (hd_is_mpeg1(h) ? 3 : 0) + ((h[1] >> 1) & 3) - 1;
-    return 2u*half_kbps[row][h[2] >> 4];
+#if defined(__CUDA_ARCH__)
+    return 2u*k_half_kbps_dev[row][h[2] >> 4];
+#else
+    return 2u*k_half_kbps_host[row][h[2] >> 4];
+#endif
 }
 
 MP3H_HD unsigned hd_sample_rate_hz(const uint8_t *h)

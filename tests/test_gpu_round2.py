@@ -322,3 +322,19 @@ def test_gpu_frame_scan_descriptors_match_host_walk(name, m):
     assert np.array_equal(o0, o1)
     for x, y in zip(out0, out1):
         assert np.array_equal(x["pcm"], y["pcm"])
+
+
+def test_pinned_input_slab_uploads_directly_same_results(m):
+    """opts.pinned_inputs: streams that sit in one page-locked region are uploaded from where they are (no staging
+    copy) by the scan route; same bytes out as the ordinary call"""
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    from e2e_probe import pinned_slab
+    names = SCAN_REGULAR + ["l3-he_free", "l1-fl1", "l3-he_mode", "l3-nonstandard-id3v2"]
+    datas = [load_vector(n) for n in names]*5
+    views, slab, keep = pinned_slab(datas)
+    r0, o0, s0 = _call(m, datas, allow_mono_stereo=True, gpu_frame_scan=-1)
+    r1, o1, s1 = _call(m, views, allow_mono_stereo=True, gpu_frame_scan=1, pinned_inputs=slab)
+    assert r0 == r1 and s1["scanned_streams"] >= 5*len(SCAN_REGULAR)
+    for a, b in zip(o0, o1):
+        assert a["samples"] == b["samples"] and np.array_equal(a["pcm"], b["pcm"])
