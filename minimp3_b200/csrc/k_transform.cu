@@ -43,14 +43,17 @@ constexpr int GT = MP3B_TILE_GRANULES;
 constexpr int kThreads = 256;
 constexpr int kSlots = (GT + 2)*2;          /* granule-channel slots incl. two halo granules per channel */
 constexpr int kXPitch = 18;                 /* rows sit in shared memory exactly as in HBM (bulk copies) */
-constexpr int kXSlot = 576;
+constexpr int kXSlot = 588;                 /* row slot pitch: 576 lines + 12, so that the same subband of neighbouring slots falls into
+                                               different banks when the IMDCT jobs of a warp span several granule-channels */
+constexpr int kTSlot = 296;                 /* likewise for the tails: 288 + 8 */
 constexpr int kRows = 15 + 18*GT;           /* time slots per channel: 15 history + tile */
 constexpr int kYPitch = 34;                 /* even: a DCT thread moves its row as 8-byte words, 16 threads cover all banks */
-constexpr int kXFloats = kSlots*kXSlot;     /* 11520 */
+constexpr int kXFloats = kSlots*kXSlot;     /* 11760 */
 constexpr int kYFloats = 2*kRows*kYPitch;   /* 10812, aliases XS */
-constexpr int kTFloats = kSlots*288;
+constexpr int kTFloats = kSlots*kTSlot;
 static_assert(sizeof(TileRec) == 256 && MP3B_TILE_SLOTS == kSlots, "tile record layout");
 static_assert(kYFloats <= kXFloats, "Y must fit in the X region");
+static_assert(kXSlot % 4 == 0 && kTSlot % 4 == 0, "16-byte aligned rows (bulk-copy destinations, float4 clears)");
 static_assert(GT*32 <= kThreads, "one FIR job per thread (stereo; a mono tile takes two rounds)");
 static_assert(15 + 18*MP3B_TILE_GRANULES_MONO <= 2*kRows, "a mono tile's rows fit the two channels' rows");
 static_assert(((GT + 2 + kThreads/32 - 1)/(kThreads/32))*2 <= 4, "a warp clears at most four rows, a quarter-warp each");
@@ -503,7 +506,7 @@ k_l3_transform(TransformArgs a, const uint16_t *__restrict__ reorder_inv, const 
         {
             float4 *zx = reinterpret_cast<float4 *>(S.x + slot*kXSlot);
             for (int k = from + gl; k < to; k += 8) zx[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-            float4 *zt = reinterpret_cast<float4 *>(S.t + slot*288);
+            float4 *zt = reinterpret_cast<float4 *>(S.t + slot*kTSlot);
 #pragma unroll
             for (int k = 0; k < 9; k++) zt[gl + 8*k] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
@@ -570,7 +573,7 @@ k_l3_transform(TransformArgs a, const uint16_t *__restrict__ reorder_inv, const 
         if (job < n_jobs3)
         {
             const SlotMeta m = S.meta[slot];
-            float *t = S.t + slot*288 + sb;
+            float *t = S.t + slot*kTSlot + sb;
             if (stateful && slot < 2*nch)
             {
                 /* carried state replaces the halo: overlap of the previous call */
@@ -630,7 +633,7 @@ k_l3_transform(TransformArgs a, const uint16_t *__restrict__ reorder_inv, const 
             const SlotMeta m = S.meta[slot];
             const int i = slot/nch - 2, ch = slot%nch;
             float prev[9], out[18];
-            const float *t = S.t + (slot - nch)*288 + sb;
+            const float *t = S.t + (slot - nch)*kTSlot + sb;
 #pragma unroll
             for (int k = 0; k < 9; k++) prev[k] = t[k*32];
             if (m.block_type == 2 && sb >= m.n_long) imdct_short_combine(prev, own[r], c_k.twid3, out);
@@ -722,7 +725,7 @@ k_l3_transform(TransformArgs a, const uint16_t *__restrict__ reorder_inv, const 
         for (int k = tid; k < nch*288; k += kThreads)
         {
             const int ch = k/288, rem = k - ch*288, sb = rem/9, i = rem - sb*9;
-            a.state_out[ch*288 + rem] = S.t[(last_slot0 + ch)*288 + i*32 + sb];
+            a.state_out[ch*288 + rem] = S.t[(last_slot0 + ch)*kTSlot + i*32 + sb];
         }
         for (int k = tid; k < nch*15*32; k += kThreads)
         {
