@@ -23,7 +23,7 @@ def main(path):
         a[1] += ms
     tot = sum(a[1] for a in agg.values())
     print("# ncu launch list summary\n")
-    print("Command: `python bench.py --steps 2 --warmup 3 --e2e-steps 1 --no-cpu-baseline` under")
+    print("Command: `python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline` under")
     print("`ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv` (raw list: %s)." % path.split("/")[-1])
     print("Per-launch times are cold-cache and serialised; compare shares, not absolutes.\n")
     print("| kernel | launches | avg ms | share of GPU time |\n|---|---|---|---|")

@@ -34,7 +34,7 @@ def main(rep, name):
     hdr, units, first = rows[0], rows[1], rows[2]
     print("# ncu --set full: %s (first captured launch)\n" % first[hdr.index("Kernel Name")])
     print("Captured with `ncu --set full --clock-control none --import-source on` on the bench command")
-    print("(`python bench.py --steps 2 --warmup 3 --e2e-steps 1 --no-cpu-baseline`, 1024 x l3-sin1k0db).\n")
+    print("(`python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline [--config ...]`, tools/profile.sh).\n")
     print("| metric | value | unit |\n|---|---|---|")
     vals = {}
     for k in KEYS:
