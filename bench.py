@@ -16,7 +16,8 @@ Workload: BASELINE.json configs (minimp3_b200/corpus.py); the default and the dr
   e2e       the public C-ABI call mp3dec_decode_batch_cuda() with HOST buffers every step: host walk, pinned
             staging, H2D, kernels, D2H of all PCM inside the timed region (pinned output slab); with N > 1 ONE call
             on rank 0 drives all N GPUs (opts.devices).  e2e_malloc: the same with per-stream malloc()ed output;
-            *.caller_pinned_inputs: the same with the streams in a caller-pinned slab (GPU frame scan, no staging copy).
+            inputs sit in a caller-pinned slab (opts.pinned_inputs: direct upload, GPU frame scan); *.pageable_inputs: the
+            same call on ordinary pageable buffers (host frame walk + staging copy).
   roofline  dominant kernel timed alone (CUDA events), algorithmic bytes / duration vs measured HBM peak, plus
             the FP32 figure (fast-algorithm flops / duration vs the FFMA peak at the sampled SM clock).
   cpu_baseline  the UNMODIFIED reference (oracle/_ref) on all host cores, a bounded sample of the same batch.
@@ -311,10 +312,11 @@ def main():
             dist.barrier(group=cpu_group)
         if rank == 0:
             devs = list(range(n_dev))
-            # primary numbers: the drop-in call on ordinary (pageable) stream buffers -- host frame walk into the
-            # library's PINNED staging slab, H2D from there.  Beside them the same call with the streams in a
-            # caller-pinned slab (opts.pinned_inputs): uploaded where they are, frames found by the GPU scan
-            # (k_scan.cu), the host only looks at the stream heads.
+            # primary numbers: the step's inputs live in pinned host memory (the contract's "host->device copy of that
+            # step's inputs from pinned host memory"): one page-locked slab, streams back to back, announced through
+            # opts.pinned_inputs -> uploaded where they are, frames found by the GPU scan (k_scan.cu), the host only
+            # looks at the stream heads.  Beside them the same call on ordinary pageable buffers (host frame walk
+            # into the library's own pinned staging slab, H2D from there): the plain drop-in use.
             offs, slab_bytes = [], 0
             for s_ in all_streams:
                 offs.append(slab_bytes)
@@ -326,11 +328,11 @@ def main():
                 slab[o:o + len(s_)] = np.frombuffer(s_, dtype=np.uint8)
                 views.append(slab[o:o + len(s_)])
             pin = (slab.ctypes.data, slab_bytes)
-            for key, output, src, extra in (("e2e", m.OUT_PINNED, all_streams, {}),
-                                            ("scope_ii", m.OUT_DEVICE, all_streams, {}),
-                                            ("e2e_malloc", m.OUT_MALLOC, all_streams, {}),
-                                            ("e2e_slab", m.OUT_PINNED, views, {"pinned_inputs": pin}),
-                                            ("scope_ii_slab", m.OUT_DEVICE, views, {"pinned_inputs": pin})):
+            for key, output, src, extra in (("e2e", m.OUT_PINNED, views, {"pinned_inputs": pin}),
+                                            ("scope_ii", m.OUT_DEVICE, views, {"pinned_inputs": pin}),
+                                            ("e2e_malloc", m.OUT_MALLOC, views, {"pinned_inputs": pin}),
+                                            ("e2e_pageable", m.OUT_PINNED, all_streams, {}),
+                                            ("scope_ii_pageable", m.OUT_DEVICE, all_streams, {})):
                 batch = m._Batch(src, device=local_rank, devices=devs if n_dev > 1 else None, raw_frames=False,
                                  allow_mono_stereo=True, output=output, host_threads=0, **extra)
                 ms_call, cs = timed_calls(batch, total_samples)
@@ -346,18 +348,18 @@ def main():
                         "ms_per_step": ms_call, "host_parse_ms": cs["host_parse_ms"], "issue_ms": cs["issue_ms"],
                         "finish_ms": cs["finish_ms"], "chunks": cs["n_chunks"], "devices": cs["n_devices"],
                         "streams_frame_scanned_on_gpu": cs["scanned_streams"], "host_threads": cores, "api": api}
-            e2e = pack("e2e", "ONE mp3dec_decode_batch_cuda(host buffers) call over %d GPU(s) -> pinned host PCM; host frame walk, "
-                              "pinned staging, H2D, kernels and D2H of all PCM inside the timed call (chunk-pipelined)" % n_dev,
+            e2e = pack("e2e", "ONE mp3dec_decode_batch_cuda(host buffers) call over %d GPU(s) -> pinned host PCM; streams in a "
+                              "caller-pinned slab (opts.pinned_inputs): stream heads on the host, H2D, GPU frame scan + all kernels, "
+                              "D2H of all PCM inside the timed call (chunk-pipelined)" % n_dev,
                        2*total_samples)
-            e2e["caller_pinned_inputs"] = pack("e2e_slab", "same call, streams in a caller-pinned slab (opts.pinned_inputs): no staging "
-                                               "copy, frame sync + reservoir accounting on the GPU (k_scan.cu)", 2*total_samples)
+            e2e["pageable_inputs"] = pack("e2e_pageable", "same call on ordinary pageable stream buffers: host frame walk + staging copy "
+                                          "into the library's pinned slab, H2D, kernels, D2H", 2*total_samples)
             e2e["d2h_gbs"] = 2*total_samples/(results["e2e"][0]*1e-3)/1e9
             e2e["note"] = ("floor = PCM bytes / PCIe D2H: %.2f GB per step; a B200's x16 Gen5 link moves ~55 GB/s, the pool's "
                            "8-GPU VM ~80-100 GB/s in aggregate" % (2*total_samples/1e9))
-            scope_ii = pack("scope_ii", "same call with MP3D_BATCH_OUT_DEVICE (SURVEY 8d scope ii): host frame walk + staging + H2D + "
-                                        "kernels, PCM stays in HBM", 0)
-            scope_ii["caller_pinned_inputs"] = pack("scope_ii_slab", "streams in a caller-pinned slab: stream heads on the host, H2D, GPU "
-                                                    "frame scan + kernels", 0)
+            scope_ii = pack("scope_ii", "same call with MP3D_BATCH_OUT_DEVICE (SURVEY 8d scope ii): stream heads on the host, H2D, GPU frame "
+                                        "scan + kernels, PCM stays in HBM", 0)
+            scope_ii["pageable_inputs"] = pack("scope_ii_pageable", "pageable stream buffers: host frame walk + staging copy + H2D + kernels", 0)
             e2e_malloc = pack("e2e_malloc", "same call with MP3D_BATCH_OUT_MALLOC (drop-in: one malloc()ed buffer per stream, "
                                             "freed by the caller inside the timed loop's untimed tail)", 2*total_samples)
 
