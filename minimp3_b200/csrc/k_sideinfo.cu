@@ -15,6 +15,53 @@ namespace mp3b {
 
 namespace {
 
+/* the 32 side-info bytes as four 64-bit words in bitstream order: the parse reads its ~60 fields from registers (the
+ * byte-wise reader of the host build turns into local-memory traffic here: 1500 LDL per thread) */
+struct SiRegBits
+{
+    unsigned long long w[4];
+    int pos, limit;
+    __device__ __forceinline__ unsigned long long word(int i) const
+    {
+        return i == 0 ? w[0] : i == 1 ? w[1] : i == 2 ? w[2] : i == 3 ? w[3] : 0ull;
+    }
+    __device__ __forceinline__ uint32_t get(int n)
+    {
+        const int s = pos;
+        pos += n;
+        if (pos > limit || n == 0) return 0;
+        const int i = s >> 6, sh = s & 63;
+        const unsigned long long hi = word(i), lo = word(i + 1);
+        const unsigned long long v = sh ? (hi << sh) | (lo >> (64 - sh)) : hi;
+        return (uint32_t)(v >> (64 - n));
+    }
+};
+
+/* frame_descs (l3_sideinfo.cuh) over the register reader */
+__device__ __forceinline__ int frame_descs_reg(const FrameRec &fr, GcDesc *out)
+{
+    SiRegBits bs;
+    const uint32_t *si = reinterpret_cast<const uint32_t *>(fr.si);
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+        bs.w[k] = (unsigned long long)__byte_perm(si[2*k], 0, 0x0123) << 32 | __byte_perm(si[2*k + 1], 0, 0x0123);
+    bs.pos = 0;
+    bs.limit = 256;
+    GranuleSide side[4];
+    if (read_side_info_t<false>(&bs, side, fr.hdr) < 0) return 0;
+    const int nch = fr.nch, n_gr = fr.n_gr;
+    const HdrBits hb(fr.hdr, nch);
+    uint64_t bit = fr.md_bit;
+    for (int igr = 0; igr < n_gr; igr++)
+        for (int ch = 0; ch < nch; ch++)
+        {
+            const GranuleSide &g = side[igr*nch + ch];
+            fill_gc_desc_hb(&out[igr*nch + ch], g, hb, ch, igr, bit);
+            bit += g.part_23_length;
+        }
+    return n_gr*nch;
+}
+
 __global__ void __launch_bounds__(256) k_l3_side_info(const FrameRec *__restrict__ frames, uint32_t n_frames, GcDesc *__restrict__ gcs)
 {
     const uint32_t f = blockIdx.x*blockDim.x + threadIdx.x;
@@ -27,7 +74,7 @@ __global__ void __launch_bounds__(256) k_l3_side_info(const FrameRec *__restrict
         for (int k = 0; k < 4; k++) dst[k] = __ldg(src + k);
     }
     GcDesc d[4];
-    const int n = frame_descs(fr, d);
+    const int n = frame_descs_reg(fr, d);
     uint4 *out = reinterpret_cast<uint4 *>(gcs + fr.gc_first);
     /* descriptors of granule 0 and granule 1 are contiguous: gc_first .. gc_first + n_gr*nch - 1 */
     for (int k = 0; k < n; k++)

@@ -753,7 +753,9 @@ k_l12_synth(Synth12Args a, const float *__restrict__ fir_coef)
     const bool stateful = a.state_in != nullptr;
     const int rows_ch = 15 + 12*n_gr;
 
-    /* rows -> shared: row r of channel ch is slot (r - 15) of the tile; r < 15 comes from the halo blocks */
+    /* rows -> shared: row r of channel ch is slot (r - 15) of the tile; r < 15 comes from the halo blocks.  The
+     * rounds are independent: unrolled, so that a warp has several rows' loads in flight instead of one */
+#pragma unroll 4
     for (int job = warp; job < rows_ch*nch; job += kThreads/32)
     {
         const int ch = job >= rows_ch ? 1 : 0, r = job - ch*rows_ch;
