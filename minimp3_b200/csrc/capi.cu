@@ -543,6 +543,7 @@ static mp3dec_batch_plan_t *plan_create_impl(const mp3dec_batch_stream_t *stream
      * chunk before; the plan's stream picks up behind them */
     cudaStream_t up = (async && !opts.cuda_stream) ? ctx->stream_h2d : P->stream;
     cudaMemcpyAsync(B.d_md.p, B.h_md.p, P->md_bytes, cudaMemcpyHostToDevice, up);
+    if (gcs) cudaMemsetAsync(B.d_gcs.p, 0, (size_t)gcs*sizeof(GcDesc), up);   /* padding slots are never written: keep them defined (the lane-order heuristic looks at them) */
     if (frs) cudaMemcpyAsync(B.d_frames.p, B.h_frames.p, (size_t)frs*sizeof(FrameRec), cudaMemcpyHostToDevice, up);
     if (tiles) cudaMemcpyAsync(B.d_tiles.p, B.h_tiles.p, (size_t)tiles*sizeof(TileDesc), cudaMemcpyHostToDevice, up);
     if (ists) cudaMemcpyAsync(B.d_istlist.p, B.h_ist.p, (size_t)ists*4, cudaMemcpyHostToDevice, up);

@@ -338,3 +338,39 @@ def test_pinned_input_slab_uploads_directly_same_results(m):
     assert r0 == r1 and s1["scanned_streams"] >= 5*len(SCAN_REGULAR)
     for a, b in zip(o0, o1):
         assert a["samples"] == b["samples"] and np.array_equal(a["pcm"], b["pcm"])
+
+
+def test_gpu_frame_scan_on_many_damaged_streams(m):
+    """200 damaged variants of four streams (byte damage anywhere incl. headers and side info, cuts at both ends,
+    deleted and duplicated ranges, junk appended) through the forced GPU scan and through the host walker: identical
+    return codes, sample counts and PCM bytes -- whatever the scan cannot vouch for must end up with the walker"""
+    rng = np.random.default_rng(20240)
+    bases = [load_vector(n) for n in ("l3-sin1k0db", "l3-compl", "M2L3_bitrate_22_all", "l3-he_44khz")]
+    datas = []
+    for t in range(200):
+        b = bytearray(bases[t % 4])
+        kind = t % 5
+        if kind == 0:
+            for _ in range(int(rng.integers(1, 8))):
+                b[int(rng.integers(0, len(b)))] = int(rng.integers(0, 256))
+        elif kind == 1:
+            b = b[int(rng.integers(0, 2000)):int(rng.integers(len(b)//2, len(b)))]
+        elif kind == 2:
+            p, n = int(rng.integers(0, len(b) - 600)), int(rng.integers(1, 600))
+            if rng.random() < 0.5:
+                del b[p:p + n]
+            else:
+                b[p:p] = b[p:p + n]
+        elif kind == 3:
+            b += rng.integers(0, 256, int(rng.integers(1, 3000)), dtype=np.uint8).tobytes()
+        else:
+            p = int(rng.integers(0, len(b) - 4))
+            b[p:p + 4] = bytes([0xFF, 0xFB, int(rng.integers(0, 256)), int(rng.integers(0, 256))])
+        datas.append(bytes(b))
+    for raw in (False, True):
+        r0, o0, s0 = _call(m, datas, raw_frames=raw, allow_mono_stereo=True, gpu_frame_scan=-1)
+        r1, o1, s1 = _call(m, datas, raw_frames=raw, allow_mono_stereo=True, gpu_frame_scan=1)
+        assert r0 == r1 and s1["scanned_streams"] > 20
+        for i, (a, b) in enumerate(zip(o0, o1)):
+            assert a["samples"] == b["samples"] and a["hz"] == b["hz"] and a["channels"] == b["channels"], (raw, i)
+            assert np.array_equal(a["pcm"], b["pcm"]), (raw, i)
