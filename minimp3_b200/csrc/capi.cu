@@ -183,6 +183,11 @@ struct BufferSet
     /* GPU frame scan (k_scan.cu) */
     PinBuf h_scan, h_sum, h_bases, h_slotmap;
     DevBuf d_raw, d_scan, d_scan_frames, d_sum, d_bases, d_slotmap;
+    /* what this set has served so far: route (0 host walker, 1 GPU frame scan) and the largest input of a plan.  A call
+     * cuts its streams into chunks of different sizes; handing every plan the set that last held a plan of its kind
+     * and size keeps repeated calls from re-growing (cudaFree + cudaMalloc / cudaHostAlloc) a too-small set each time */
+    int route = -1;
+    size_t served_bytes = 0;
     void release()
     {
         h_md.release(); h_gcs.release(); h_frames.release(); h_tiles.release(); h_ist.release(); h_order.release(); h_gcbase.release(); h_pcm.release(); h_l12.release(); h_tiles12.release();
@@ -244,22 +249,36 @@ DeviceCtx *get_ctx(int device)
     return c;
 }
 
-BufferSet *acquire_set(DeviceCtx *c)
+BufferSet *acquire_set(DeviceCtx *c, int route, size_t input_bytes)
 {
     std::lock_guard<std::mutex> lock(c->mu);
-    if (!c->free_sets.empty())
+    /* best fit: same route first; the smallest set that has held at least this much, else the largest one */
+    int best = -1;
+    auto better = [&](const BufferSet *a, const BufferSet *b) {   /* a preferable to b */
+        const bool ra = a->route == route, rb = b->route == route;
+        if (ra != rb) return ra;
+        const bool fa = a->served_bytes >= input_bytes, fb = b->served_bytes >= input_bytes;
+        if (fa != fb) return fa;
+        return fa ? a->served_bytes < b->served_bytes : a->served_bytes > b->served_bytes;
+    };
+    for (int i = 0; i < (int)c->free_sets.size(); i++)
+        if (best < 0 || better(c->free_sets[i], c->free_sets[best])) best = i;
+    BufferSet *s;
+    if (best >= 0)
     {
-        BufferSet *s = c->free_sets.back();
-        c->free_sets.pop_back();
-        return s;
-    }
-    return new BufferSet();
+        s = c->free_sets[best];
+        c->free_sets.erase(c->free_sets.begin() + best);
+    } else
+        s = new BufferSet();
+    if (s->route != route) { s->route = route; s->served_bytes = 0; }
+    if (s->served_bytes < input_bytes) s->served_bytes = input_bytes;
+    return s;
 }
 
 void release_set(DeviceCtx *c, BufferSet *s)
 {
     std::lock_guard<std::mutex> lock(c->mu);
-    if (c->free_sets.size() < 16) c->free_sets.push_back(s);
+    if (c->free_sets.size() < 48) c->free_sets.push_back(s);
     else { s->release(); delete s; }
 }
 
@@ -397,7 +416,11 @@ static mp3dec_batch_plan_t *plan_create_impl(const mp3dec_batch_stream_t *stream
     P->stream = opts.cuda_stream ? (cudaStream_t)opts.cuda_stream : ctx->stream;
     P->n_streams = n_streams;
     P->sample_size = opts.float_output ? 4 : 2;
-    P->bufs = acquire_set(ctx);
+    {
+        size_t in_bytes = 0;
+        for (int i = 0; i < n_streams; i++) in_bytes += streams[i].size;
+        P->bufs = acquire_set(ctx, 0, in_bytes);
+    }
     BufferSet &B = *P->bufs;
 
     const double t0 = now_ms();
@@ -720,7 +743,7 @@ static ScanJob *scan_begin(const mp3dec_batch_stream_t *streams, int n_streams, 
     P->opts = opts;
     P->stream = opts.cuda_stream ? (cudaStream_t)opts.cuda_stream : ctx->stream;
     P->sample_size = opts.float_output ? 4 : 2;
-    P->bufs = acquire_set(ctx);
+    P->bufs = acquire_set(ctx, 1, (size_t)raw_bytes);
     BufferSet &B = *P->bufs;
     J->P = P;
     /* the scans of a call's chunks must not queue up behind each other (each walks its streams frame by frame at
@@ -1414,7 +1437,7 @@ int mp3dec_decode_batch_cuda(const mp3dec_batch_stream_t *streams, int n_streams
          * way -- that copy, not the frame walk, is what the host stage costs (measured: 4.2 ms of 4.5 ms on config 2) --
          * and the scan only adds its latency; with inputs the caller pinned (opts.pinned_inputs) the copy disappears
          * and the host is left with the stream heads. */
-        const bool pays = opts && opts->pinned_inputs && opts->pinned_inputs_bytes && n_c >= 64;
+        const bool pays = opts && opts->pinned_inputs && opts->pinned_inputs_bytes && n_streams >= 64;   /* the call's count: the first chunks are small by design */
         if (scan_mode > 0 || (scan_mode == 0 && pays)) jobs[c] = scan_begin(streams + first[c], n_c, opts, &err);
     }
     for (int c = 0; c < n_chunks && !err; c++)

@@ -44,6 +44,6 @@ if __name__ == "__main__":
                 n = b.call()
                 ts.append((time.perf_counter() - t0)*1e3)
             cs = b.call_stats()
-            print("cfg %s %-24s out %-6s: %.2f ms (best %.2f) = %.1f Gsamples/s; scanned %d, host %.2f ms, issue %.2f, finish %.2f"
+            print("cfg %s %-24s out %-6s: %.2f ms (best %.2f) = %.1f Gsamples/s; scanned %d, host %.2f ms, issue %.2f, finish %.2f; calls %s"
                   % (cfg, label, name, sorted(ts)[len(ts)//2], min(ts), n/min(ts)/1e6, cs["scanned_streams"], cs["host_parse_ms"],
-                     cs["issue_ms"], cs["finish_ms"]), flush=True)
+                     cs["issue_ms"], cs["finish_ms"], " ".join("%.0f" % t for t in ts)), flush=True)
