@@ -304,7 +304,12 @@ class _Batch:
         err = self.L.mp3dec_decode_batch_cuda(self.streams, self.n, self.infos, self.rets, C.byref(self.opts))
         if err:
             raise RuntimeError("mp3dec_decode_batch_cuda failed: %d" % err)
-        return sum(self.infos[i].samples for i in range(self.n))
+        if not self.n:
+            return 0
+        # mp3dec_file_info_t.samples of every stream in one go (a Python loop over 8192 ctypes structs costs ms)
+        words = np.frombuffer(self.infos, dtype=np.uint8).reshape(self.n, C.sizeof(FileInfo))
+        off = FileInfo.samples.offset
+        return int(words[:, off:off + 8].copy().view(np.uint64).sum())
 
     def call_stats(self):
         """where the time of the last call() on this thread went (mp3dec_batch_last_call_stats)"""

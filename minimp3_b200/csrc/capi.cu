@@ -221,6 +221,7 @@ struct DeviceCtx
 
 std::mutex g_ctx_mu;
 DeviceCtx *g_ctx[64];
+cudaEvent_t g_dbg_base = nullptr;     /* MP3B_DEBUG_TIMING: start of the current call on the read-back stream */
 
 DeviceCtx *get_ctx(int device)
 {
@@ -313,6 +314,7 @@ struct mp3dec_batch_plan
     size_t sample_size = 2;
     bool taps = false;
     cudaEvent_t ev_kernels = nullptr, ev_d2h = nullptr, ev_h2d = nullptr;
+    cudaEvent_t ev_dbg0 = nullptr;        /* MP3B_DEBUG_TIMING only */
     cudaStream_t scan_stream = nullptr;   /* GPU frame scan route: upload + scan + record kernels of this plan */
     std::vector<int> out_index;    /* stream i of the plan is stream out_index[i] of the caller (empty: identity) */
     bool export_on_destroy = false; /* one-call entry point with pinned / device output: the caller holds pointers into bufs */
@@ -757,8 +759,7 @@ static ScanJob *scan_begin(const mp3dec_batch_stream_t *streams, int n_streams, 
     {
         bool ok = (direct || B.h_md.ensure(raw_bytes + 64)) && B.d_raw.ensure(raw_bytes + 64) && B.h_scan.ensure((size_t)nc*sizeof(ScanStream)) &&
                   B.d_scan.ensure((size_t)nc*sizeof(ScanStream)) &&
-                  B.d_scan_frames.ensure((size_t)n_slots*sizeof(ScanFrame) + 64) && B.h_sum.ensure((size_t)nc*sizeof(ScanSummary)) &&
-                  B.d_sum.ensure((size_t)nc*sizeof(ScanSummary));
+                  B.d_scan_frames.ensure((size_t)n_slots*sizeof(ScanFrame) + 64) && B.h_sum.ensure((size_t)nc*sizeof(ScanSummary));
         if (!ok) { *err = MP3D_E_MEMORY; mp3dec_batch_plan_destroy(P); scan_job_free(J); return nullptr; }
         ScanStream *hs = (ScanStream *)B.h_scan.p;
         uint32_t slot = 0;
@@ -794,9 +795,12 @@ static ScanJob *scan_begin(const mp3dec_batch_stream_t *streams, int n_streams, 
         sa.streams = (const ScanStream *)B.d_scan.p;
         sa.n_streams = (uint32_t)nc;
         sa.frames = (ScanFrame *)B.d_scan_frames.p;
-        sa.summaries = (ScanSummary *)B.d_sum.p;
+        /* the summaries go straight into page-locked host memory (unified addressing: the kernel stores through the
+         * host pointer).  As a device-to-host copy they would queue in the copy engine behind the PCM read-backs of
+         * the earlier chunks -- measured: the scan of chunk 5 of 8 came back 13 ms late, and the first PCM copy waited
+         * 0.8 ms for summary copies submitted before it */
+        sa.summaries = (ScanSummary *)B.h_sum.p;
         cudaError_t e = launch_stream_scan(sa, up);
-        cudaMemcpyAsync(B.h_sum.p, B.d_sum.p, (size_t)nc*sizeof(ScanSummary), cudaMemcpyDeviceToHost, up);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&J->ev_sum, cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventRecord(J->ev_sum, up);
         if (e != cudaSuccess)
@@ -1184,12 +1188,18 @@ static int plan_begin_fetch(mp3dec_batch_plan_t *P, cudaStream_t copy_stream)
     if (!B.h_pcm.ensure((size_t)P->n_samples*ss + 64)) return MP3D_E_MEMORY;
     if (copy_stream != P->stream)
     {
-        if (!P->ev_kernels) cudaEventCreateWithFlags(&P->ev_kernels, cudaEventDisableTiming);
+        if (!P->ev_kernels) cudaEventCreateWithFlags(&P->ev_kernels, getenv("MP3B_DEBUG_TIMING") ? cudaEventDefault : cudaEventDisableTiming);
         cudaEventRecord(P->ev_kernels, P->stream);
         cudaStreamWaitEvent(copy_stream, P->ev_kernels, 0);
     }
+    static const bool dbg = getenv("MP3B_DEBUG_TIMING") != nullptr;
+    if (dbg)
+    {   /* debug timeline: when this plan's read-back ran, relative to the end of its kernels */
+        cudaEventCreate(&P->ev_dbg0);
+        cudaEventRecord(P->ev_dbg0, copy_stream);
+    }
     cudaMemcpyAsync(B.h_pcm.p, B.d_pcm.p, (size_t)P->n_samples*ss, cudaMemcpyDeviceToHost, copy_stream);
-    if (!P->ev_d2h) cudaEventCreateWithFlags(&P->ev_d2h, cudaEventDisableTiming);
+    if (!P->ev_d2h) cudaEventCreateWithFlags(&P->ev_d2h, dbg ? cudaEventDefault : cudaEventDisableTiming);
     cudaEventRecord(P->ev_d2h, copy_stream);
     P->d2h_started = true;
     return 0;
@@ -1206,6 +1216,21 @@ static int plan_finish_fetch(mp3dec_batch_plan_t *P, mp3dec_file_info_t *infos, 
     {
         fprintf(stderr, "minimp3_b200: decode failed: %s\n", cudaGetErrorString(e));
         return MP3D_E_CUDA;
+    }
+    if (P->ev_dbg0)
+    {
+        float ms = 0.f, k1 = -1.f, c0 = -1.f, c1 = -1.f;
+        cudaEventElapsedTime(&ms, P->ev_dbg0, P->ev_d2h);
+        if (g_dbg_base)
+        {
+            if (P->ev_kernels) cudaEventElapsedTime(&k1, g_dbg_base, P->ev_kernels);
+            cudaEventElapsedTime(&c0, g_dbg_base, P->ev_dbg0);
+            cudaEventElapsedTime(&c1, g_dbg_base, P->ev_d2h);
+        }
+        fprintf(stderr, "  read-back of %zu bytes: %.3f ms = %.1f GB/s; kernels done %.3f, copy queue free %.3f, copy done %.3f\n",
+                (size_t)P->n_samples*ss, ms, (double)P->n_samples*ss/ms/1e6, k1, c0, c1);
+        cudaEventDestroy(P->ev_dbg0);
+        P->ev_dbg0 = nullptr;
     }
     std::atomic<int> oom(0);
     parallel_for(P->n_streams, mode == MP3D_BATCH_OUT_MALLOC ? P->opts.host_threads : 1, [&](int i) {
@@ -1417,6 +1442,15 @@ int mp3dec_decode_batch_cuda(const mp3dec_batch_stream_t *streams, int n_streams
     }
     static const bool dbg_timing = getenv("MP3B_DEBUG_TIMING") != nullptr;
     const double tt0 = now_ms();
+    if (dbg_timing)
+    {
+        DeviceCtx *c = get_ctx(opts ? opts->device : 0);
+        if (c)
+        {
+            if (!g_dbg_base) cudaEventCreate(&g_dbg_base);
+            cudaEventRecord(g_dbg_base, c->stream_d2h);
+        }
+    }
     auto launch = [&](mp3dec_batch_plan_t *P, int first_stream) {
         parts.push_back(Part{ P, first_stream });
         P->export_on_destroy = exports;
@@ -1480,8 +1514,10 @@ int mp3dec_decode_batch_cuda(const mp3dec_batch_stream_t *streams, int n_streams
     for (Part &pt : parts)
     {
         if (!err)
+        {
             err = plan_finish_fetch(pt.plan, infos_out ? infos_out + pt.first : nullptr, rets_out ? rets_out + pt.first : nullptr);
-        else
+            if (dbg_timing) fprintf(stderr, "  part done at t=%.3f\n", now_ms() - tt0);
+        } else
             cudaStreamSynchronize(pt.plan->stream);
     }
     const double tt2 = now_ms();
