@@ -22,6 +22,7 @@
 #include "../../include/minimp3_b200.h"
 #include "host_parse.h"
 #include "kernels.h"
+#include "l12_decode.cuh"
 #include "mp3_hdr.cuh"
 
 using namespace mp3b;
@@ -178,7 +179,7 @@ struct PinBuf
 struct BufferSet
 {
     PinBuf h_md, h_gcs, h_frames, h_tiles, h_ist, h_order, h_gcbase, h_pcm, h_l12, h_tiles12;
-    DevBuf d_md, d_gcs, d_frames, d_tiles, d_tile_recs, d_tile_jobs, d_counter, d_istlist, d_order, d_order_sorted, d_order_scratch, d_gcbase, d_xr, d_nzl, d_istpos, d_pcm, d_l12, d_tiles12, d_sub12;
+    DevBuf d_md, d_gcs, d_frames, d_tiles, d_tile_recs, d_tile_jobs, d_counter, d_istlist, d_order, d_order_sorted, d_order_scratch, d_gcbase, d_xr, d_nzl, d_istpos, d_pcm, d_l12, d_tiles12, d_sub12, d_l12info;
     DevBuf d_tap_q, d_tap_scf, d_tap_sub, d_phase_clk;
     /* GPU frame scan (k_scan.cu) */
     PinBuf h_scan, h_sum, h_bases, h_slotmap;
@@ -191,7 +192,7 @@ struct BufferSet
     void release()
     {
         h_md.release(); h_gcs.release(); h_frames.release(); h_tiles.release(); h_ist.release(); h_order.release(); h_gcbase.release(); h_pcm.release(); h_l12.release(); h_tiles12.release();
-        d_l12.release(); d_tiles12.release(); d_sub12.release();
+        d_l12.release(); d_tiles12.release(); d_sub12.release(); d_l12info.release();
         d_md.release(); d_gcs.release(); d_frames.release(); d_tiles.release(); d_tile_recs.release(); d_tile_jobs.release(); d_counter.release(); d_istlist.release(); d_order.release(); d_order_sorted.release(); d_order_scratch.release(); d_gcbase.release(); d_xr.release(); d_nzl.release();
         h_scan.release(); h_sum.release(); h_bases.release(); h_slotmap.release();
         d_raw.release(); d_scan.release(); d_scan_frames.release(); d_sum.release(); d_bases.release(); d_slotmap.release();
@@ -559,6 +560,7 @@ static mp3dec_batch_plan_t *plan_create_impl(const mp3dec_batch_stream_t *stream
                           B.d_gcbase.ensure(((size_t)n_streams + 1)*4 + 64))) &&
          B.d_l12.ensure((size_t)l12s*sizeof(L12FrameDesc) + 64) &&
          B.d_tiles12.ensure((size_t)tiles12*sizeof(TileDesc) + 64) && B.d_sub12.ensure((size_t)blks*384*sizeof(float) + 64) &&
+         B.d_l12info.ensure((size_t)l12s*sizeof(L12Compact) + 64) &&
          B.d_xr.ensure((size_t)gcs*576*sizeof(float) + 64) && B.d_nzl.ensure((size_t)gcs*2 + 64) &&
          B.d_istpos.ensure((size_t)gcs*40 + 64) && B.d_pcm.ensure((size_t)samples*P->sample_size + 64);
     if (!ok) { *err = MP3D_E_MEMORY; mp3dec_batch_plan_destroy(P); return nullptr; }
@@ -1118,6 +1120,7 @@ static int plan_run_stages(mp3dec_batch_plan_t *P, int stage_mask)
         la.md_words = ea.md_words; la.md_n_words = ea.md_n_words;
         la.frames = (const L12FrameDesc *)B.d_l12.p; la.n_frames = (uint32_t)P->n_l12;
         la.sub12 = (float *)B.d_sub12.p;
+        la.info = (L12Compact *)B.d_l12info.p;
         e = launch_l12_dequant(la, P->stream);
         if (e == cudaSuccess)
         {
@@ -1609,7 +1612,7 @@ static int decode_frame_impl(mp3dec_t *dec, const uint8_t *mp3, int mp3_bytes, v
         const int n_samples = n_blocks*384*nch;
         const size_t md_bytes = round_up((size_t)fp.payload_bytes + 64, 16);
         bool ok = B.h_md.ensure(md_bytes + 256) && B.d_md.ensure(md_bytes) && B.d_l12.ensure(64) && B.d_tiles12.ensure(64) &&
-                  B.d_sub12.ensure(6*384*4) && B.d_pcm.ensure(2304*4) && B.h_pcm.ensure(2304*4) &&
+                  B.d_sub12.ensure(6*384*4) && B.d_l12info.ensure(sizeof(L12Compact)) && B.d_pcm.ensure(2304*4) && B.h_pcm.ensure(2304*4) &&
                   ctx->d_state_in.ensure(1536*4) && ctx->d_state_out.ensure(1536*4) && ctx->h_state.ensure(2*1536*4);
         if (!ok) return 0;
         uint8_t *h = (uint8_t *)B.h_md.p;
@@ -1634,7 +1637,7 @@ static int decode_frame_impl(mp3dec_t *dec, const uint8_t *mp3, int mp3_bytes, v
         cudaMemcpyAsync(ctx->d_state_in.p, hs, 960*4, cudaMemcpyHostToDevice, s);
         Layer12Args la;
         la.md_words = (const uint32_t *)B.d_md.p; la.md_n_words = md_bytes/4;
-        la.frames = (const L12FrameDesc *)B.d_l12.p; la.n_frames = 1; la.sub12 = (float *)B.d_sub12.p;
+        la.frames = (const L12FrameDesc *)B.d_l12.p; la.n_frames = 1; la.sub12 = (float *)B.d_sub12.p; la.info = (L12Compact *)B.d_l12info.p;
         cudaError_t e = launch_l12_dequant(la, s);
         if (e == cudaSuccess)
         {

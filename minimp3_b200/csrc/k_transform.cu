@@ -744,7 +744,7 @@ template <bool FLOAT_OUT>
 __global__ void __launch_bounds__(kThreads, 3)
 k_l12_synth(Synth12Args a, const float *__restrict__ fir_coef)
 {
-    __shared__ float y[kY12Floats + GT*2*12*2];
+    __shared__ __align__(16) float y[kY12Floats + GT*2*12*2];
     __shared__ __align__(16) float fir_taps[512];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     stage_fir_taps(fir_taps, fir_coef, tid);
@@ -753,27 +753,28 @@ k_l12_synth(Synth12Args a, const float *__restrict__ fir_coef)
     const bool stateful = a.state_in != nullptr;
     const int rows_ch = 15 + 12*n_gr;
 
-    /* rows -> shared: row r of channel ch is slot (r - 15) of the tile; r < 15 comes from the halo blocks.  The
-     * rounds are independent: unrolled, so that a warp has several rows' loads in flight instead of one */
+    /* rows -> shared: row r of channel ch is slot (r - 15) of the tile; r < 15 comes from the halo blocks.  A thread
+     * moves 16 bytes of a row, the rounds are independent and unrolled: four loads in flight per thread */
+    const int n_quads = rows_ch*nch*8;
 #pragma unroll 4
-    for (int job = warp; job < rows_ch*nch; job += kThreads/32)
+    for (int job = tid; job < n_quads; job += kThreads)
     {
-        const int ch = job >= rows_ch ? 1 : 0, r = job - ch*rows_ch;
-        float v = 0.f;
+        const int q = job & 7, rr = job >> 3;
+        const int ch = rr >= rows_ch ? 1 : 0, r = rr - ch*rows_ch;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (r >= 15)
         {
             const int b = (r - 15)/12, slot = (r - 15) - b*12;
-            v = __ldg(a.sub12 + (size_t)(tile.gc_first + b*nch + ch)*384 + slot*32 + lane);
-        } else if (stateful)
-        {
-            v = 0.f;     /* carried history is already transformed; filled after the DCT */
-        } else
+            v = __ldg(reinterpret_cast<const float4 *>(a.sub12 + (size_t)(tile.gc_first + b*nch + ch)*384 + slot*32) + q);
+        } else if (!stateful)     /* carried history is already transformed; filled after the DCT */
         {
             const int blk = r >= 3 ? tile.halo[ch][0] : tile.halo[ch][1];
             const int slot = r >= 3 ? r - 3 : 9 + r;
-            if (blk >= 0) v = __ldg(a.sub12 + (size_t)blk*384 + slot*32 + lane);
+            if (blk >= 0) v = __ldg(reinterpret_cast<const float4 *>(a.sub12 + (size_t)blk*384 + slot*32) + q);
         }
-        y[(ch*kRows12 + r)*kYPitch + lane] = v;
+        float2 *dst = reinterpret_cast<float2 *>(y + (ch*kRows12 + r)*kYPitch + q*4);
+        dst[0] = make_float2(v.x, v.y);
+        dst[1] = make_float2(v.z, v.w);
     }
     __syncthreads();
     for (int job = tid; job < rows_ch*nch; job += kThreads)
@@ -785,12 +786,13 @@ k_l12_synth(Synth12Args a, const float *__restrict__ fir_coef)
             for (int k = 0; k < 32; k++) row[k] = a.state_in[(ch*15 + r)*32 + k];
             continue;
         }
+        float2 *row2 = reinterpret_cast<float2 *>(row);
         float v[32];
 #pragma unroll
-        for (int k = 0; k < 32; k++) v[k] = row[k];
+        for (int k = 0; k < 32; k += 2) { const float2 p = row2[k >> 1]; v[k] = p.x; v[k + 1] = p.y; }
         dct2_32_paired(v);
 #pragma unroll
-        for (int k = 0; k < 32; k++) row[k] = v[k];
+        for (int k = 0; k < 32; k += 2) row2[k >> 1] = make_float2(v[k], v[k + 1]);
     }
     __syncthreads();
     float *special = y + kY12Floats;

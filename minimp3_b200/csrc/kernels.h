@@ -64,6 +64,8 @@ struct TransformArgs
     long long *phase_clk;
 };
 
+struct L12Compact;     /* l12_decode.cuh */
+
 struct Layer12Args
 {
     const uint32_t *md_words;
@@ -71,6 +73,7 @@ struct Layer12Args
     const L12FrameDesc *frames;
     uint32_t n_frames;
     float *sub12;                 /* [n_blockch][12][32] scaled subband samples */
+    L12Compact *info;             /* scratch [n_frames]: the parsed scale info, written by k_l12_scale_info */
 };
 
 /* synthesis over Layer I/II blocks: TileDesc.gc_first / halo index block-channels of sub12 */

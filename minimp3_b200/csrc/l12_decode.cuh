@@ -101,9 +101,21 @@ struct L12Info
     float scf[3*64];
 };
 
-/* L12_read_scale_info + L12_read_scalefactors (minimp3.h:362-432).  Reader needs get(n). */
-template <class Reader>
-MP3_HD void l12_read_scale_info(const uint8_t *hdr, unsigned kbps_total, Reader &br, L12Info *sci, bool want_scf)
+/* the scalefactor of 6-bit index b for a band quantised with allocation ba (minimp3.h:385-400):
+ * 2^-20 * 2^(-(b%3)/3) / levels * 2^(21 - b/3) */
+MP3_HD float l12_scf_value(int b, int ba)
+{
+    const int lv = ba < 17 ? (1 << ba) - 1 : (2 << (ba - 17)) + 1;
+    const int r = b % 3;
+    const float base = r == 0 ? 9.53674316e-07f : r == 1 ? 7.56931807e-07f : 6.00777173e-07f;
+    return MP3_FMUL(MP3_FDIV(base, (float)lv), (float)((1 << 21) >> (b/3)));
+}
+
+/* L12_read_scale_info + L12_read_scalefactors (minimp3.h:362-432).  Reader needs get(n); Info needs total_bands,
+ * stereo_bands and bitalloc[64]; scf_out(3*i + part, index, ba) receives the scalefactor index in force for every
+ * (band-channel i, part) -- -1 where the band carries nothing -- and the allocation it scales. */
+template <class Reader, class Info, class ScfOut>
+MP3_HD void l12_parse_scale_info(const uint8_t *hdr, unsigned kbps_total, Reader &br, Info *sci, ScfOut scf_out)
 {
     L12Alloc a;
     l12_alloc_table(hdr, kbps_total, &a);
@@ -124,31 +136,47 @@ MP3_HD void l12_read_scale_info(const uint8_t *hdr, unsigned kbps_total, Reader 
         scfcod[i] = (uint8_t)(sci->bitalloc[i] ? (a.layer1 ? 2 : (int)br.get(2)) : 6);
     for (int i = 0; i < 2*a.total_bands; i++)
     {
-        float s = 0;
         const int ba = sci->bitalloc[i];
         const int mask = ba ? 4 + ((19 >> scfcod[i]) & 3) : 0;
+        int cur = -1;       /* a part without an index of its own keeps the previous part's */
         for (int m = 4, k = 0; m; m >>= 1, k++)
         {
-            if (mask & m)
-            {
-                const int b = (int)br.get(6);
-                if (want_scf)
-                {
-                    /* 2^-20 * 2^(-(b%3)/3) / (levels) * 2^(21 - b/3) */
-                    const int lv = ba < 17 ? (1 << ba) - 1 : (2 << (ba - 17)) + 1;
-                    const int r = b % 3;
-                    const float base = r == 0 ? 9.53674316e-07f : r == 1 ? 7.56931807e-07f : 6.00777173e-07f;
-                    s = MP3_FMUL(MP3_FDIV(base, (float)lv), (float)((1 << 21) >> (b/3)));
-                }
-            }
-            if (want_scf) sci->scf[3*i + k] = s;
+            if (mask & m) cur = (int)br.get(6);
+            scf_out(3*i + k, cur, ba);
         }
     }
     for (int i = a.stereo_bands; i < a.total_bands; i++) sci->bitalloc[2*i + 1] = 0;
 }
 
+template <class Reader>
+MP3_HD void l12_read_scale_info(const uint8_t *hdr, unsigned kbps_total, Reader &br, L12Info *sci, bool want_scf)
+{
+    l12_parse_scale_info(hdr, kbps_total, br, sci, [&](int idx, int code, int ba) {
+        if (want_scf) sci->scf[idx] = code < 0 ? 0.f : l12_scf_value(code, ba);
+    });
+}
+
+/* the same parse in compact form: what the scale-info kernel leaves in HBM for the sample kernel (272 bytes per frame) */
+struct alignas(16) L12Compact
+{
+    uint8_t bitalloc[64];
+    uint8_t scf_index[192];      /* per (band-channel, part); 0xFF: none */
+    uint64_t sample_bit_off;     /* absolute bit offset of the first sub-block of samples */
+    int32_t sub_bits;            /* bits per sub-block */
+    uint8_t total_bands, stereo_bands, group, pad;
+};
+static_assert(sizeof(L12Compact) == 272, "17 x 16 bytes");
+
+/* allocation that scales (band-channel i): the second channel of a joint-stereo band is scaled with the first one's
+ * allocation (its own entry is cleared once the scalefactors are read, minimp3.h:375, 402-405) */
+MP3_HD int l12_scale_alloc(const uint8_t *bitalloc, int stereo_bands, int i)
+{
+    return ((i & 1) && (i >> 1) >= stereo_bands) ? bitalloc[i - 1] : bitalloc[i];
+}
+
 /* bits one L12_dequantize_granule sub-block (one value of j) consumes */
-MP3_HD int l12_subblock_bits(const L12Info &sci, int group_size)
+template <class Info>
+MP3_HD int l12_subblock_bits(const Info &sci, int group_size)
 {
     int bits = 0;
     for (int i = 0; i < 2*sci.total_bands; i++)
@@ -166,44 +194,35 @@ MP3_HD int l12_subblock_bits(const L12Info &sci, int group_size)
 }
 
 /*
- * One sub-block (minimp3.h:434-467 inner j loop) + scaling and joint-stereo copy (minimp3.h:469-481):
- * group_size consecutive time slots of every band.  out(ch, slot, sb) receives sample * scalefactor;
- * igr selects which of the three scalefactors of a band applies.
+ * One band of one sub-block (minimp3.h:434-467, the body of the inner j loop) + scaling and joint-stereo copy
+ * (minimp3.h:469-481): group_size consecutive time slots.  v[ch][k] receives sample * scalefactor (zeros beyond
+ * total_bands); igr selects which of the three scalefactors of the band applies.
  */
-template <class Reader, class Out>
-MP3_HD void l12_dequant_subblock(Reader &br, const L12Info &sci, int group_size, int igr, int slot0, Out out)
+template <class Reader>
+MP3_HD void l12_dequant_band(Reader &br, const L12Info &sci, int group_size, int igr, int b, float v[2][3])
 {
-    for (int b = 0; b < 32; b++)
+    for (int ch = 0; ch < 2; ch++)
+        for (int k = 0; k < 3; k++) v[ch][k] = 0.f;
+    if (b >= sci.total_bands) return;
+    for (int ch = 0; ch < 2; ch++)
     {
-        float v[2][3] = { { 0.f, 0.f, 0.f }, { 0.f, 0.f, 0.f } };
-        if (b < sci.total_bands)
+        const int ba = sci.bitalloc[2*b + ch];
+        if (!ba) continue;
+        if (ba < 17)
         {
-            for (int ch = 0; ch < 2; ch++)
-            {
-                const int ba = sci.bitalloc[2*b + ch];
-                if (!ba) continue;
-                if (ba < 17)
-                {
-                    const int half = (1 << (ba - 1)) - 1;
-                    for (int k = 0; k < group_size; k++) v[ch][k] = (float)((int)br.get(ba) - half);
-                } else
-                {
-                    const unsigned mod = (2u << (ba - 17)) + 1;
-                    unsigned code = br.get((int)(mod + 2 - (mod >> 3)));
-                    for (int k = 0; k < group_size; k++, code /= mod) v[ch][k] = (float)((int)(code % mod) - (int)(mod/2));
-                }
-            }
-            if (b >= sci.stereo_bands)
-                for (int k = 0; k < 3; k++) v[1][k] = v[0][k];     /* joint stereo: one set of samples, two scalefactors */
-            const float s0 = sci.scf[3*(2*b) + igr], s1 = sci.scf[3*(2*b + 1) + igr];
-            for (int k = 0; k < 3; k++) { v[0][k] = MP3_FMUL(v[0][k], s0); v[1][k] = MP3_FMUL(v[1][k], s1); }
-        }
-        for (int k = 0; k < group_size; k++)
+            const int half = (1 << (ba - 1)) - 1;
+            for (int k = 0; k < group_size; k++) v[ch][k] = (float)((int)br.get(ba) - half);
+        } else
         {
-            out(0, slot0 + k, b, v[0][k]);
-            out(1, slot0 + k, b, v[1][k]);
+            const unsigned mod = (2u << (ba - 17)) + 1;
+            unsigned code = br.get((int)(mod + 2 - (mod >> 3)));
+            for (int k = 0; k < group_size; k++, code /= mod) v[ch][k] = (float)((int)(code % mod) - (int)(mod/2));
         }
     }
+    if (b >= sci.stereo_bands)
+        for (int k = 0; k < 3; k++) v[1][k] = v[0][k];     /* joint stereo: one set of samples, two scalefactors */
+    const float s0 = sci.scf[3*(2*b) + igr], s1 = sci.scf[3*(2*b + 1) + igr];
+    for (int k = 0; k < 3; k++) { v[0][k] = MP3_FMUL(v[0][k], s0); v[1][k] = MP3_FMUL(v[1][k], s1); }
 }
 
 }  // namespace mp3b

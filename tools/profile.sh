@@ -1,7 +1,7 @@
 #!/bin/bash
 # Run under gpurun on one B200: plain run first (must exit 0), then the ncu launch list and one
 # --set full capture per kernel of the same command.  Outputs land in gpurun_out/.
-#   bash tools/profile.sh [transform|entropy|launches|all] [bench args...]
+#   bash tools/profile.sh [transform|entropy|launches|all|kernel:<name regex>] [bench args...]
 set -u
 mkdir -p gpurun_out
 what=${1:-all}; shift || true
@@ -20,4 +20,9 @@ if [ "$what" = entropy ] || [ "$what" = all ]; then
   ncu --set full --clock-control none --import-source on -k regex:k_l3_entropy -s 3 -c 1 -f -o gpurun_out/prof_entropy $CMD > gpurun_out/ncu_entropy.log 2>&1
   echo "entropy capture rc=$?"
 fi
+case "$what" in kernel:*)
+  k=${what#kernel:}
+  ncu --set full --clock-control none --import-source on -k regex:$k -s 3 -c 1 -f -o gpurun_out/prof_$k $CMD > gpurun_out/ncu_$k.log 2>&1
+  echo "$k capture rc=$?";;
+esac
 ls -la gpurun_out | tail -8
