@@ -837,6 +837,19 @@ int tables_upload(DeviceTables *t)
             for (int e = 0; e < 576; e++) map[r*576 + fwd[r*576 + e]] = (uint16_t)e;
     }
     build_fir(fir);
+    static uint8_t band[3*8*576];
+    for (int kind = 0; kind < 3; kind++)
+        for (int sr = 0; sr < 8; sr++)
+        {
+            const uint8_t *w = kind == 0 ? MP3T_SFB_LONG + sr*23 : kind == 1 ? MP3T_SFB_MIXED + sr*40 : MP3T_SFB_SHORT + sr*40;
+            uint8_t *o = band + (kind*8 + sr)*576;
+            int line = 0, b = 0;
+            for (; w[b] && line < 576; b++)
+                for (int k = 0; k < w[b] && line < 576; k++) o[line++] = (uint8_t)b;
+            for (; line < 576; line++) o[line] = (uint8_t)(b ? b - 1 : 0);
+        }
+    if (cudaMalloc(&t->band_of_line, sizeof(band)) != cudaSuccess) return -1;
+    if (cudaMemcpy(t->band_of_line, band, sizeof(band), cudaMemcpyHostToDevice) != cudaSuccess) return -1;
     if (cudaMalloc(&t->reorder_map, sizeof(map)) != cudaSuccess) return -1;
     if (cudaMalloc(&t->fir_coef, sizeof(fir)) != cudaSuccess) return -1;
     if (cudaMemcpy(t->reorder_map, map, sizeof(map), cudaMemcpyHostToDevice) != cudaSuccess) return -1;
@@ -848,6 +861,8 @@ void tables_free(DeviceTables *t)
 {
     cudaFree(t->reorder_map);
     cudaFree(t->fir_coef);
+    cudaFree(t->band_of_line);
+    t->band_of_line = nullptr;
     t->reorder_map = nullptr;
     t->fir_coef = nullptr;
 }

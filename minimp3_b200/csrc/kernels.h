@@ -15,6 +15,7 @@ struct DeviceTables
 {
     uint16_t *reorder_map;   /* [16][576]: (sr_idx*2 + mixed) -> source line of short-block destination line e */
     float *fir_coef;         /* [32][16]: per output phase j the 16 signed window taps */
+    uint8_t *band_of_line;   /* [3][8][576]: (kind: 0 long, 1 mixed, 2 short; sr_idx) -> scalefactor band of spectral line */
 };
 
 struct EntropyArgs
