@@ -2,7 +2,8 @@
 """Turn an .ncu-rep (one `ncu --set full` capture) into a small markdown summary for profiles/.
 
     python tools/ncu_summary.py gpurun_out/prof_transform.ncu-rep transform > profiles/r01_transform.md
-Also updates profiles/traffic.json[<name>] = dram bytes read + written per launch (GB).
+Also updates profiles/traffic.json[<name>] = dram bytes read + written per launch (GB) for the names bench.py reads
+(transform, entropy, entropy_mips).
 """
 import csv
 import io
@@ -54,7 +55,8 @@ def main(rep, name):
         t = json.load(open(tp)) if os.path.exists(tp) else {}
         t[name] = (rd + wr)/1e9
         t[name + "_note"] = "GB per launch (dram__bytes_read.sum + dram__bytes_write.sum), from %s" % os.path.basename(rep)
-        json.dump(t, open(tp, "w"), indent=1, sort_keys=True)
+        if name in ("transform", "entropy", "entropy_mips"):
+            json.dump(t, open(tp, "w"), indent=1, sort_keys=True)
         print("\nDRAM traffic per launch: %.3f GB read + %.3f GB written = %.3f GB" % (rd/1e9, wr/1e9, (rd + wr)/1e9))
     except Exception as e:
         print("\n(no dram counters: %s)" % e)
