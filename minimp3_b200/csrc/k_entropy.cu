@@ -15,6 +15,7 @@
  * shared memory.  Rows are only written up to the last decoded line (rounded up to 32); nzl[] tells the consumer.
  */
 #include <cuda_runtime.h>
+#include <stddef.h>
 
 #include "kernels.h"
 #define MP3T_QUAL static __device__ const
@@ -50,9 +51,33 @@ extern __shared__ __align__(16) unsigned char g_scratch[];
 }  // namespace
 }  // namespace mp3b
 
+/* the two tables of the decode loop are read with explicit shared-space loads from a 32-bit address: through the
+ * named array the compiler rebuilt the shared window base (S2R SR_CgaCtaId, MOV, LEA) in front of every access --
+ * three times per decoded pair -- rather than spend a register on it */
+namespace mp3b {
+namespace {
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t lds_u16(uint32_t a)
+{
+    unsigned short v;
+    asm("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a));
+    return v;
+}
+struct SharedF32
+{
+    uint32_t base;
+    __device__ __forceinline__ float operator[](int i) const
+    {
+        float v;
+        asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(base + 4u*(uint32_t)i));
+        return v;
+    }
+};
+}  // namespace
+}  // namespace mp3b
 #if defined(__CUDA_ARCH__)
-#define MP3B_ENT_LUT(T, i) (g_tabs.lut[i])
-#define MP3B_ENT_POW43(T) (g_tabs.pow43)
+#define MP3B_ENT_LUT(T, i) (mp3b::lds_u16((T).smem_base + (uint32_t)offsetof(mp3b::SharedTables, lut) + 2u*(uint32_t)(i)))
+#define MP3B_ENT_POW43(T) (mp3b::SharedF32{ (T).smem_base + (uint32_t)offsetof(mp3b::SharedTables, pow43) })
 #define MP3B_ENT_TABINFO(T, i) (g_tabs.tabinfo[i])
 #define MP3B_ENT_SFB(T, kind, row) \
     (g_tabs.sfb + ((kind) == 0 ? (row)*23 : (kind) == 1 ? kSfbMixed + (row)*40 : kSfbShort + (row)*40))
@@ -96,6 +121,9 @@ __global__ void __launch_bounds__(kWarpsPerBlock*32, kBlocksPerSm) k_l3_entropy(
     T.c1info[0] = (uint32_t)kC1Base | (6u << 16);
     T.c1info[1] = (uint32_t)(kC1Base + 64) | (4u << 16);
     T.sfb_long = S.sfb; T.sfb_short = S.sfb + kSfbShort; T.sfb_mixed = S.sfb + kSfbMixed;
+    /* kept in a register: coming out of an asm statement the compiler cannot rebuild it at every use */
+    T.smem_base = smem_u32(&g_tabs);
+    asm volatile("" : "+r"(T.smem_base));
 
     WarpScratch &W = scratch[warp];
     const uint32_t n_groups = (a.n_order + 31)/32;

@@ -38,6 +38,7 @@ struct EntropyTables
     const uint32_t *tabinfo;    /* [32] base | rootw << 16 | linbits << 20 */
     uint32_t c1info[2];         /* count1 table A / B: LUT base | root width << 16 (entries: len << 8 | vwxy) */
     const uint8_t *sfb_long, *sfb_short, *sfb_mixed;
+    uint32_t smem_base;     /* device build: shared-space address of the kernel's table block (k_entropy.cu) */
 };
 
 /* MSB-first bit reader over big-endian bytes, fed by aligned 32-bit loads.  The 64-bit window is kept as two
@@ -104,19 +105,30 @@ struct BitRd
         off = (int)(bit_off & 31);
         base = -off;
     }
-    /* Brings the cursor back into the first word (needs off < 64).  The words only move, nothing is shifted: the
-     * cursor is applied by top() / top2() when bits are looked at, and consuming bits is one addition.  Written
-     * without a branch: in a warp of 32 granules some lane crosses a word at almost every call. */
+    /* Brings the cursor back into the first word (needs off < 64: true wherever it is called -- a step without
+     * escapes moves the cursor by 21 bits at most, one with escapes calls normalize_wide() itself).  The words only
+     * move, nothing is shifted: the cursor is applied by top() / top2() when bits are looked at, and consuming bits
+     * is one addition.  Written without a branch: in a warp of 32 granules some lane crosses a word at almost every
+     * call. */
     MP3_HD void normalize()
+    {
+        const int step = off & 32;              /* off < 64: 32 when the cursor has left the first word, else 0 */
+        const bool adv = step != 0;
+        hi = adv ? lo : hi;
+        lo = adv ? next : lo;
+        next = adv ? be(next2) : next;          /* the byte swap waits here, one word after the load was issued */
+        if (adv) { next2 = raw(wp); wp += 1; }
+        off ^= step;
+        base += step;
+    }
+    /* the same for a cursor anywhere below 96 (takes one word off, may leave the cursor in the second word) */
+    MP3_HD void normalize_wide()
     {
         const bool adv = off >= 32;
         hi = adv ? lo : hi;
         lo = adv ? next : lo;
-        next = adv ? be(next2) : next;          /* the byte swap waits here, one word after the load was issued */
-        if (adv) next2 = raw(wp);
-        wp += adv ? 1 : 0;
-        off -= adv ? 32 : 0;
-        base += adv ? 32 : 0;
+        next = adv ? be(next2) : next;
+        if (adv) { next2 = raw(wp); wp += 1; off -= 32; base += 32; }
     }
     /* the 32 bits at the cursor, and the 32 behind them (cursor < 32) */
     MP3_HD uint32_t top() const { return shl_hi(hi, lo, off); }
@@ -332,6 +344,9 @@ struct GranuleDecoder
         one = 0.f;
         pending = 0; extent = 0;
         c1info = (d.flags0 & GCF_COUNT1_TABLE) ? T.c1info[1] : T.c1info[0];
+#if defined(__CUDA_ARCH__)
+        asm volatile("" : "+r"(c1info));    /* a register, not four instructions per step rebuilding it from the flags */
+#endif
     }
 
     MP3_HD float band_scale(int b) const { return l3_ldexp_q2(gain, (int)iscf[b*iscf_st] << scf_shift); }
@@ -430,7 +445,7 @@ struct GranuleDecoder
             br.skip(c + n1 + s1 + n2 + s2);
             /* only a step with escapes can leave the cursor beyond the second word: take one word off now so that
              * the next call's normalize() finds it below 64 */
-            if (n1 | n2) br.normalize();
+            if (n1 | n2) br.normalize_wide();
             /* a zero value gives one * 0 = +0 and reads no sign */
             v0 = flip_sign(MP3_FMUL(one, l3_pow43(x, MP3B_ENT_POW43(T))), neg_x);
             v1 = flip_sign(MP3_FMUL(one, l3_pow43(y, MP3B_ENT_POW43(T))), neg_y);
