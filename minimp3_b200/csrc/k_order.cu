@@ -5,8 +5,8 @@
  * its longest lane.  The host walker orders every stream's granule-channels by size on its own (build_order in
  * host_parse.cpp).  Here the streams of a window of 32 consecutive streams are merged: inside a window the
  * granule-channels are sorted by (big_values, part_23_length / 8) -- the two side-info fields L3_huffman's loops
- * run on (minimp3.h:742-877; read by L3_read_side_info, minimp3.h:484-607) -- and, among equals, laid out position
- * by position (slot k of every stream of the window next to each other).  Streams that are alike -- same material,
+ * run on (minimp3.h:742-877; read by L3_read_side_info, minimp3.h:484-607) -- and, among equals, by 256-slot stretch
+ * of the stream timeline, stream after stream.  Streams that are alike -- same material,
  * same encoder settings; at best copies of each other, as in BASELINE.json's batch -- then fill whole warps with
  * lanes of equal length (lane efficiency 0.81 -> 0.99 on that batch).  A window of unrelated streams would lose a
  * few per cent against the per-stream order (the two fields predict the line count poorly across sample rates and
@@ -32,11 +32,12 @@ namespace mp3b {
 namespace {
 
 constexpr int kWindowShift = 5;                   /* 32 streams per window */
+constexpr int kSlotBlockShift = 8;                /* 256 slots per block of the slot field */
 
 struct KeyLayout
 {
     int pos_bits;       /* slot index inside the stream ... */
-    int pos_shift;      /* ... without its lowest bits when the key would not fit into 64 (never below ~10^9 slots) */
+    int pos_shift;      /* ... without its lowest kSlotBlockShift bits */
     int total_bits;
 };
 
@@ -82,27 +83,50 @@ __global__ void __launch_bounds__(256) k_order_alike(const GcDesc *__restrict__ 
             }
         }
     }
-    /* the list arrives stream by stream: a warp almost always sits inside one window and adds once */
+    /* the list arrives stream by stream: a block almost always sits inside one window.  Warps of the block's first
+     * window add up in shared memory and the block adds once (one atomic pair per warp on the same 64 words of HBM was
+     * most of this kernel's time); anything else goes to the counters directly */
+    __shared__ uint32_t s_cnt[2], s_win;
+    if (threadIdx.x == 0) { s_cnt[0] = s_cnt[1] = 0; s_win = win; }
+    __syncthreads();
     const uint32_t win0 = __shfl_sync(0xffffffffu, win, 0);
     if (__all_sync(0xffffffffu, win == win0))
     {
         const uint32_t n_same = __popc(__ballot_sync(0xffffffffu, same)), n_counted = __popc(__ballot_sync(0xffffffffu, counted));
         if ((threadIdx.x & 31) == 0 && win0 != 0xFFFFFFFFu && n_counted)
         {
-            atomicAdd(stat + 2*win0, n_same);
-            atomicAdd(stat + 2*win0 + 1, n_counted);
+            if (win0 == s_win)
+            {
+                atomicAdd(&s_cnt[0], n_same);
+                atomicAdd(&s_cnt[1], n_counted);
+            } else
+            {
+                atomicAdd(stat + 2*win0, n_same);
+                atomicAdd(stat + 2*win0 + 1, n_counted);
+            }
         }
     } else if (counted)
     {
         if (same) atomicAdd(stat + 2*win, 1u);
         atomicAdd(stat + 2*win + 1, 1u);
     }
+    __syncthreads();
+    if (threadIdx.x == 0 && s_cnt[1])
+    {
+        atomicAdd(stat + 2*s_win, s_cnt[0]);
+        atomicAdd(stat + 2*s_win + 1, s_cnt[1]);
+    }
 }
 
 /* key, most significant first, of a window whose streams are alike:
- *     window | big_values (9, descending) | part_23_length / 8 (9, descending) | slot | stream inside the window (5)
+ *     window | big_values (9, descending) | part_23_length / 8 (9, descending) | slot / 256
  * and of any other window (the walker's per-stream order):
- *     window | stream inside the window (5) part_23_length / 16 (8) 0 (5) | slot | 0 (5) */
+ *     window | stream inside the window (5) part_23_length / 16 (8) 0 (5) | slot / 256
+ * The sort is stable and the list arrives in (stream, slot) order, so equal keys stay stream by stream, slot by slot:
+ * the lanes of a warp are then granules of equal size from one stretch (256 slots, a second or two of audio, some
+ * tens of KB of bitstream) of one stream, or of neighbouring streams where a stream runs out of them.  With the full
+ * slot and the stream in the key (slot k of all 32 streams side by side) the same batches decoded 5-9 % slower and the
+ * sort needed a fifth pass. */
 __global__ void __launch_bounds__(256) k_order_keys(const GcDesc *__restrict__ gcs, const uint32_t *__restrict__ order_in, uint32_t n,
                                                     const uint32_t *__restrict__ gc_base, uint32_t n_streams, int pos_bits, int pos_shift,
                                                     const uint32_t *__restrict__ stat, int force, unsigned long long *__restrict__ keys)
@@ -124,12 +148,10 @@ __global__ void __launch_bounds__(256) k_order_keys(const GcDesc *__restrict__ g
         k = k << 9 | (511u - big);
         k = k << 9 | (511u - len8);
         k = k << pos_bits | (slot >> pos_shift);
-        k = k << kWindowShift | in_win;
     } else
     {
         k = k << 18 | (in_win << 13 | min((w & 0xffffu) >> 4, 255u) << 5);
         k = k << pos_bits | (slot >> pos_shift);
-        k = k << kWindowShift;
     }
     keys[i] = k;
 }
@@ -144,15 +166,11 @@ int bits_for(uint64_t max_value)
 KeyLayout key_layout(uint32_t n_streams, uint32_t max_slots)
 {
     KeyLayout L;
-    L.pos_bits = bits_for(max_slots ? max_slots - 1 : 0);
-    L.pos_shift = 0;
-    const int fixed_bits = bits_for((n_streams - 1) >> kWindowShift) + 9 + 9 + kWindowShift;
-    if (fixed_bits + L.pos_bits > 64)
-    {
-        L.pos_shift = fixed_bits + L.pos_bits - 64;
-        L.pos_bits -= L.pos_shift;
-    }
-    L.total_bits = fixed_bits + L.pos_bits;
+    const int slot_bits = bits_for(max_slots ? max_slots - 1 : 0);
+    L.pos_shift = slot_bits < kSlotBlockShift ? slot_bits : kSlotBlockShift;
+    L.pos_bits = slot_bits - L.pos_shift;
+    const int fixed_bits = bits_for((n_streams - 1) >> kWindowShift) + 9 + 9;
+    L.total_bits = fixed_bits + L.pos_bits;      /* <= 27 + 18 + 24 */
     return L;
 }
 

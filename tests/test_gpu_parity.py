@@ -292,9 +292,9 @@ def test_mixed_layer_corpus(m, ref):
 
 
 def test_regrouped_lane_order_lists_every_granule_channel_once(m):
-    # capi.cu regroup_lane_order: streams of a window of 32 are merged position by position and sorted by
-    # (big_values, part_23_length / 8); every real granule-channel must still be listed exactly once, and copies of
-    # one stream must end up in whole warps of the same granule-channel
+    # k_order.cu: the streams of a window of 32 are merged and sorted by (big_values, part_23_length / 8), equal keys
+    # by 256-slot stretch of the stream timeline; every real granule-channel must still be listed exactly once, and
+    # copies of one stream must end up in whole warps of granule-channels of one size class
     data = [load_vector("l3-sin1k0db")]*64 + [load_vector("l3-compl"), load_vector("l3-he_mode"), load_vector("l1-fl1")]*3
     plan = m.BatchPlan(data, device=0)
     try:
@@ -310,11 +310,18 @@ def test_regrouped_lane_order_lists_every_granule_channel_once(m):
             n_real[d] = (len(one.read_tap(8)), int(one.stats["n_granule_channels"]))
             one.close()
         assert len(order) == sum(n_real[d][0] for d in data)
-        # first window: 32 copies of one stream -> lanes 32 k .. 32 k + 31 hold slot j of streams 0..31
+        # first window: 32 copies of one stream -> every warp's 32 lanes have the same two size fields, and the window's
+        # part of the list holds every slot of every copy once
         per = n_real[data[0]][1]
         first = order[:32*n_real[data[0]][0]].reshape(-1, 32)
-        assert np.all(first % per == first[:, :1] % per)
-        assert np.all(np.sort(first // per, axis=1) == np.arange(32))
+        assert first.max() < 32*per
+        gcs = plan.read_tap(4)          # GcDesc bytes: part_23_length at 8, big_values at 10
+        p23 = gcs[:, 8].astype(np.int64) | gcs[:, 9].astype(np.int64) << 8
+        big = gcs[:, 10].astype(np.int64) | gcs[:, 11].astype(np.int64) << 8
+        key = big[first]*1024 + (p23[first] >> 3)
+        assert np.all(key == key[:, :1])
+        assert np.all(np.diff(key[:, 0]) <= 0)          # longest first
+        assert np.array_equal(np.sort(first.ravel()), np.sort(np.concatenate([c*per + np.sort(order[order < per]) for c in range(32)])))
     finally:
         plan.close()
 
