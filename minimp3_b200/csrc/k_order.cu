@@ -4,7 +4,7 @@
  * The entropy kernel decodes 32 granule-channels per warp in lock step (one lane each), so a warp takes as long as
  * its longest lane.  The host walker orders every stream's granule-channels by size on its own (build_order in
  * host_parse.cpp).  Here the streams of a window of 32 consecutive streams are merged: inside a window the
- * granule-channels are sorted by (big_values, part_23_length / 8) -- the two side-info fields L3_huffman's loops
+ * granule-channels are sorted by (big_values / 2, part_23_length / 16) -- the two side-info fields L3_huffman's loops
  * run on (minimp3.h:742-877; read by L3_read_side_info, minimp3.h:484-607) -- and, among equals, by 256-slot stretch
  * of the stream timeline, stream after stream.  Streams that are alike -- same material,
  * same encoder settings; at best copies of each other, as in BASELINE.json's batch -- then fill whole warps with
@@ -119,9 +119,9 @@ __global__ void __launch_bounds__(256) k_order_alike(const GcDesc *__restrict__ 
 }
 
 /* key, most significant first, of a window whose streams are alike:
- *     window | big_values (9, descending) | part_23_length / 8 (9, descending) | slot / 256
+ *     window | big_values / 2 (8, descending) | part_23_length / 16 (8, descending) | slot / 256
  * and of any other window (the walker's per-stream order):
- *     window | stream inside the window (5) part_23_length / 16 (8) 0 (5) | slot / 256
+ *     window | stream inside the window (5) part_23_length / 16 (8) 0 (3) | slot / 256
  * The sort is stable and the list arrives in (stream, slot) order, so equal keys stay stream by stream, slot by slot:
  * the lanes of a warp are then granules of equal size from one stretch (256 slots, a second or two of audio, some
  * tens of KB of bitstream) of one stream, or of neighbouring streams where a stream runs out of them.  With the full
@@ -144,13 +144,15 @@ __global__ void __launch_bounds__(256) k_order_keys(const GcDesc *__restrict__ g
     {
         /* longest first: the entropy kernel's warps claim their groups in list order, so the groups claimed last --
          * the tail that decides when the kernel ends -- are the short ones */
-        const uint32_t len8 = min((w & 0xffffu) >> 3, 511u), big = min(w >> 16, 511u);
-        k = k << 9 | (511u - big);
-        k = k << 9 | (511u - len8);
+        /* eight bits each (pairs of big values, 16 bits of main data): with the five window bits of a 1024-stream
+         * batch and three for the slot stretch the key is 24 bits, three passes of the radix sort */
+        const uint32_t len16 = min((w & 0xffffu) >> 4, 255u), big2 = min(w >> 17, 255u);
+        k = k << 8 | (255u - big2);
+        k = k << 8 | (255u - len16);
         k = k << pos_bits | (slot >> pos_shift);
     } else
     {
-        k = k << 18 | (in_win << 13 | min((w & 0xffffu) >> 4, 255u) << 5);
+        k = k << 16 | (in_win << 11 | min((w & 0xffffu) >> 4, 255u) << 3);
         k = k << pos_bits | (slot >> pos_shift);
     }
     keys[i] = k;
@@ -169,8 +171,8 @@ KeyLayout key_layout(uint32_t n_streams, uint32_t max_slots)
     const int slot_bits = bits_for(max_slots ? max_slots - 1 : 0);
     L.pos_shift = slot_bits < kSlotBlockShift ? slot_bits : kSlotBlockShift;
     L.pos_bits = slot_bits - L.pos_shift;
-    const int fixed_bits = bits_for((n_streams - 1) >> kWindowShift) + 9 + 9;
-    L.total_bits = fixed_bits + L.pos_bits;      /* <= 27 + 18 + 24 */
+    const int fixed_bits = bits_for((n_streams - 1) >> kWindowShift) + 8 + 8;
+    L.total_bits = fixed_bits + L.pos_bits;      /* <= 27 + 16 + 24 */
     return L;
 }
 

@@ -292,7 +292,7 @@ def test_mixed_layer_corpus(m, ref):
 
 
 def test_regrouped_lane_order_lists_every_granule_channel_once(m):
-    # k_order.cu: the streams of a window of 32 are merged and sorted by (big_values, part_23_length / 8), equal keys
+    # k_order.cu: the streams of a window of 32 are merged and sorted by (big_values / 2, part_23_length / 16), equal keys
     # by 256-slot stretch of the stream timeline; every real granule-channel must still be listed exactly once, and
     # copies of one stream must end up in whole warps of granule-channels of one size class
     data = [load_vector("l3-sin1k0db")]*64 + [load_vector("l3-compl"), load_vector("l3-he_mode"), load_vector("l1-fl1")]*3
@@ -318,7 +318,7 @@ def test_regrouped_lane_order_lists_every_granule_channel_once(m):
         gcs = plan.read_tap(4)          # GcDesc bytes: part_23_length at 8, big_values at 10
         p23 = gcs[:, 8].astype(np.int64) | gcs[:, 9].astype(np.int64) << 8
         big = gcs[:, 10].astype(np.int64) | gcs[:, 11].astype(np.int64) << 8
-        key = big[first]*1024 + (p23[first] >> 3)
+        key = (big[first] >> 1)*1024 + (p23[first] >> 4)
         assert np.all(key == key[:, :1])
         assert np.all(np.diff(key[:, 0]) <= 0)          # longest first
         assert np.array_equal(np.sort(first.ravel()), np.sort(np.concatenate([c*per + np.sort(order[order < per]) for c in range(32)])))
