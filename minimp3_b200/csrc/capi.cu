@@ -615,7 +615,7 @@ static mp3dec_batch_plan_t *plan_create_impl(const mp3dec_batch_stream_t *stream
     P->stats.n_frames = P->n_frames;
     P->stats.h2d_bytes = P->md_bytes + frs*sizeof(FrameRec) + tiles*sizeof(TileDesc) + ists*4 + orders*4 +
                          l12s*sizeof(L12FrameDesc) + tiles12*sizeof(TileDesc);
-    P->stats.kernels_per_run = (orders ? 1 : 0) + (ists ? 1 : 0) + (tiles ? 2 : 0) + (l12s ? 1 : 0) + (tiles12 ? 1 : 0);
+    P->stats.kernels_per_run = (orders ? 1 : 0) + (ists ? 1 : 0) + (tiles ? 2 : 0) + (l12s ? 2 : 0) + (tiles12 ? 1 : 0);
     P->stats.kernels_prep = (frs ? 1 : 0) + (sort_order ? 2 : 0);    /* own kernels; the radix sort behind them is CUB's */
     P->stats.host_parse_ms = t1 - t0;
     P->stats.h2d_ms = h2d;
