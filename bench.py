@@ -356,7 +356,7 @@ def main():
                                           "into the library's pinned slab, H2D, kernels, D2H", 2*total_samples)
             e2e["d2h_gbs"] = 2*total_samples/(results["e2e"][0]*1e-3)/1e9
             e2e["note"] = ("floor = PCM bytes / device-to-host bandwidth: %.2f GB per step; tools/d2h_ceiling.py (plain cudaMemcpyAsync "
-                           "into pinned memory, all GPUs at once) measured 56 / 70 / 72 / 93 GB/s in aggregate at 1 / 2 / 4 / 8 GPUs "
+                           "into pinned memory, all GPUs at once) measured 56 / 70 / 72 / 91 GB/s in aggregate at 1 / 2 / 4 / 8 GPUs "
                            "on this pool's 8-GPU box" % (2*total_samples/1e9))
             scope_ii = pack("scope_ii", "same call with MP3D_BATCH_OUT_DEVICE (SURVEY 8d scope ii): stream heads on the host, H2D, GPU frame "
                                         "scan + kernels, PCM stays in HBM", 0)
