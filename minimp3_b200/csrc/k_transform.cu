@@ -459,7 +459,8 @@ k_l3_transform(TransformArgs a, const uint16_t *__restrict__ reorder_inv, const 
         const uint2 v = __ldg(reinterpret_cast<const uint2 *>(&rec->slot[warp + kW*lane]));
         ts_mono.gc = (int)v.x; ts_mono.info = v.y;
     }
-    const int n_units = n_slots/nch;
+    const int n_units = n_gr + 2;
+    const int nsh = nch - 1;           /* nch is 1 or 2: slot / nch == slot >> nsh, slot % nch == slot & nsh (no integer division) */
     const int my_unit = nch == 2 ? warp + kW*uj : warp + kW*lane;
     const int my_ch = nch == 2 ? uch : 0;
     const int my_slot = my_unit*nch + my_ch;
@@ -577,7 +578,7 @@ k_l3_transform(TransformArgs a, const uint16_t *__restrict__ reorder_inv, const 
             if (stateful && slot < 2*nch)
             {
                 /* carried state replaces the halo: overlap of the previous call */
-                const int ch = slot%nch;
+                const int ch = slot & nsh;
                 const bool newest = slot >= nch;
 #pragma unroll
                 for (int i = 0; i < 9; i++) t[i*32] = newest ? a.state_in[ch*288 + sb*9 + i] : 0.f;
@@ -631,7 +632,7 @@ k_l3_transform(TransformArgs a, const uint16_t *__restrict__ reorder_inv, const 
         if (slot >= nch)
         {
             const SlotMeta m = S.meta[slot];
-            const int i = slot/nch - 2, ch = slot%nch;
+            const int i = (slot >> nsh) - 2, ch = slot & nsh;
             float prev[9], out[18];
             const float *t = S.t + (slot - nch)*kTSlot + sb;
 #pragma unroll
